@@ -1,0 +1,125 @@
+/* ksched.h — C ABI of the B200 scheduling core (libksched.so).
+ *
+ * Drop-in boundary for the hot path of acrlabs/kube-scheduler-rs-reference.  The reference is a binary
+ * crate with no FFI; the three in-crate functions this library replaces are (paths relative to
+ * /root/reference):
+ *   check_node_validity(&Pod,&Node,&Context) -> Result<(),InvalidNodeReason>   src/predicates.rs:63-77
+ *   select_node_for_pod(&Pod,&Context) -> Option<Node>                         src/main.rs:51-71
+ *   Context{client,node_store} (node cache + per-cell LIST of bound pods)      src/util.rs:12-15,
+ *                                                                              src/predicates.rs:21-38
+ * A Rust host would bind these entry points with an `extern "C"` block (INTEGRATION.md shows it);
+ * signatures use only plain pointers, sizes and opaque handles.  No torch / C++ types cross the ABI.
+ *
+ * Units: cpu = int64 millicores, memory = int64 bytes, labels = W x uint64 bit columns per row
+ * (bit set on a node = node carries that (key,value) pair; bit set on a pod = selector requires it).
+ * Cell semantics (bit-exact with oracle/oracle.c):
+ *   fit   = req_cpu <= free_cpu && req_mem <= free_mem          (src/predicates.rs:42, non-strict)
+ *   match = for all w: (sel[w] & ~labels[w]) == 0               (src/predicates.rs:45-61)
+ *   code  = !fit ? 1 : !match ? 2 : 0                           (src/predicates.rs:68-76, fit first)
+ * All functions return KS_OK (0) or a negative KS_ERR_*; nothing aborts or throws across the ABI
+ * (the reference panics on malformed data, src/predicates.rs:29,31,36).  ks_last_error() returns a
+ * thread-local description of the most recent failure on the calling thread.
+ */
+#ifndef KSCHED_H
+#define KSCHED_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KS_OK 0
+#define KS_ERR_INVALID (-1)
+#define KS_ERR_CUDA (-2)
+#define KS_ERR_PARSE (-3)
+#define KS_ERR_NOMEM (-4)
+#define KS_ERR_RANGE (-5)
+#define KS_ERR_INEXACT (-6)
+#define KS_ERR_MISSING (-7)
+#define KS_ERR_NO_DEVICE (-8)
+
+/* cell codes = Ok(()) / InvalidNodeReason (src/predicates.rs:14-18) */
+#define KS_CELL_OK 0
+#define KS_CELL_NOT_ENOUGH_RESOURCES 1
+#define KS_CELL_NODE_SELECTOR_MISMATCH 2
+
+/* score policies (spec extension — the reference has no score; DESIGN.md "Score") */
+#define KS_SCORE_LEFTOVER 0        /* (free_cpu-req_cpu)*2^22 + (free_mem-req_mem); separable => static node order */
+#define KS_SCORE_LEAST_ALLOCATED 1 /* ((free_cpu-req_cpu)*100/alloc_cpu + (free_mem-req_mem)*100/alloc_mem)/2, floor */
+
+/* where caller-owned buffers live */
+#define KS_MEM_HOST 0
+#define KS_MEM_DEVICE 1
+
+/* ks_select flags */
+#define KS_SELECT_AUTO 0u
+#define KS_SELECT_FORCE_DIRECT 1u  /* per-cell kernel (any policy) */
+#define KS_SELECT_FORCE_BITPAR 2u  /* bit-parallel kernel (KS_SCORE_LEFTOVER only) */
+#define KS_SELECT_TIMING 4u        /* record CUDA events around each kernel; read with ks_last_timings */
+
+/* value limits enforced on inputs so that scores and sums stay inside int64 */
+#define KS_MAX_CPU_MILLI ((int64_t)1 << 36)
+#define KS_MAX_MEM_BYTES ((int64_t)1 << 55)
+#define KS_MAX_LABEL_WORDS 8u
+
+typedef struct ks_snapshot ks_snapshot; /* replaces Context.node_store + the LIST, src/util.rs:12-15 */
+
+typedef struct ks_pods { /* SoA view of P pending pods (what total_pod_resources + node_selector pack to) */
+    uint64_t n;
+    const int64_t* req_cpu;  /* [n] millicores   (src/util.rs:54-75 per pod) */
+    const int64_t* req_mem;  /* [n] bytes */
+    const uint64_t* sel;     /* [n*W] required label bits (all zero = no selector) */
+    int32_t mem_space;       /* KS_MEM_HOST or KS_MEM_DEVICE for the three arrays above */
+} ks_pods;
+
+typedef struct ks_bindings { /* outputs; any pointer may be NULL to skip that output */
+    int32_t* node_idx;       /* [n] argmax-score feasible node, ties -> lowest index, -1 = NoNodeFound */
+    int64_t* score;          /* [n] score of node_idx (0 when -1) */
+    uint32_t* feasible_cnt;  /* [n] number of feasible nodes */
+    int32_t mem_space;       /* space of the three arrays above */
+    uint8_t* mask;           /* [n rows] feasible bit-mask, bit (n%8) of byte n/8 of the row */
+    uint64_t mask_row_bytes; /* row pitch; multiple of 32, >= ks_mask_row_bytes(N) */
+    int32_t mask_space;      /* space of mask (may differ: keep a 6 GB mask in HBM, bindings on host) */
+} ks_bindings;
+
+const char* ks_last_error(void);
+int ks_version(void);
+int ks_device_count(void);           /* number of CUDA devices visible; 0 when none */
+uint64_t ks_launch_count(void);      /* kernels launched by this library since load */
+uint64_t ks_mask_row_bytes(uint32_t n_nodes); /* 32 * ceil(n_nodes/256) */
+
+/* ---- snapshot: device-resident node table (replaces node_store.state(), src/main.rs:56) ---- */
+int ks_snapshot_create(int device, ks_snapshot** out);
+void ks_snapshot_destroy(ks_snapshot* s);
+/* host arrays; labels = [n_nodes*label_words]; resets bound load (free = alloc). */
+int ks_snapshot_set_nodes(ks_snapshot* s, uint32_t n_nodes, uint32_t label_words, const int64_t* alloc_cpu,
+                          const int64_t* alloc_mem, const uint64_t* labels);
+/* K0: free[n] = alloc[n] - sum over bound pods on n (src/predicates.rs:27-38).  host arrays. */
+int ks_snapshot_set_bound(ks_snapshot* s, uint64_t n_bound, const int32_t* node_idx, const int64_t* req_cpu,
+                          const int64_t* req_mem);
+/* incremental: one more pod bound to node_idx (what the next LIST would show after src/main.rs:103) */
+int ks_snapshot_apply_bind(ks_snapshot* s, int32_t node_idx, int64_t req_cpu, int64_t req_mem);
+int ks_snapshot_get_free(ks_snapshot* s, int64_t* free_cpu, int64_t* free_mem); /* D2H, [n_nodes] each */
+uint32_t ks_snapshot_num_nodes(const ks_snapshot* s);
+uint32_t ks_snapshot_label_words(const ks_snapshot* s);
+
+/* ---- per-cell entry = check_node_validity (src/predicates.rs:63-77) ---- */
+int ks_check_cell(ks_snapshot* s, int64_t req_cpu, int64_t req_mem, const uint64_t* sel, uint32_t node_idx);
+/* K1: all P*N reason codes, out_codes[p*N+n] in host memory (small problems / parity tests) */
+int ks_check_cells(ks_snapshot* s, const ks_pods* pods, uint8_t* out_codes);
+
+/* ---- per-pod batched entry = select_node_for_pod over P pods ("predicates::run") ---- */
+int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, ks_bindings* out,
+              void* cuda_stream /* cudaStream_t or NULL = library stream; call returns after completion
+                                   for host-space outputs, after enqueue for all-device outputs */);
+/* milliseconds of the kernels of the last KS_SELECT_TIMING call on this snapshot:
+ * ms[0]=dominant mask/score kernel, ms[1]=argmax scan / combine, ms[2]=total enqueue-to-done. */
+int ks_last_timings(ks_snapshot* s, float ms[3]);
+/* name of the dominant kernel path the last ks_select used: "direct" or "bitpar" */
+const char* ks_last_path(const ks_snapshot* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSCHED_H */

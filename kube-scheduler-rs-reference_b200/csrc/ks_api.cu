@@ -1,0 +1,473 @@
+// ks_api.cu — implementation of the C ABI declared in include/ksched.h (snapshot handle, staging,
+// path selection).  Plain CUDA runtime; no torch, no oracle, no CPU fallback: every entry point that
+// computes returns KS_ERR_NO_DEVICE / KS_ERR_CUDA when no B200 is present.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "ks_bitpar.h"
+#include "ks_internal.cuh"
+#include "ks_launch.h"
+
+using namespace ks;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(KS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                     \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() {
+        return static_cast<T*>(p);
+    }
+};
+
+struct ks_snapshot {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t N = 0, Npad = 0, W = 1;
+    DevBuf alloc_cpu, alloc_mem, free_cpu, free_mem, prio, labels, flag;
+    DevBuf st_rc, st_rm, st_sel, st_idx, st_score, st_cnt, st_mask, st_codes, st_bnode, st_bcpu, st_bmem;
+    DevBuf part_key, part_idx, part_cnt;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timing_valid = false;
+    bool derived_dirty = true; // prio + bit-parallel index must be rebuilt before the next select
+    const char* last_path = "none";
+    BitparIndex bp;
+    std::mutex mu;
+};
+
+static NodeTable node_table(ks_snapshot* s) {
+    NodeTable nt;
+    nt.free_cpu = s->free_cpu.as<int64_t>();
+    nt.free_mem = s->free_mem.as<int64_t>();
+    nt.alloc_cpu = s->alloc_cpu.as<int64_t>();
+    nt.alloc_mem = s->alloc_mem.as<int64_t>();
+    nt.labels = s->labels.as<uint64_t>();
+    nt.N = s->N;
+    nt.Npad = s->Npad;
+    nt.W = s->W;
+    return nt;
+}
+
+extern "C" {
+
+const char* ks_last_error(void) { return g_err; }
+int ks_version(void) { return 100; }
+int ks_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+uint64_t ks_launch_count(void) { return g_launches.load(); }
+uint64_t ks_mask_row_bytes(uint32_t n_nodes) { return 32ull * ((n_nodes + 255ull) / 256ull); }
+
+int ks_snapshot_create(int device, ks_snapshot** out) {
+    if (!out) return fail(KS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = ks_device_count();
+    if (n <= 0) return fail(KS_ERR_NO_DEVICE, "no CUDA device visible: libksched has no CPU fallback");
+    if (device < 0 || device >= n) return fail(KS_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(KS_ERR_NO_DEVICE, "device %d is sm_%d%d; libksched is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    ks_snapshot* s = new (std::nothrow) ks_snapshot();
+    if (!s) return fail(KS_ERR_NOMEM, "out of host memory");
+    s->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = s->flag.ensure(sizeof(int));
+    if (e != cudaSuccess) {
+        ks_snapshot_destroy(s);
+        return fail(KS_ERR_CUDA, "snapshot init failed: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return KS_OK;
+}
+
+void ks_snapshot_destroy(ks_snapshot* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    DevBuf* bufs[] = {&s->alloc_cpu, &s->alloc_mem, &s->free_cpu, &s->free_mem, &s->prio,     &s->labels,
+                      &s->flag,      &s->st_rc,     &s->st_rm,    &s->st_sel,   &s->st_idx,   &s->st_score,
+                      &s->st_cnt,    &s->st_mask,   &s->st_codes, &s->st_bnode, &s->st_bcpu,  &s->st_bmem,
+                      &s->part_key,  &s->part_idx,  &s->part_cnt};
+    for (DevBuf* b : bufs) b->release();
+    bitpar_release(s->bp);
+    for (int i = 0; i < 4; i++)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+uint32_t ks_snapshot_num_nodes(const ks_snapshot* s) { return s ? s->N : 0; }
+uint32_t ks_snapshot_label_words(const ks_snapshot* s) { return s ? s->W : 0; }
+
+int ks_snapshot_set_nodes(ks_snapshot* s, uint32_t n_nodes, uint32_t label_words, const int64_t* alloc_cpu,
+                          const int64_t* alloc_mem, const uint64_t* labels) {
+    if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
+    if (label_words != 1 && label_words != 2 && label_words != 4 && label_words != 8)
+        return fail(KS_ERR_INVALID, "label_words must be 1, 2, 4 or 8 (got %u)", label_words);
+    if (n_nodes && (!alloc_cpu || !alloc_mem || !labels)) return fail(KS_ERR_INVALID, "NULL node array");
+    if (n_nodes > (1u << 30)) return fail(KS_ERR_RANGE, "n_nodes too large");
+    for (uint32_t n = 0; n < n_nodes; n++) {
+        if (alloc_cpu[n] > KS_MAX_CPU_MILLI || alloc_cpu[n] < -KS_MAX_CPU_MILLI || alloc_mem[n] > KS_MAX_MEM_BYTES ||
+            alloc_mem[n] < -KS_MAX_MEM_BYTES)
+            return fail(KS_ERR_RANGE, "node %u allocatable outside +-2^36 millicores / +-2^55 bytes", n);
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    const uint32_t Npad = ((n_nodes + TILE_N - 1) / TILE_N) * TILE_N;
+    s->N = n_nodes;
+    s->Npad = Npad;
+    s->W = label_words;
+    s->derived_dirty = true;
+    if (Npad == 0) return KS_OK;
+    std::vector<int64_t> h(Npad);
+    std::vector<uint64_t> hl((size_t)Npad * label_words, 0);
+    const size_t nb = (size_t)Npad * 8;
+    CU_TRY(s->alloc_cpu.ensure(nb));
+    CU_TRY(s->alloc_mem.ensure(nb));
+    CU_TRY(s->free_cpu.ensure(nb));
+    CU_TRY(s->free_mem.ensure(nb));
+    CU_TRY(s->prio.ensure(nb));
+    CU_TRY(s->labels.ensure(nb * label_words));
+    // allocatable: pad with 0; free: pad with INT64_MIN (never feasible)
+    for (uint32_t n = 0; n < Npad; n++) h[n] = n < n_nodes ? alloc_cpu[n] : 0;
+    CU_TRY(cudaMemcpyAsync(s->alloc_cpu.p, h.data(), nb, cudaMemcpyHostToDevice, s->stream));
+    for (uint32_t n = n_nodes; n < Npad; n++) h[n] = INT64_MIN;
+    CU_TRY(cudaMemcpyAsync(s->free_cpu.p, h.data(), nb, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    for (uint32_t n = 0; n < Npad; n++) h[n] = n < n_nodes ? alloc_mem[n] : 0;
+    CU_TRY(cudaMemcpyAsync(s->alloc_mem.p, h.data(), nb, cudaMemcpyHostToDevice, s->stream));
+    for (uint32_t n = n_nodes; n < Npad; n++) h[n] = INT64_MIN;
+    CU_TRY(cudaMemcpyAsync(s->free_mem.p, h.data(), nb, cudaMemcpyHostToDevice, s->stream));
+    for (uint32_t n = 0; n < n_nodes; n++)
+        for (uint32_t w = 0; w < label_words; w++) hl[(size_t)w * Npad + n] = labels[(size_t)n * label_words + w];
+    CU_TRY(cudaMemcpyAsync(s->labels.p, hl.data(), nb * label_words, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+static int reset_free_to_alloc(ks_snapshot* s) {
+    // free[0..N) = alloc[0..N); the padding keeps its INT64_MIN sentinels
+    CU_TRY(cudaMemcpyAsync(s->free_cpu.p, s->alloc_cpu.p, (size_t)s->N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU_TRY(cudaMemcpyAsync(s->free_mem.p, s->alloc_mem.p, (size_t)s->N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    return KS_OK;
+}
+
+int ks_snapshot_set_bound(ks_snapshot* s, uint64_t n_bound, const int32_t* node_idx, const int64_t* req_cpu,
+                          const int64_t* req_mem) {
+    if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
+    if (n_bound && (!node_idx || !req_cpu || !req_mem)) return fail(KS_ERR_INVALID, "NULL bound array");
+    for (uint64_t b = 0; b < n_bound; b++) {
+        if (node_idx[b] < 0 || (uint32_t)node_idx[b] >= s->N)
+            return fail(KS_ERR_INVALID, "bound pod %llu: node index %d out of range", (unsigned long long)b,
+                        node_idx[b]);
+        if (req_cpu[b] > KS_MAX_CPU_MILLI || req_cpu[b] < -KS_MAX_CPU_MILLI || req_mem[b] > KS_MAX_MEM_BYTES ||
+            req_mem[b] < -KS_MAX_MEM_BYTES)
+            return fail(KS_ERR_RANGE, "bound pod %llu request out of range", (unsigned long long)b);
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    s->derived_dirty = true;
+    if (s->N == 0) return KS_OK;
+    int rc = reset_free_to_alloc(s);
+    if (rc) return rc;
+    if (n_bound) {
+        CU_TRY(s->st_bnode.ensure(n_bound * 4));
+        CU_TRY(s->st_bcpu.ensure(n_bound * 8));
+        CU_TRY(s->st_bmem.ensure(n_bound * 8));
+        CU_TRY(cudaMemcpyAsync(s->st_bnode.p, node_idx, n_bound * 4, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(cudaMemcpyAsync(s->st_bcpu.p, req_cpu, n_bound * 8, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(cudaMemcpyAsync(s->st_bmem.p, req_mem, n_bound * 8, cudaMemcpyHostToDevice, s->stream));
+        CU_TRY(launch_free_reduce(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->st_bnode.as<int32_t>(),
+                                  s->st_bcpu.as<int64_t>(), s->st_bmem.as<int64_t>(), n_bound, s->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+int ks_snapshot_apply_bind(ks_snapshot* s, int32_t node_idx, int64_t req_cpu, int64_t req_mem) {
+    if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
+    if (node_idx < 0 || (uint32_t)node_idx >= s->N) return fail(KS_ERR_INVALID, "node index %d out of range", node_idx);
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    s->derived_dirty = true;
+    CU_TRY(s->st_bnode.ensure(4));
+    CU_TRY(s->st_bcpu.ensure(8));
+    CU_TRY(s->st_bmem.ensure(8));
+    CU_TRY(cudaMemcpyAsync(s->st_bnode.p, &node_idx, 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(cudaMemcpyAsync(s->st_bcpu.p, &req_cpu, 8, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(cudaMemcpyAsync(s->st_bmem.p, &req_mem, 8, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(launch_free_reduce(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->st_bnode.as<int32_t>(),
+                              s->st_bcpu.as<int64_t>(), s->st_bmem.as<int64_t>(), 1, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+int ks_snapshot_get_free(ks_snapshot* s, int64_t* free_cpu, int64_t* free_mem) {
+    if (!s || !free_cpu || !free_mem) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    if (s->N == 0) return KS_OK;
+    CU_TRY(cudaMemcpyAsync(free_cpu, s->free_cpu.p, (size_t)s->N * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaMemcpyAsync(free_mem, s->free_mem.p, (size_t)s->N * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+// rebuild what depends on free[]: range check, static priorities, bit-parallel index
+static int refresh_derived(ks_snapshot* s, cudaStream_t st) {
+    if (!s->derived_dirty || s->N == 0) return KS_OK;
+    CU_TRY(cudaMemsetAsync(s->flag.p, 0, sizeof(int), st));
+    CU_TRY(launch_node_prio(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->prio.as<int64_t>(), s->N, s->Npad,
+                            s->flag.as<int>(), st));
+    int flag = 0;
+    CU_TRY(cudaMemcpyAsync(&flag, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (flag) return fail(KS_ERR_RANGE, "free resources of some node exceed +-2^36 millicores / +-2^55 bytes");
+    cudaError_t e = bitpar_build(s->bp, node_table(s), s->prio.as<int64_t>(), st);
+    if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel index build failed: %s", cudaGetErrorString(e));
+    s->derived_dirty = false;
+    return KS_OK;
+}
+
+static int stage_pods(ks_snapshot* s, const ks_pods* pods, cudaStream_t st, PodView* pv) {
+    const uint64_t P = pods->n;
+    pv->P = (uint32_t)P;
+    if (pods->mem_space == KS_MEM_DEVICE) {
+        pv->req_cpu = pods->req_cpu;
+        pv->req_mem = pods->req_mem;
+        pv->sel = pods->sel;
+        return KS_OK;
+    }
+    CU_TRY(s->st_rc.ensure(P * 8));
+    CU_TRY(s->st_rm.ensure(P * 8));
+    CU_TRY(s->st_sel.ensure(P * 8 * s->W));
+    CU_TRY(cudaMemcpyAsync(s->st_rc.p, pods->req_cpu, P * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(s->st_rm.p, pods->req_mem, P * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(s->st_sel.p, pods->sel, P * 8 * s->W, cudaMemcpyHostToDevice, st));
+    pv->req_cpu = s->st_rc.as<int64_t>();
+    pv->req_mem = s->st_rm.as<int64_t>();
+    pv->sel = s->st_sel.as<uint64_t>();
+    return KS_OK;
+}
+
+static int check_pods(const ks_snapshot* s, const ks_pods* pods) {
+    if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
+    if (!pods) return fail(KS_ERR_INVALID, "pods is NULL");
+    if (pods->n > 0xfffffff0ull) return fail(KS_ERR_RANGE, "too many pods in one call");
+    if (pods->n && (!pods->req_cpu || !pods->req_mem || !pods->sel)) return fail(KS_ERR_INVALID, "NULL pod array");
+    if (pods->mem_space != KS_MEM_HOST && pods->mem_space != KS_MEM_DEVICE)
+        return fail(KS_ERR_INVALID, "bad pods.mem_space");
+    return KS_OK;
+}
+
+int ks_check_cells(ks_snapshot* s, const ks_pods* pods, uint8_t* out_codes) {
+    int rc = check_pods(s, pods);
+    if (rc) return rc;
+    if (!out_codes) return fail(KS_ERR_INVALID, "out_codes is NULL");
+    const uint64_t cells = pods->n * (uint64_t)s->N;
+    if (cells == 0) return KS_OK;
+    if (cells > (1ull << 31)) return fail(KS_ERR_RANGE, "ks_check_cells is for <= 2^31 cells");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    PodView pv;
+    rc = stage_pods(s, pods, s->stream, &pv);
+    if (rc) return rc;
+    CU_TRY(s->st_codes.ensure(cells));
+    CU_TRY(launch_check_cells(node_table(s), pv, s->st_codes.as<uint8_t>(), 0, s->N, s->stream));
+    CU_TRY(cudaMemcpyAsync(out_codes, s->st_codes.p, cells, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+int ks_check_cell(ks_snapshot* s, int64_t req_cpu, int64_t req_mem, const uint64_t* sel, uint32_t node_idx) {
+    if (!s || !sel) return fail(KS_ERR_INVALID, "NULL argument");
+    if (node_idx >= s->N) return fail(KS_ERR_INVALID, "node index %u out of range", node_idx);
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    ks_pods pods;
+    pods.n = 1;
+    pods.req_cpu = &req_cpu;
+    pods.req_mem = &req_mem;
+    pods.sel = sel;
+    pods.mem_space = KS_MEM_HOST;
+    PodView pv;
+    int rc = stage_pods(s, &pods, s->stream, &pv);
+    if (rc) return rc;
+    CU_TRY(s->st_codes.ensure(16));
+    CU_TRY(launch_check_cells(node_table(s), pv, s->st_codes.as<uint8_t>(), node_idx, 1, s->stream));
+    uint8_t code = 0xff;
+    CU_TRY(cudaMemcpyAsync(&code, s->st_codes.p, 1, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return (int)code;
+}
+
+int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, ks_bindings* out, void* cuda_stream) {
+    int rc = check_pods(s, pods);
+    if (rc) return rc;
+    if (!out) return fail(KS_ERR_INVALID, "out is NULL");
+    if (policy != KS_SCORE_LEFTOVER && policy != KS_SCORE_LEAST_ALLOCATED) return fail(KS_ERR_INVALID, "bad policy");
+    if ((flags & KS_SELECT_FORCE_BITPAR) && policy != KS_SCORE_LEFTOVER)
+        return fail(KS_ERR_INVALID, "the bit-parallel path implements KS_SCORE_LEFTOVER only");
+    if ((flags & KS_SELECT_FORCE_BITPAR) && (flags & KS_SELECT_FORCE_DIRECT)) return fail(KS_ERR_INVALID, "bad flags");
+    const uint64_t P = pods->n;
+    if (out->mask) {
+        if (out->mask_row_bytes % 32 != 0 || out->mask_row_bytes < ks_mask_row_bytes(s->N))
+            return fail(KS_ERR_INVALID, "mask_row_bytes must be a multiple of 32 and >= %llu",
+                        (unsigned long long)ks_mask_row_bytes(s->N));
+    }
+    if (P == 0) return KS_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    const bool timing = (flags & KS_SELECT_TIMING) != 0;
+    s->timing_valid = false;
+    if (timing) CU_TRY(cudaEventRecord(s->ev[0], st));
+
+    rc = refresh_derived(s, st);
+    if (rc) return rc;
+
+    const bool out_host = out->mem_space == KS_MEM_HOST;
+    const bool mask_host = out->mask && out->mask_space == KS_MEM_HOST;
+    OutView ov;
+    ov.node_idx = out->node_idx;
+    ov.score = out->score;
+    ov.cnt = out->feasible_cnt;
+    ov.mask = reinterpret_cast<uint32_t*>(out->mask);
+    ov.mask_row_words = out->mask_row_bytes / 4;
+    ov.mask_valid_words = (uint32_t)(ks_mask_row_bytes(s->N) / 4);
+    if (out_host) {
+        if (out->node_idx) {
+            CU_TRY(s->st_idx.ensure(P * 4));
+            ov.node_idx = s->st_idx.as<int32_t>();
+        }
+        if (out->score) {
+            CU_TRY(s->st_score.ensure(P * 8));
+            ov.score = s->st_score.as<int64_t>();
+        }
+        if (out->feasible_cnt) {
+            CU_TRY(s->st_cnt.ensure(P * 4));
+            ov.cnt = s->st_cnt.as<uint32_t>();
+        }
+    }
+    if (mask_host) {
+        CU_TRY(s->st_mask.ensure(P * out->mask_row_bytes));
+        ov.mask = s->st_mask.as<uint32_t>();
+    }
+
+    if (s->N == 0) { // empty node store: every pod gets None (src/main.rs:56,70)
+        if (ov.node_idx) CU_TRY(cudaMemsetAsync(ov.node_idx, 0xff, P * 4, st));
+        if (ov.score) CU_TRY(cudaMemsetAsync(ov.score, 0, P * 8, st));
+        if (ov.cnt) CU_TRY(cudaMemsetAsync(ov.cnt, 0, P * 4, st));
+        s->last_path = "empty";
+    } else {
+        SelectLaunch L;
+        L.nt = node_table(s);
+        rc = stage_pods(s, pods, st, &L.pv);
+        if (rc) return rc;
+        L.ov = ov;
+        L.policy = policy;
+        L.stream = st;
+        bool use_bitpar = false;
+        if (flags & KS_SELECT_FORCE_BITPAR) use_bitpar = true;
+        else if (!(flags & KS_SELECT_FORCE_DIRECT))
+            use_bitpar = policy == KS_SCORE_LEFTOVER && bitpar_profitable(s->bp, L.pv.P);
+        if (timing) CU_TRY(cudaEventRecord(s->ev[1], st));
+        if (use_bitpar) {
+            cudaError_t e = bitpar_select(s->bp, L, s->prio.as<int64_t>(), timing ? s->ev[2] : nullptr);
+            if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
+            s->last_path = "bitpar";
+        } else {
+            const uint32_t n_tiles = s->Npad / TILE_N;
+            const uint32_t pod_ctas = (L.pv.P + direct_pods_per_cta(s->W) - 1) / direct_pods_per_cta(s->W);
+            uint32_t n_chunks = 1;
+            if (pod_ctas < 2 * 148) n_chunks = std::min<uint32_t>(n_tiles, (2 * 148 + pod_ctas - 1) / pod_ctas);
+            const uint32_t tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+            n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+            PartialView part{nullptr, nullptr, nullptr};
+            if (n_chunks > 1) {
+                CU_TRY(s->part_key.ensure((size_t)n_chunks * P * 8));
+                CU_TRY(s->part_idx.ensure((size_t)n_chunks * P * 4));
+                CU_TRY(s->part_cnt.ensure((size_t)n_chunks * P * 4));
+                part.key = s->part_key.as<int64_t>();
+                part.idx = s->part_idx.as<int32_t>();
+                part.cnt = s->part_cnt.as<uint32_t>();
+            }
+            cudaError_t e = launch_select_direct(L, part, n_chunks, tiles_per_chunk);
+            if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct select failed: %s", cudaGetErrorString(e));
+            if (timing) CU_TRY(cudaEventRecord(s->ev[2], st));
+            s->last_path = "direct";
+        }
+    }
+    if (out_host) {
+        if (out->node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
+        if (out->score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
+        if (out->feasible_cnt) CU_TRY(cudaMemcpyAsync(out->feasible_cnt, ov.cnt, P * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (mask_host)
+        CU_TRY(cudaMemcpyAsync(out->mask, ov.mask, P * out->mask_row_bytes, cudaMemcpyDeviceToHost, st));
+    if (timing) {
+        CU_TRY(cudaEventRecord(s->ev[3], st));
+        s->timing_valid = s->N != 0;
+    }
+    if (out_host || mask_host || pods->mem_space == KS_MEM_HOST || timing) CU_TRY(cudaStreamSynchronize(st));
+    return KS_OK;
+}
+
+int ks_last_timings(ks_snapshot* s, float ms[3]) {
+    if (!s || !ms) return fail(KS_ERR_INVALID, "NULL argument");
+    if (!s->timing_valid) return fail(KS_ERR_INVALID, "no KS_SELECT_TIMING call recorded");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaEventSynchronize(s->ev[3]));
+    CU_TRY(cudaEventElapsedTime(&ms[0], s->ev[1], s->ev[2]));
+    CU_TRY(cudaEventElapsedTime(&ms[1], s->ev[2], s->ev[3]));
+    CU_TRY(cudaEventElapsedTime(&ms[2], s->ev[0], s->ev[3]));
+    return KS_OK;
+}
+
+const char* ks_last_path(const ks_snapshot* s) { return s ? s->last_path : "none"; }
+
+} // extern "C"

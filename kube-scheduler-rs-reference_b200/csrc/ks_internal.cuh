@@ -1,0 +1,105 @@
+// ks_internal.cuh — shared device-side views, PTX helpers and launch plumbing (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/ksched.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libksched is written for sm_100a (B200) only"
+#endif
+
+namespace ks {
+
+constexpr int TILE_N = 1024;        // nodes per shared-memory tile of the direct kernel
+constexpr int DIRECT_THREADS = 256; // 8 warps
+
+// Device-resident node table (SoA, padded to a multiple of TILE_N with never-feasible sentinels:
+// free = INT64_MIN, labels = 0).  labels are word-major: labels[w*Npad + n].
+struct NodeTable {
+    const int64_t* free_cpu;
+    const int64_t* free_mem;
+    const int64_t* alloc_cpu;
+    const int64_t* alloc_mem;
+    const uint64_t* labels;
+    uint32_t N, Npad, W;
+};
+
+struct PodView {
+    const int64_t* req_cpu;
+    const int64_t* req_mem;
+    const uint64_t* sel; // row-major [P*W]
+    uint32_t P;
+};
+
+struct OutView {
+    int32_t* node_idx;
+    int64_t* score;
+    uint32_t* cnt;
+    uint32_t* mask;          // may be nullptr
+    uint64_t mask_row_words; // row pitch in 32-bit words
+    uint32_t mask_valid_words; // words per row that may be written: 8*ceil(N/256)
+};
+
+// Per-(chunk,pod) partial results when the node dimension is split across CTAs (small P).
+struct PartialView {
+    int64_t* key;  // best policy key (LEFTOVER: node priority; LEAST_ALLOCATED: score)
+    int32_t* idx;
+    uint32_t* cnt;
+};
+
+extern std::atomic<uint64_t> g_launches;
+
+// ---- PTX helpers: mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes multiple of 16, 16B-aligned)
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- launch-side plumbing shared by the API and the kernel files ----
+struct SelectLaunch {
+    NodeTable nt;
+    PodView pv;
+    OutView ov;
+    int policy;
+    cudaStream_t stream;
+};
+
+} // namespace ks

@@ -1,0 +1,17 @@
+// ks_launch.h — host-callable launchers implemented in ks_direct.cu / ks_bitpar.cu
+#pragma once
+#include "ks_internal.cuh"
+
+namespace ks {
+
+cudaError_t launch_free_reduce(int64_t* free_cpu, int64_t* free_mem, const int32_t* bnode, const int64_t* bcpu,
+                               const int64_t* bmem, uint64_t B, cudaStream_t st);
+cudaError_t launch_node_prio(const int64_t* free_cpu, const int64_t* free_mem, int64_t* prio, uint32_t N,
+                             uint32_t Npad, int* range_flag, cudaStream_t st);
+cudaError_t launch_check_cells(const NodeTable& nt, const PodView& pv, uint8_t* codes, uint32_t node_begin,
+                               uint32_t node_count, cudaStream_t st);
+uint32_t direct_pods_per_cta(uint32_t W);
+cudaError_t launch_select_direct(const SelectLaunch& L, const PartialView& part, uint32_t n_chunks,
+                                 uint32_t tiles_per_chunk);
+
+} // namespace ks

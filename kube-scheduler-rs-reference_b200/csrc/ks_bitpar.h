@@ -1,16 +1,50 @@
-// ks_bitpar.h — bit-parallel fast path (ks_bitpar.cu): per-tile threshold tables + label-pair columns
-// turn 32 cells into one LOP3; argmax = first feasible node in static priority order.
+// ks_bitpar.h — bit-parallel fast path (ks_bitpar.cu).
+//
+// Idea: `req <= free` depends only on ORDER.  Nodes are ranked once per snapshot (global position of each
+// node in ascending free_cpu / free_mem order); a pod's request becomes a global rank threshold (binary
+// search once per pod).  For a tile of 256 nodes the feasible bits of one resource are then a row of a
+// prefix table indexed by the tile-local rank of the threshold, and the tile-local rank is
+//   base[bucket][tile] + popc(member[bucket][tile] & lowmask)
+// (bucket = 64 consecutive global positions).  Label selectors are ANDs of per-(key,value) node columns.
+// One thread produces 256 cells (8 mask words) with ~50 instructions; the kernel is bound by the HBM
+// write of the mask.  KS_SCORE_LEFTOVER is separable (node part - pod part), so argmax-score is the first
+// feasible node in a static priority order: a short early-exit scan per pod (k_first_fit).
 #pragma once
 #include "ks_internal.cuh"
 
 namespace ks {
 
+constexpr int BP_TILE = 256;          // nodes per tile = 8 mask words = one 32-byte row
+constexpr int BP_ROWS = BP_TILE + 1;  // prefix-table rows per tile and resource (local rank 0..256)
+constexpr int BP_TABLE_BYTES = BP_ROWS * 32;
+constexpr int BP_THREADS = 1024;
+constexpr int BP_POD_CHUNK = 1024;    // pods per shared-memory count chunk
+constexpr int BP_SMEM_MAX = 232448;   // 227 KB opt-in limit per CTA
+
+struct BitparLayout { // byte offsets inside one column-block blob
+    uint32_t nt;       // tiles per column block
+    uint32_t nb;       // buckets of 64 global positions: (N >> 6) + 1
+    uint32_t ncb;      // column blocks
+    uint32_t off_baseC, off_membC, off_baseM, off_membM, off_tabC, off_tabM, off_pairs;
+    uint32_t blob_bytes;
+};
+
 struct BitparIndex {
-    void* blob = nullptr;      // per-tile index blobs, contiguous (see ks_bitpar.cu for the layout)
-    size_t blob_cap = 0;
-    void* order = nullptr;     // nodes in descending priority order: SoA {free_cpu, free_mem, labels[W], node_idx}
-    size_t order_cap = 0;
-    uint32_t N = 0, Npad = 0, W = 0, n_tiles = 0;
+    // per-snapshot index (device)
+    int64_t* sortedC = nullptr;  // [N] free_cpu ascending
+    int64_t* sortedM = nullptr;  // [N] free_mem ascending
+    uint32_t* gposC = nullptr;   // [N] position of node n in sortedC (ties by node index)
+    uint32_t* gposM = nullptr;
+    int64_t* ord_fc = nullptr;   // nodes in descending priority order (ties by node index), padded to 32
+    int64_t* ord_fm = nullptr;
+    int64_t* ord_prio = nullptr;
+    uint64_t* ord_lab = nullptr; // word-major [W][Nord]
+    int32_t* ord_idx = nullptr;
+    uint8_t* blob = nullptr;     // ncb blobs of blob_bytes
+    uint2* pod_ranks = nullptr;  // per-call scratch [P]
+    size_t cap_nodes = 0, cap_blob = 0, cap_pods = 0, cap_lab = 0;
+    uint32_t N = 0, Nord = 0, W = 0;
+    BitparLayout lay{};
     bool valid = false;
 };
 

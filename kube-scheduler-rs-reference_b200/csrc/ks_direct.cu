@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS)
 #pragma unroll
             for (int w = 0; w < W; w++) lab[w] = s_lab[w * TILE_N + ln];
             const int32_t node = (int32_t)(tile * TILE_N + ln);
+            const bool real = (uint32_t)node < nt.N; // padding sentinels are never feasible
             int64_t key_n = 0, ac = 0, am = 0;
             if (POLICY == KS_SCORE_LEFTOVER) {
                 key_n = (int64_t)(((uint64_t)fc << 22) + (uint64_t)fm); // node priority; pod part is constant
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS)
                 uint64_t miss = 0;
 #pragma unroll
                 for (int w = 0; w < W; w++) miss |= sel[i][w] & ~lab[w];
-                const bool ok = fit && (miss == 0);
+                const bool ok = fit && (miss == 0) && real;
                 const uint32_t b = __ballot_sync(0xffffffffu, ok);
                 cnt[i] += __popc(b);
                 if (EMIT_MASK) acc[i] = (lane == g) ? b : acc[i];

@@ -1,0 +1,265 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI vs the CPU oracle, bit-exact
+(integer / bit work: no tolerance).  Small sizes compare everything; BASELINE.json's full sizes use a full
+packed-oracle comparison where the CPU finishes in seconds (C2) and size-independent properties + sampled
+rows beyond that (C3)."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, mask_bits, pack_by_dictionary, rows_to_str
+
+pytestmark = pytest.mark.gpu
+
+import os
+
+_ALL_PATHS = {"direct": 1, "bitpar": 2}  # KS_SELECT_FORCE_DIRECT / KS_SELECT_FORCE_BITPAR
+PATHS = {k: v for k, v in _ALL_PATHS.items() if k in os.environ.get("KS_TEST_PATHS", "direct,bitpar").split(",")}
+
+
+def _oracle(orc, cl, policy, want_codes=False):
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    return orc.run_packed(fc, fm, ac, am, lab, rc, rm, sel, policy=policy, want_codes=want_codes)
+
+
+def _snapshot(ks, cl):
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    snap = ks.Snapshot(0)
+    snap.set_nodes(ac, am, lab)
+    snap.set_bound(bn, bc, bm)
+    return snap, (rc, rm, sel)
+
+
+def _assert_same(r, o, tag):
+    oidx, oscore, ocnt, omask, _ = o
+    assert np.array_equal(r.feasible_cnt, ocnt), f"{tag}: feasible_cnt"
+    assert np.array_equal(r.mask, omask), f"{tag}: mask"
+    assert np.array_equal(r.node_idx, oidx), f"{tag}: node_idx"
+    assert np.array_equal(r.score, oscore), f"{tag}: score"
+
+
+def test_gv1_config_c1_through_abi(ks, orc):
+    """BASELINE.json configs[0]: 10 pods x 5 nodes, resource_fits only — golden vector GV-1."""
+    g = load_golden("gv1.json")
+    names = [n["name"] for n in g["nodes"]]
+    alloc = [(4000, 8589934592), (2000, 4294967296), (8000, 17179869184), (1000, 1073741824), (0, 0)]
+    bound = [(1, 500, 1073741824), (2, 2000, 4294967296), (2, 500, 536870912), (3, 1000, 1073741824), (4, 100, 1)]
+    labels, sel = pack_by_dictionary([n["labels"] for n in g["nodes"]], [None] * 10)
+    assert names == ["n0", "n1", "n2", "n3", "n4"]
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes([a[0] for a in alloc], [a[1] for a in alloc], labels)
+        snap.set_bound([b[0] for b in bound], [b[1] for b in bound], [b[2] for b in bound])
+        fc, fm = snap.free()
+        assert list(fc) == g["expected_free_cpu_milli"] and list(fm) == g["expected_free_mem_bytes"]
+        rc, rm = g["expected_req_cpu_milli"], g["expected_req_mem_bytes"]
+        codes = snap.check_cells(rc, rm, sel)
+        assert rows_to_str(codes == 0) == g["expected_feasible_rows"]
+        assert set(np.unique(codes)) <= {0, 1}
+        for name, flag in PATHS.items():
+            r = snap.select(rc, rm, sel, flags=flag, want_mask=True)
+            assert rows_to_str(mask_bits(r.mask, 5)) == g["expected_feasible_rows"], name
+            assert list(r.node_idx) == g["expected_node_idx_leftover"], name
+            assert list(r.feasible_cnt) == [s.count("1") for s in g["expected_feasible_rows"]], name
+        for p in range(10):
+            for n in range(5):
+                assert snap.check_cell(rc[p], rm[p], sel[p], n) == codes[p, n]
+
+
+def test_gv1_objects_vs_faithful_oracle(ks, orc):
+    """Same GV-1 objects through the faithful (string-parsing) oracle and through the GPU reason codes."""
+    g = load_golden("gv1.json")
+    arena = ks.objects.ObjectArena()
+    nodes, allp, pods = arena.nodes(g["nodes"]), arena.pods(g["bound_pods"]), arena.pods(g["pods"])
+    oc = orc.Cluster(nodes, 5, allp, len(g["bound_pods"]))
+    _, _, _, _, ocodes = oc.run(pods, 10, want_codes=True)
+    labels, sel = pack_by_dictionary([n["labels"] for n in g["nodes"]], [None] * 10)
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes([4000, 2000, 8000, 1000, 0], [8589934592, 4294967296, 17179869184, 1073741824, 0], labels)
+        snap.set_bound([1, 2, 2, 3, 4], [500, 2000, 500, 1000, 100], [1073741824, 4294967296, 536870912, 1073741824, 1])
+        codes = snap.check_cells(g["expected_req_cpu_milli"], g["expected_req_mem_bytes"], sel)
+    assert np.array_equal(codes, ocodes)
+
+
+SHAPES = [
+    (1, 1, 8), (5, 31, 8), (33, 32, 8), (100, 1024, 8), (257, 1025, 8), (1000, 3000, 8), (300, 2049, 16),
+    (64, 2500, 32), (40, 1300, 64), (2000, 256, 8), (3, 20000, 8),
+]
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("P,N,keys", SHAPES)
+def test_random_clusters_leftover(ks, orc, path, P, N, keys):
+    cl = ks.synth.make(P, N, seed=1000 + P + N, n_keys=keys, bound_per_node=4)
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    with snap:
+        fc, fm = snap.free()
+        cfc, cfm = cl.free()
+        assert np.array_equal(fc, cfc) and np.array_equal(fm, cfm)  # K0 vs numpy
+        r = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEFTOVER, flags=PATHS[path], want_mask=True)
+        assert r.path == path
+        _assert_same(r, _oracle(orc, cl, 0), f"{path} {P}x{N} W={cl.label_words}")
+
+
+@pytest.mark.parametrize("P,N,keys", [(5, 31, 8), (257, 1025, 8), (500, 3000, 8), (64, 2500, 32), (3, 20000, 8)])
+def test_random_clusters_least_allocated(ks, orc, P, N, keys):
+    cl = ks.synth.make(P, N, seed=2000 + P + N, n_keys=keys, bound_per_node=4)
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    with snap:
+        r = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, want_mask=True)
+        assert r.path == "direct"
+        _assert_same(r, _oracle(orc, cl, 1), f"least-allocated {P}x{N}")
+        assert r.score.min() >= 0 and r.score.max() <= 100
+
+
+def test_reason_codes_match_oracle(ks, orc):
+    cl = ks.synth.make(200, 777, seed=31, bound_per_node=4)
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    with snap:
+        codes = snap.check_cells(rc, rm, sel)
+    ocodes = _oracle(orc, cl, 0, want_codes=True)[4]
+    assert np.array_equal(codes, ocodes)
+    assert set(np.unique(codes)) == {0, 1, 2}
+
+
+def test_objects_faithful_oracle_vs_gpu(ks, orc):
+    """End-to-end object parity: strings -> faithful oracle (per-cell parse + bound re-sum) vs GPU on packed."""
+    cl = ks.synth.make(48, 300, seed=77, bound_per_node=3)
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    nodes, bound, pods = arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+    oc = orc.Cluster(nodes, cl.N, bound, cl.B)
+    f = oc.run(pods, cl.P, policy=0)
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    with snap:
+        for name, flag in PATHS.items():
+            r = snap.select(rc, rm, sel, flags=flag, want_mask=True)
+            _assert_same(r, f, f"objects {name}")
+
+
+def test_edge_cases(ks, orc):
+    one = np.ones((1, 1), np.uint64)
+    with ks.Snapshot(0) as snap:
+        # empty node store: every pod gets None (src/main.rs:56,70)
+        snap.set_nodes(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros((0, 1), np.uint64))
+        r = snap.select([1, 2], [1, 2], np.zeros((2, 1), np.uint64))
+        assert list(r.node_idx) == [-1, -1] and list(r.feasible_cnt) == [0, 0] and list(r.score) == [0, 0]
+        # zero-request pod fits iff free >= 0 in both (node with negative free is infeasible)
+        snap.set_nodes([1000, 1000], [100, 100], np.zeros((2, 1), np.uint64))
+        snap.set_bound([1], [1001], [0])
+        for flag in PATHS.values():
+            r = snap.select([0, 1000, 1001], [0, 100, 0], np.zeros((3, 1), np.uint64), flags=flag, want_mask=True)
+            assert list(r.feasible_cnt) == [1, 1, 0] and list(r.node_idx) == [0, 0, -1]
+            assert list(r.score) == [1000 * (1 << 22) + 100, 0, 0]
+        # selector bit no node carries -> NodeSelectorMismatch everywhere; fit still reported first
+        assert snap.check_cell(0, 0, one[0], 0) == ks.KS_CELL_NODE_SELECTOR_MISMATCH
+        assert snap.check_cell(5000, 0, one[0], 0) == ks.KS_CELL_NOT_ENOUGH_RESOURCES
+        # ties -> lowest node index
+        snap.set_nodes([500] * 40, [64] * 40, np.zeros((40, 1), np.uint64))
+        for flag in PATHS.values():
+            r = snap.select([100], [1], np.zeros((1, 1), np.uint64), flags=flag)
+            assert r.node_idx[0] == 0 and r.feasible_cnt[0] == 40
+
+
+def test_incremental_bind_equals_rebuild(ks, orc):
+    cl = ks.synth.make(300, 500, seed=5, bound_per_node=2)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    with ks.Snapshot(0) as a, ks.Snapshot(0) as b:
+        a.set_nodes(ac, am, lab)
+        a.set_bound(bn, bc, bm)
+        r0 = a.select(rc, rm, sel)
+        # bind the first 20 schedulable pods one by one
+        extra = [(int(r0.node_idx[p]), int(rc[p]), int(rm[p])) for p in range(300) if r0.node_idx[p] >= 0][:20]
+        for n, c, m in extra:
+            a.apply_bind(n, c, m)
+        b.set_nodes(ac, am, lab)
+        b.set_bound(np.concatenate([bn, [e[0] for e in extra]]), np.concatenate([bc, [e[1] for e in extra]]),
+                    np.concatenate([bm, [e[2] for e in extra]]))
+        fa, fb = a.free(), b.free()
+        assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
+        for flag in PATHS.values():
+            ra = a.select(rc, rm, sel, flags=flag, want_mask=True)
+            rb = b.select(rc, rm, sel, flags=flag, want_mask=True)
+            assert np.array_equal(ra.node_idx, rb.node_idx) and np.array_equal(ra.mask, rb.mask)
+
+
+def test_device_buffers_and_user_stream(ks, orc):
+    """KS_MEM_DEVICE arguments (torch tensors only provide the memory and the stream)."""
+    import torch
+    cl = ks.synth.make(5000, 4000, seed=9)
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    o = _oracle(orc, cl, 0)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(np.ascontiguousarray(x.view(np.int64))).to(dev) for x in (rc, rm, sel)]
+    row = ks.mask_row_bytes(cl.N)
+    idx = torch.empty(cl.P, dtype=torch.int32, device=dev)
+    score = torch.empty(cl.P, dtype=torch.int64, device=dev)
+    cnt = torch.empty(cl.P, dtype=torch.int32, device=dev)
+    mask = torch.zeros((cl.P, row), dtype=torch.uint8, device=dev)
+    st = torch.cuda.Stream()
+    with snap:
+        for flag in PATHS.values():
+            idx.fill_(-7)
+            mask.zero_()
+            torch.cuda.synchronize()
+            snap.select_raw(cl.P, t[0], t[1], t[2], ks.KS_MEM_DEVICE, idx, score, cnt, ks.KS_MEM_DEVICE, mask=mask,
+                            mask_row_bytes=row, mask_space=ks.KS_MEM_DEVICE, flags=flag, stream=st.cuda_stream)
+            st.synchronize()
+            assert np.array_equal(idx.cpu().numpy(), o[0])
+            assert np.array_equal(score.cpu().numpy(), o[1])
+            assert np.array_equal(cnt.cpu().numpy().view(np.uint32), o[2])
+            assert np.array_equal(mask.cpu().numpy(), o[3])
+
+
+def test_bad_arguments_are_status_codes(ks):
+    with ks.Snapshot(0) as snap:
+        with pytest.raises(ks.KsError):
+            snap.set_nodes([1], [1], np.zeros((1, 3), np.uint64))  # W must be 1/2/4/8
+        with pytest.raises(ks.KsError):
+            snap.set_nodes([1 << 40], [1], np.zeros((1, 1), np.uint64))  # out of range
+        snap.set_nodes([1], [1], np.zeros((1, 1), np.uint64))
+        with pytest.raises(ks.KsError):
+            snap.set_bound([3], [1], [1])  # node index out of range
+        with pytest.raises(ks.KsError):
+            snap.select([1], [1], np.zeros((1, 1), np.uint64), policy=7)
+
+
+def _properties(ks, r, N):
+    bits_cnt = np.unpackbits(r.mask, axis=1).sum(axis=1)
+    assert np.array_equal(bits_cnt.astype(np.uint32), r.feasible_cnt)          # checksum of the mask
+    assert np.array_equal(r.node_idx < 0, r.feasible_cnt == 0)                 # None <=> empty feasible set
+    has = r.node_idx >= 0
+    idx = r.node_idx[has].astype(np.int64)
+    rows = np.nonzero(has)[0]
+    assert ((r.mask[rows, idx // 8] >> (idx % 8).astype(np.uint8)) & 1).all()  # chosen node is feasible
+    assert (r.mask[:, (N + 7) // 8:] == 0).all()                               # padding bits stay clear
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_config_c2_full_size_bit_exact(ks, orc, path):
+    """BASELINE.json configs[1]: 100k pods x 10k nodes, resource_fits + nodeSelector (1e9 cells), full compare."""
+    cl = ks.synth.config("c2")
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    with snap:
+        r = snap.select(rc, rm, sel, flags=PATHS[path], want_mask=True)
+    _properties(ks, r, cl.N)
+    _assert_same(r, _oracle(orc, cl, 0), f"C2 {path}")
+
+
+def test_config_c3_full_size_properties(ks, orc):
+    """BASELINE.json configs[2]: 1M x 50k (5e10 cells): both kernel paths must agree on bindings everywhere,
+    the mask is checked on a pod slab through its properties, and sampled rows against the oracle."""
+    cl = ks.synth.config("c3")
+    snap, (rc, rm, sel) = _snapshot(ks, cl)
+    with snap:
+        a = snap.select(rc, rm, sel, flags=PATHS["bitpar"])
+        b = snap.select(rc, rm, sel, flags=PATHS["direct"])
+        assert np.array_equal(a.node_idx, b.node_idx) and np.array_equal(a.score, b.score)
+        assert np.array_equal(a.feasible_cnt, b.feasible_cnt)
+        assert np.array_equal(a.node_idx < 0, a.feasible_cnt == 0)
+        lo = 400_000
+        slab = snap.select(rc[lo:lo + 20000], rm[lo:lo + 20000], sel[lo:lo + 20000], flags=PATHS["bitpar"], want_mask=True)
+        _properties(ks, slab, cl.N)
+        assert np.array_equal(slab.node_idx, a.node_idx[lo:lo + 20000])
+    sample = cl.take_pods(lo, 2000)
+    o = _oracle(orc, sample, 0)
+    assert np.array_equal(slab.node_idx[:2000], o[0]) and np.array_equal(slab.mask[:2000], o[3])
+    assert np.array_equal(slab.feasible_cnt[:2000], o[2]) and np.array_equal(slab.score[:2000], o[1])

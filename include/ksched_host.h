@@ -1,0 +1,77 @@
+/* ksched_host.h — host layer of libksched.so: the reference's scheduling surface over Pod/Node OBJECTS.
+ *
+ * The reference's host is Rust (async fns inside a binary crate).  No Rust toolchain exists in this image,
+ * so this layer is C++ behind a C ABI that keeps the reference's names, argument meaning and error
+ * behaviour; a Rust controller would bind it with the `extern "C"` block shown in INTEGRATION.md and keep
+ * its reconcile() loop.  Mapping (paths relative to /root/reference):
+ *   ksh_total_pod_resources   <- total_pod_resources            src/util.rs:54-75
+ *   ksh_is_pod_bound          <- is_pod_bound                   src/util.rs:38-45
+ *   ksh_context               <- Context{client,node_store}     src/util.rs:12-15 (+ the LIST of src/predicates.rs:21-38)
+ *   ksh_check_node_validity   <- check_node_validity            src/predicates.rs:63-77
+ *   ksh_select_nodes          <- select_node_for_pod, batched   src/main.rs:51-71 (argmax score instead of 5 random draws)
+ *   ksh_reconcile             <- reconcile                      src/main.rs:73-120 (builds the Binding, does not POST it)
+ *   KSH_RECONCILE_*           <- ReconcileError                 src/error.rs:5-15
+ * The layer packs objects into the SoA/bitmask form of ksched.h and calls the CUDA core; it never evaluates
+ * a predicate on the CPU.  Malformed quantities / missing allocatable keys (reference: panic) return
+ * KS_ERR_PARSE / KS_ERR_MISSING at pack time.
+ */
+#ifndef KSCHED_HOST_H
+#define KSCHED_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ks_objects.h"
+#include "ksched.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reconcile outcomes: Ok(Action::await_change()) or ReconcileError (src/error.rs:5-15) */
+#define KSH_RECONCILE_OK 0                   /* pod already bound (src/main.rs:74-76) or binding produced */
+#define KSH_RECONCILE_NO_NODE_FOUND 1        /* ReconcileError::NoNodeFound (src/main.rs:116-118) */
+#define KSH_RECONCILE_BINDING_OBJECT_FAILED 2 /* ReconcileError::CreateBindingObjectFailed (src/main.rs:111-114);
+                                                 also a pod without namespace (reference: unwrap panic, :80) */
+#define KSH_RECONCILE_BINDING_FAILED 3       /* ReconcileError::CreateBindingFailed: transport, caller side (:105-108) */
+
+/* Kubernetes quantity strings, exact: cpu -> millicores, memory -> bytes.
+ * KS_ERR_PARSE (malformed), KS_ERR_INEXACT (finer than 1m / 1 byte), KS_ERR_RANGE. */
+int ksh_parse_cpu_millicores(const char* quantity, int64_t* out);
+int ksh_parse_memory_bytes(const char* quantity, int64_t* out);
+
+int ksh_total_pod_resources(const ks_pod_obj* pod, int64_t* cpu_millicores, int64_t* mem_bytes);
+int ksh_is_pod_bound(const ks_pod_obj* pod);
+
+typedef struct ksh_context ksh_context;
+int ksh_context_create(int device, ksh_context** out);
+void ksh_context_destroy(ksh_context* ctx);
+/* node store contents (what reflector::Store<Node>::state() returns, src/main.rs:56) */
+int ksh_context_set_nodes(ksh_context* ctx, const ks_node_obj* nodes, uint32_t n_nodes);
+/* every pod object the API server holds; those with spec.nodeName naming a known node are the LIST results
+ * of src/predicates.rs:22-34 (any phase) and are charged to that node; the rest are ignored here. */
+int ksh_context_set_cluster_pods(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods);
+uint32_t ksh_context_num_nodes(const ksh_context* ctx);
+uint32_t ksh_context_label_words(const ksh_context* ctx);
+ks_snapshot* ksh_context_snapshot(ksh_context* ctx); /* borrowed; valid until the next ksh_context_* mutation */
+
+/* Pack P pod objects into caller buffers (req_cpu[P], req_mem[P], sel[P*W]) with the context's current label
+ * dictionary, growing the dictionary (and re-uploading node columns) when a selector names a new pair.
+ * Returns W (>0) on success so the caller can size `sel` = P * 8 words up front (KS_MAX_LABEL_WORDS). */
+int ksh_pack_pods(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int64_t* req_cpu, int64_t* req_mem,
+                  uint64_t* sel, uint32_t sel_stride_words);
+
+int ksh_check_node_validity(ksh_context* ctx, const ks_pod_obj* pod, uint32_t node_idx);
+int ksh_select_nodes(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int policy, int32_t* out_node_idx,
+                     int64_t* out_score, uint32_t* out_feasible_cnt);
+
+/* One reconcile: skip bound pods, select, emit `POST /api/v1/namespaces/{ns}/pods/{name}/binding` body, and
+ * charge the pod to the chosen node in the snapshot (what the next LIST would show).  *node_idx = -1 if none.
+ * binding_json may be NULL; otherwise receives a NUL-terminated JSON document (truncated to cap). */
+int ksh_reconcile(ksh_context* ctx, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* binding_json,
+                  size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSCHED_HOST_H */

@@ -85,6 +85,9 @@ static NodeTable node_table(ks_snapshot* s) {
 
 extern "C" {
 
+// internal hook for the host layer (host/ksh_host.cpp); not declared in include/
+void ks__set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
+
 const char* ks_last_error(void) { return g_err; }
 int ks_version(void) { return 100; }
 int ks_device_count(void) {

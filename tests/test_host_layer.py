@@ -1,0 +1,145 @@
+"""Host layer (C++ behind include/ksched_host.h).  CPU part: the product's own quantity parser and
+total_pod_resources against the golden KATs and against the oracle's independent implementation.
+GPU part: object-level parity of check_node_validity / select_node_for_pod / reconcile with the faithful oracle."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, mask_bits
+
+
+def test_product_quantity_parser_matches_golden_and_oracle(ks, orc):
+    kats = load_golden("quantity_kats.json")
+    for s, want in kats["ok"]:
+        rc_c, vc = ks.host.parse_cpu_millicores(s)
+        orc_rc, ov = orc.parse_quantity(s)
+        if isinstance(want, str):
+            assert rc_c == {"INEXACT": -6, "RANGE": -5}[want], s
+            continue
+        assert orc_rc == 0 and rc_c == 0 and vc == want == ov, s   # cpu unit = 1/1000 = oracle unit
+        rc_m, vm = ks.host.parse_memory_bytes(s)
+        if want % 1000 == 0:
+            assert rc_m == 0 and vm == want // 1000, s
+        else:
+            assert rc_m == -6, s                                    # sub-byte memory is outside the exact domain
+    for s in kats["bad"]:
+        assert ks.host.parse_cpu_millicores(s)[0] == -3, s
+        assert ks.host.parse_memory_bytes(s)[0] == -3, s
+
+
+def test_total_pod_resources_and_is_pod_bound_match_oracle(ks, orc):
+    g = load_golden("gv1.json")
+    arena = ks.objects.ObjectArena()
+    pods = arena.pods(g["pods"] + g["bound_pods"])
+    for i in range(len(g["pods"])):
+        rc, c, m = ks.host.total_pod_resources(pods, i)
+        assert (rc, c, m) == (0, g["expected_req_cpu_milli"][i], g["expected_req_mem_bytes"][i])
+    for i in range(len(g["pods"]) + len(g["bound_pods"])):
+        out = (C.c_int64 * 2)()
+        assert orc.lib.orc_total_pod_resources(C.addressof(pods) + i * C.sizeof(pods._type_), out) == 0
+        rc, c, m = ks.host.total_pod_resources(pods, i)
+        assert (c, m * 1000) == (out[0], out[1])
+        assert ks.host.is_pod_bound(pods, i) == bool(orc.lib.orc_is_pod_bound(C.addressof(pods) + i * C.sizeof(pods._type_)))
+
+
+def test_random_object_totals_match_packed_generator(ks, orc):
+    cl = ks.synth.make(200, 50, seed=3)
+    _, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    pods, bound = arena.pods(pods_s), arena.pods(bound_s)
+    for p in range(cl.P):
+        assert ks.host.total_pod_resources(pods, p) == (0, cl.req_cpu[p], cl.req_mem[p])
+    for b in range(0, cl.B, 7):
+        assert ks.host.total_pod_resources(bound, b) == (0, cl.bound_cpu[b], cl.bound_mem[b])
+
+
+def test_malformed_objects_are_status_codes(ks):
+    arena = ks.objects.ObjectArena()
+    pods = arena.pods([{"name": "a", "containers": [{"cpu": "one"}]}, {"name": "b", "containers": [{"memory": "1.5"}]}])
+    assert ks.host.total_pod_resources(pods, 0)[0] == -3
+    assert ks.host.total_pod_resources(pods, 1)[0] == -6
+    assert b"memory quantity" in ks.lib.ks_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _cluster_objects(ks, cl):
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    return arena, arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,N,keys,policy", [(64, 200, 8, 0), (300, 1500, 8, 0), (40, 300, 32, 1)])
+def test_select_nodes_objects_vs_faithful_oracle(ks, orc, P, N, keys, policy):
+    cl = ks.synth.make(P, N, seed=900 + P, n_keys=keys, bound_per_node=3)
+    arena, nodes, bound, pods = _cluster_objects(ks, cl)
+    oc = orc.Cluster(nodes, cl.N, bound, cl.B)
+    oidx, oscore, ocnt, _, ocodes = oc.run(pods, P, policy=policy, want_codes=True)
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(nodes, cl.N)
+        ctx.set_cluster_pods(bound, cl.B)
+        idx, score, cnt = ctx.select_nodes(pods, P, policy=policy)
+        assert np.array_equal(idx, oidx) and np.array_equal(score, oscore) and np.array_equal(cnt, ocnt)
+        # the dictionary only holds pairs that selectors name: far fewer bits than node label pairs
+        assert ctx.label_words <= max(1, cl.label_words)
+        for p in range(0, P, 7):
+            for n in range(0, N, 13):
+                assert ctx.check_node_validity(pods, p, n) == ocodes[p, n]
+
+
+@pytest.mark.gpu
+def test_gv1_objects_through_host_layer(ks, orc):
+    g = load_golden("gv1.json")
+    arena = ks.objects.ObjectArena()
+    nodes, allp, pods = arena.nodes(g["nodes"]), arena.pods(g["bound_pods"]), arena.pods(g["pods"])
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(nodes, 5)
+        ctx.set_cluster_pods(allp, len(g["bound_pods"]))
+        idx, score, cnt = ctx.select_nodes(pods, 10)
+        assert list(idx) == g["expected_node_idx_leftover"]
+        assert list(cnt) == [r.count("1") for r in g["expected_feasible_rows"]]
+        rows = ["".join("1" if ctx.check_node_validity(pods, p, n) == 0 else "0" for n in range(5)) for p in range(10)]
+        assert rows == g["expected_feasible_rows"]
+
+
+@pytest.mark.gpu
+def test_reference_selector_tests_through_host_layer(ks):
+    """The reference's three tests (src/predicates/test.rs:42-58) on the GPU path: node without status has
+    (0,0) allocatable and the fixture pods request nothing, so fit holds and the code isolates the selector."""
+    for case in load_golden("selector_kats.json")["cases"]:
+        arena = ks.objects.ObjectArena()
+        pods, nodes = arena.pods([case["pod"]]), arena.nodes([case["node"]])
+        with ks.host.Context(0) as ctx:
+            ctx.set_nodes(nodes, 1)
+            code = ctx.check_node_validity(pods, 0, 0)
+        assert (code == 0) == case["expect"], case["id"]
+        assert code in (0, 2)
+
+
+@pytest.mark.gpu
+def test_reconcile_mirror(ks, orc):
+    arena = ks.objects.ObjectArena()
+    nodes = arena.nodes([{"name": "small", "allocatable": {"cpu": "1", "memory": "1000"}},
+                         {"name": "big \"quoted\"", "allocatable": {"cpu": "2", "memory": "4000"}, "labels": {"d": "x"}}])
+    pods = arena.pods([
+        {"name": "a", "ns": "ns1", "containers": [{"cpu": "1500m", "memory": "3000"}]},
+        {"name": "b", "ns": "ns1", "containers": [{"cpu": "600m", "memory": "10"}]},
+        {"name": "c", "ns": "ns1", "containers": [{"cpu": "600m", "memory": "10"}]},
+        {"name": "bound", "ns": "ns1", "node_name": "small", "containers": [{"cpu": "9", "memory": "9"}]},
+        {"name": "sel", "ns": "ns1", "containers": [], "selector": {"d": "y"}},
+    ])
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(nodes, 2)
+        ctx.set_cluster_pods(arena.pods([]), 0)
+        rc, node, js = ctx.reconcile(pods, 0)
+        assert (rc, node) == (0, 1)
+        doc = json.loads(js)
+        assert doc == {"apiVersion": "v1", "kind": "Binding", "metadata": {"name": "a", "namespace": "ns1"},
+                       "target": {"name": "big \"quoted\""}}
+        # capacity was committed: 'big' now has 500m/1000 left, so b goes to 'small', and c fits nowhere
+        assert ctx.reconcile(pods, 1)[:2] == (0, 0)
+        assert ctx.reconcile(pods, 2)[:2] == (ks.host.KSH_RECONCILE_NO_NODE_FOUND, -1)
+        assert ctx.reconcile(pods, 3) == (0, -1, "")          # already bound -> await_change, no binding
+        assert ctx.reconcile(pods, 4)[:2] == (ks.host.KSH_RECONCILE_NO_NODE_FOUND, -1)

@@ -131,7 +131,7 @@ def cpu_reference_arm(cl, ks, seconds, policy, threads=0):
     arena = ks.objects.ObjectArena()
     nodes, bound = arena.nodes(nodes_s), arena.pods(bound_s)
     oc = orc.Cluster(nodes, cl.N, bound, cl.B)
-    probe_n = max(cores, 4)
+    probe_n = max(4 * cores, 16)
 
     def run(first, count):
         _, _, pods_s = ks.objects.cluster_specs(cl, pod_slice=slice(first, first + count))
@@ -287,7 +287,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ks.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms, scan_ms = [], []
+    kern_ms, scan_ms, call_ms = [], [], []
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -301,6 +301,7 @@ def main():
         t = snap.last_timings()
         kern_ms.append(t[0])
         scan_ms.append(t[1])
+        call_ms.append(t[2])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ks.launch_count() - launches0
@@ -355,6 +356,7 @@ def main():
             "label_words": W, "bound_pods": cl.B, "seed": hex(seed), "path": snap.last_path(),
             "parallelism": f"pods sharded x{world}, node table replicated" + (", 1 NCCL all-gather of bindings/step" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": t_wall,
+            "call_ms_inside_library": sum(call_ms) / len(call_ms),
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": P * (16 + 8 * W), "d2h_bytes_per_step": P * 16,

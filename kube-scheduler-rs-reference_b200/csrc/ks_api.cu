@@ -418,9 +418,9 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         if (flags & KS_SELECT_FORCE_BITPAR) use_bitpar = true;
         else if (!(flags & KS_SELECT_FORCE_DIRECT))
             use_bitpar = policy == KS_SCORE_LEFTOVER && bitpar_profitable(s->bp, L.pv.P);
-        if (timing) CU_TRY(cudaEventRecord(s->ev[1], st));
+        if (timing && !use_bitpar) CU_TRY(cudaEventRecord(s->ev[1], st));
         if (use_bitpar) {
-            cudaError_t e = bitpar_select(s->bp, L, s->prio.as<int64_t>(), timing ? s->ev[2] : nullptr);
+            cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
             if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
             s->last_path = "bitpar";
         } else {

@@ -2,12 +2,15 @@
 //
 //   per snapshot   k_rank_nodes     global rank of every node in free_cpu / free_mem / priority order
 //                  k_build_tile     per-tile prefix tables, bucket base+membership, label-pair columns
-//   per call       k_pod_ranks      request -> global rank threshold (2 binary searches per pod)
+//                                   (built twice: node-index order for the mask, priority order for argmax)
+//   per call       k_pod_ranks      request -> global rank threshold (splitters in smem + short global search)
 //                  k_mask_bitpar    persistent; column-block index blob staged in shared memory by TMA bulk
 //                                   copies (cp.async.bulk + mbarrier); 1 thread = 1 (pod, 256-node tile):
 //                                   2x(base + popc(member & low)) -> 2 table rows -> AND label columns ->
-//                                   two 128-bit stores of the mask row segment; counts reduced in smem
-//                  k_first_fit      argmax KS_SCORE_LEFTOVER = first feasible node in priority order
+//                                   two 128-bit stores of the mask row segment; counts by segmented warp
+//                                   shuffle + one RED per (pod, warp)
+//                  k_first_fit_bp   argmax KS_SCORE_LEFTOVER = first feasible node in priority order, found
+//                                   256 nodes at a time with the same table machinery (early exit)
 // Semantics per cell are exactly predicates.rs:42 / :45-61 (see include/ksched.h); only the evaluation
 // order differs, and every output is compared bit-for-bit with the oracle in tests/.
 #include "ks_bitpar.h"
@@ -20,8 +23,8 @@ namespace ks {
 __global__ void __launch_bounds__(256)
     k_rank_nodes(NodeTable nt, const int64_t* __restrict__ prio, int64_t* __restrict__ sortedC,
                  int64_t* __restrict__ sortedM, uint32_t* __restrict__ gposC, uint32_t* __restrict__ gposM,
-                 int64_t* __restrict__ ord_fc, int64_t* __restrict__ ord_fm, int64_t* __restrict__ ord_prio,
-                 uint64_t* __restrict__ ord_lab, int32_t* __restrict__ ord_idx, uint32_t Nord) {
+                 int64_t* __restrict__ ord_prio, int32_t* __restrict__ ord_idx, uint32_t Nord,
+                 int64_t* __restrict__ splC, int64_t* __restrict__ splM, uint32_t spl_stride) {
     __shared__ int64_t s_fc[1024], s_fm[1024], s_pr[1024];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t N = nt.N;
@@ -52,17 +55,13 @@ __global__ void __launch_bounds__(256)
         gposM[n] = cM;
         sortedC[cC] = fc;
         sortedM[cM] = fm;
-        ord_fc[cP] = fc;
-        ord_fm[cP] = fm;
+        if (cC % spl_stride == 0) splC[cC / spl_stride] = fc;
+        if (cM % spl_stride == 0) splM[cM / spl_stride] = fm;
         ord_prio[cP] = pr;
         ord_idx[cP] = (int32_t)n;
-        for (uint32_t w = 0; w < nt.W; w++) ord_lab[(size_t)w * Nord + cP] = nt.labels[(size_t)w * nt.Npad + n];
-    } else if (n < Nord) { // padding of the priority order: never feasible
-        ord_fc[n] = INT64_MIN;
-        ord_fm[n] = INT64_MIN;
+    } else if (n < Nord) { // padding of the priority order
         ord_prio[n] = INT64_MIN;
         ord_idx[n] = -1;
-        for (uint32_t w = 0; w < nt.W; w++) ord_lab[(size_t)w * Nord + n] = 0;
     }
 }
 
@@ -72,9 +71,11 @@ __device__ __forceinline__ uint32_t table_chunk(uint32_t row, uint32_t half) {
     return 2u * row + (half ^ ((row >> 2) & 1u));
 }
 
+// One CTA builds the index of one 256-slot tile.  slot_node maps slot -> node (nullptr = identity, i.e. the
+// node-index order used for the mask; ord_idx = priority order used for the argmax).
 __global__ void __launch_bounds__(288)
     k_build_tile(NodeTable nt, const uint32_t* __restrict__ gposC, const uint32_t* __restrict__ gposM,
-                 uint8_t* __restrict__ blob, BitparLayout lay) {
+                 const int32_t* __restrict__ slot_node, uint8_t* __restrict__ blob, BitparLayout lay) {
     __shared__ uint32_t s_g[2][BP_TILE];
     __shared__ uint16_t s_lr[2][BP_TILE];
     __shared__ uint8_t s_valid[BP_TILE];
@@ -82,8 +83,9 @@ __global__ void __launch_bounds__(288)
     const uint32_t tile_g = blockIdx.x, cb = tile_g / lay.nt, t = tile_g % lay.nt, s = threadIdx.x;
     uint8_t* B = blob + (size_t)cb * lay.blob_bytes;
     if (s < BP_TILE) {
-        const uint32_t n = tile_g * BP_TILE + s;
-        const bool v = n < nt.N;
+        const uint32_t slot = tile_g * BP_TILE + s;
+        const bool v = slot < nt.N;
+        const uint32_t n = v ? (slot_node ? (uint32_t)slot_node[slot] : slot) : 0;
         s_valid[s] = v;
         s_g[0][s] = v ? gposC[n] : 0xFFFFFFFFu;
         s_g[1][s] = v ? gposM[n] : 0xFFFFFFFFu;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(288)
         }
     }
     __syncthreads();
-    // prefix tables: row r = nodes of the tile whose tile-local rank is >= r  (i.e. free >= threshold)
+    // prefix tables: row r = slots of the tile whose tile-local rank is >= r  (i.e. free >= threshold)
     if (s < BP_ROWS) {
         for (int r = 0; r < 2; r++) {
             uint32_t w[8];
@@ -168,11 +170,12 @@ __global__ void __launch_bounds__(288)
 }
 
 // ------------------------------------------------------------------------------------------------ per call
-__device__ __forceinline__ uint32_t lower_bound_i64(const int64_t* __restrict__ a, uint32_t n, int64_t x) {
+template <class Ptr>
+__device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x) {
     uint32_t lo = 0, len = n; // number of elements < x
     while (len > 0) {
         const uint32_t half = len >> 1;
-        if (__ldg(a + lo + half) < x) {
+        if (a[lo + half] < x) {
             lo += half + 1;
             len -= half + 1;
         } else {
@@ -182,12 +185,37 @@ __device__ __forceinline__ uint32_t lower_bound_i64(const int64_t* __restrict__ 
     return lo;
 }
 
-__global__ void k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM,
-                            uint32_t N, uint2* __restrict__ rk) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pv.P) return;
-    // nodes at sorted positions >= rank have free >= request  <=>  request <= free (predicates.rs:42)
-    rk[p] = make_uint2(lower_bound_i64(sortedC, N, pv.req_cpu[p]), lower_bound_i64(sortedM, N, pv.req_mem[p]));
+// rank = number of nodes with free < request; nodes at sorted positions >= rank satisfy request <= free
+// (predicates.rs:42).  Two-level search: <=1024 splitters per resource in shared memory, then a window of
+// spl_stride-1 elements of the global sorted array.
+__global__ void __launch_bounds__(256)
+    k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM, uint32_t N,
+                const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
+                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero) {
+    __shared__ int64_t s_spl[2][1024];
+    for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
+        s_spl[0][k] = splC[k];
+        s_spl[1][k] = splM[k];
+    }
+    __syncthreads();
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pv.P; p += gridDim.x * blockDim.x) {
+        uint32_t out[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int64_t x = r ? __ldg(pv.req_mem + p) : __ldg(pv.req_cpu + p);
+            const int64_t* sorted = r ? sortedM : sortedC;
+            const uint32_t c = lower_bound_i64(s_spl[r], n_spl, x);
+            uint32_t ans = 0;
+            if (c > 0) {
+                const uint32_t lo = (c - 1) * stride + 1; // sorted[lo-1] < x <= sorted[c*stride] (if it exists)
+                const uint32_t len = min(stride - 1, N - lo);
+                ans = lo + lower_bound_i64(sorted + lo, len, x);
+            }
+            out[r] = ans;
+        }
+        rk[p] = make_uint2(out[0], out[1]);
+        if (cnt_zero) cnt_zero[p] = 0; // k_mask_bitpar accumulates feasible counts with REDs
+    }
 }
 
 template <int W>
@@ -196,7 +224,6 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                   OutView ov) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(smem + lay.blob_bytes);
 
     const uint32_t tid = threadIdx.x, nt = lay.nt, P = pv.P;
     // static split of the (column block, pod) units over the persistent CTAs
@@ -209,13 +236,15 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     }
     __syncthreads();
     uint32_t phase = 0;
-    const uint32_t div_magic = ((1u << 20) + nt - 1) / nt; // exact i/nt for i < 2^15 (BP_POD_CHUNK*nt <= 2^15)
 
-    const uint16_t* baseC = reinterpret_cast<const uint16_t*>(smem + lay.off_baseC);
-    const uint16_t* baseM = reinterpret_cast<const uint16_t*>(smem + lay.off_baseM);
-    const unsigned long long* membC = reinterpret_cast<const unsigned long long*>(smem + lay.off_membC);
-    const unsigned long long* membM = reinterpret_cast<const unsigned long long*>(smem + lay.off_membM);
-    const uint4* pairs = reinterpret_cast<const uint4*>(smem + lay.off_pairs);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t a_baseC = s_base + lay.off_baseC, a_baseM = s_base + lay.off_baseM;
+    const uint32_t a_membC = s_base + lay.off_membC, a_membM = s_base + lay.off_membM;
+    const uint32_t a_tabC = s_base + lay.off_tabC, a_tabM = s_base + lay.off_tabM;
+    const uint32_t a_pairs = s_base + lay.off_pairs;
+    const uint32_t nt_log2 = 31 - __clz(nt); // nt is a power of two (make_layout_smem)
+    const uint32_t dpl = BP_THREADS >> nt_log2;
+    const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
 
     while (u0 < u1) {
         const uint32_t cb = (uint32_t)(u0 / P);
@@ -232,140 +261,204 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
             for (uint32_t off = 0; off < lay.blob_bytes; off += 32768u)
                 tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
         }
+
+        const uint32_t items = (pb - pa) * nt; // item i = (pod pa + i / nt, tile i % nt): lanes = adjacent tiles
+        uint32_t i = tid, pl = tid >> nt_log2;
+        const uint32_t t = tid & (nt - 1); // BP_THREADS is a multiple of nt: a thread keeps its tile
+        bool act = i < items;
+        uint2 r = act ? __ldg(rk + pa + pl) : make_uint2(0, 0); // prefetch while the blob is in flight
+        unsigned long long sel[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) sel[w] = act ? __ldg(pv.sel + (size_t)(pa + pl) * W + w) : 0ull;
+
         mbar_wait(&bar, phase);
         phase ^= 1;
 
-        for (uint32_t pc0 = pa; pc0 < pb; pc0 += BP_POD_CHUNK) {
-            const uint32_t n_p = min((uint32_t)BP_POD_CHUNK, pb - pc0);
-            if (ov.cnt) {
-                for (uint32_t i = tid; i < n_p; i += BP_THREADS) cnt_s[i] = 0;
-                __syncthreads();
+        while ((i & ~31u) < items) { // warp-uniform trip count (shuffles below need the whole warp)
+            const uint2 cr = r;
+            const uint32_t cpl = pl, ct = t;
+            const bool cact = act;
+            unsigned long long csel[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) csel[w] = sel[w];
+            // software prefetch of the next item's pod data
+            i += BP_THREADS;
+            pl += dpl;
+            act = i < items;
+            if (act) {
+                r = __ldg(rk + pa + pl);
+#pragma unroll
+                for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)(pa + pl) * W + w);
             }
-            const uint32_t items = n_p * nt;
-            for (uint32_t i = tid; i < items; i += BP_THREADS) {
-                const uint32_t pl = (i * div_magic) >> 20;
-                const uint32_t t = i - pl * nt;
-                const uint32_t p = pc0 + pl;
-                const uint2 r = __ldg(rk + p);
-                // tile-local rank of each threshold: nodes of the tile at global positions < threshold
-                const uint32_t hc = r.x >> 6, hm = r.y >> 6;
-                const uint32_t rankC = baseC[hc * nt + t] + __popcll(membC[hc * nt + t] & ((1ull << (r.x & 63)) - 1ull));
-                const uint32_t rankM = baseM[hm * nt + t] + __popcll(membM[hm * nt + t] & ((1ull << (r.y & 63)) - 1ull));
-                const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + t * BP_TABLE_BYTES);
-                const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + t * BP_TABLE_BYTES);
-                const uint4 c0 = tc[table_chunk(rankC, 0)], c1 = tc[table_chunk(rankC, 1)];
-                const uint4 m0 = tm[table_chunk(rankM, 0)], m1 = tm[table_chunk(rankM, 1)];
-                uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
-                uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
+
+            uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+            if (cact) {
+                // tile-local rank of each threshold = tile nodes at global positions < threshold
+                const uint32_t ec = (cr.x >> 6) * nt + ct, em = (cr.y >> 6) * nt + ct;
+                uint32_t bc, bm;
+                unsigned long long mc, mm;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bc) : "r"(a_baseC + ec * 2));
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mc) : "r"(a_membC + ec * 8));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bm) : "r"(a_baseM + em * 2));
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mm) : "r"(a_membM + em * 8));
+                const uint32_t rankC = bc + __popcll(mc & ((1ull << (cr.x & 63)) - 1ull));
+                const uint32_t rankM = bm + __popcll(mm & ((1ull << (cr.y & 63)) - 1ull));
+                const uint32_t tc = a_tabC + ct * BP_TABLE_BYTES, tm = a_tabM + ct * BP_TABLE_BYTES;
+                uint4 c0, c1, m0, m1;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(tc + table_chunk(rankC, 0) * 16));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(tc + table_chunk(rankC, 1) * 16));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m0.x), "=r"(m0.y), "=r"(m0.z), "=r"(m0.w) : "r"(tm + table_chunk(rankM, 0) * 16));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m1.x), "=r"(m1.y), "=r"(m1.z), "=r"(m1.w) : "r"(tm + table_chunk(rankM, 1) * 16));
+                a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
+                b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
 #pragma unroll
                 for (int w = 0; w < W; w++) {
-                    unsigned long long bits = __ldg(pv.sel + (size_t)p * W + w);
+                    unsigned long long bits = csel[w];
                     while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
                         const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
                         bits &= bits - 1;
-                        const uint4 q0 = pairs[(bit * nt + t) * 2], q1 = pairs[(bit * nt + t) * 2 + 1];
+                        const uint32_t pa_ = a_pairs + (bit * nt + ct) * 32;
+                        uint4 q0, q1;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(pa_));
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(pa_ + 16));
                         a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
                         b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
                     }
                 }
-                if (ov.cnt) {
-                    const uint32_t c = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) +
-                                       __popc(b.y) + __popc(b.z) + __popc(b.w);
-                    if (c) atomicAdd(&cnt_s[pl], c);
-                }
-                if (ov.mask) {
-                    const uint32_t word = (cb * nt + t) * 8;
+                if (want_mask) {
+                    const uint32_t word = (cb * nt + ct) * 8;
                     if (word < ov.mask_valid_words) {
-                        uint4* dst = reinterpret_cast<uint4*>(ov.mask + (size_t)p * ov.mask_row_words + word);
+                        uint4* dst = reinterpret_cast<uint4*>(ov.mask + (size_t)(pa + cpl) * ov.mask_row_words + word);
                         __stcs(dst, a);
                         __stcs(dst + 1, b);
                     }
                 }
             }
-            if (ov.cnt) {
-                __syncthreads();
-                for (uint32_t i = tid; i < n_p; i += BP_THREADS) {
-                    const uint32_t c = cnt_s[i];
-                    if (lay.ncb == 1) ov.cnt[pc0 + i] = c;
-                    else if (c) atomicAdd(&ov.cnt[pc0 + i], c);
+            if (want_cnt) {
+                // the nt lanes of one pod are an aligned power-of-two group: xor butterfly, one RED per pod
+                uint32_t c = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) +
+                             __popc(b.z) + __popc(b.w);
+                for (uint32_t off = 1; off < nt; off <<= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+                if (cact && ct == 0) {
+                    if (lay.ncb == 1) ov.cnt[pa + cpl] = c; // single writer, no zero-init needed
+                    else if (c) atomicAdd(&ov.cnt[pa + cpl], c);
                 }
-                __syncthreads();
             }
         }
     }
 }
 
-// argmax of the separable score = first feasible node in descending priority order.  One warp per pod,
-// 32 candidates per step, early exit.  Pods whose feasible count is already known to be 0 are skipped.
+// argmax of the separable score = first feasible node in descending priority order.  One thread per pod walks
+// the priority-ordered index 256 nodes per step (same rank + table + column machinery, read through L1/L2)
+// and stops at the first non-empty tile.  Pods whose feasible count is already known to be 0 are skipped.
 template <int W>
 __global__ void __launch_bounds__(256)
-    k_first_fit(const int64_t* __restrict__ ord_fc, const int64_t* __restrict__ ord_fm,
-                const int64_t* __restrict__ ord_prio, const uint64_t* __restrict__ ord_lab,
-                const int32_t* __restrict__ ord_idx, uint32_t Nord, PodView pv, OutView ov) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    k_first_fit_bp(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
+                   const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= pv.P) return;
-    const int64_t rc = __ldg(pv.req_cpu + p), rm = __ldg(pv.req_mem + p);
-    uint64_t sel[W];
-#pragma unroll
-    for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
     int32_t best = -1;
     int64_t score = 0;
     if (!(ov.cnt && ov.cnt[p] == 0)) {
-        for (uint32_t base = 0; base < Nord; base += 32) {
-            const uint32_t i = base + lane;
-            bool ok = (rc <= __ldg(ord_fc + i)) & (rm <= __ldg(ord_fm + i));
-            uint64_t miss = 0;
+        const uint2 r = __ldg(rk + p);
+        unsigned long long sel[W];
 #pragma unroll
-            for (int w = 0; w < W; w++) miss |= sel[w] & ~__ldg(ord_lab + (size_t)w * Nord + i);
-            ok = ok && miss == 0 && __ldg(ord_idx + i) >= 0;
-            const uint32_t b = __ballot_sync(0xffffffffu, ok);
-            if (b) {
-                const uint32_t f = base + __ffs(b) - 1;
-                best = __ldg(ord_idx + f);
-                score = __ldg(ord_prio + f) - (int64_t)(((uint64_t)rc << 22) + (uint64_t)rm);
+        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+        const uint16_t* baseC = reinterpret_cast<const uint16_t*>(blobP + lay.off_baseC) + (size_t)(r.x >> 6) * lay.nt;
+        const uint16_t* baseM = reinterpret_cast<const uint16_t*>(blobP + lay.off_baseM) + (size_t)(r.y >> 6) * lay.nt;
+        const unsigned long long* membC =
+            reinterpret_cast<const unsigned long long*>(blobP + lay.off_membC) + (size_t)(r.x >> 6) * lay.nt;
+        const unsigned long long* membM =
+            reinterpret_cast<const unsigned long long*>(blobP + lay.off_membM) + (size_t)(r.y >> 6) * lay.nt;
+        const unsigned long long lowC = (1ull << (r.x & 63)) - 1ull, lowM = (1ull << (r.y & 63)) - 1ull;
+        const uint4* pairs = reinterpret_cast<const uint4*>(blobP + lay.off_pairs);
+        for (uint32_t k = 0; k < lay.nt; k++) {
+            const uint32_t rankC = __ldg(baseC + k) + __popcll(__ldg(membC + k) & lowC);
+            const uint32_t rankM = __ldg(baseM + k) + __popcll(__ldg(membM + k) & lowM);
+            const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + (size_t)k * BP_TABLE_BYTES);
+            const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + (size_t)k * BP_TABLE_BYTES);
+            const uint4 c0 = __ldg(tc + table_chunk(rankC, 0)), c1 = __ldg(tc + table_chunk(rankC, 1));
+            const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
+            uint32_t m[8] = {c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w,
+                             c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w};
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                unsigned long long bits = sel[w];
+                while (bits) {
+                    const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    const uint4 q0 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2);
+                    const uint4 q1 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2 + 1);
+                    m[0] &= q0.x; m[1] &= q0.y; m[2] &= q0.z; m[3] &= q0.w;
+                    m[4] &= q1.x; m[5] &= q1.y; m[6] &= q1.z; m[7] &= q1.w;
+                }
+            }
+            int first = -1;
+#pragma unroll
+            for (int j = 7; j >= 0; j--)
+                if (m[j]) first = j * 32 + __ffs(m[j]) - 1;
+            if (first >= 0) {
+                const uint32_t slot = k * BP_TILE + first;
+                best = __ldg(ord_idx + slot);
+                score = __ldg(ord_prio + slot) -
+                        (int64_t)(((uint64_t)__ldg(pv.req_cpu + p) << 22) + (uint64_t)__ldg(pv.req_mem + p));
                 break;
             }
         }
     }
-    if (lane == 0) {
-        if (ov.node_idx) ov.node_idx[p] = best;
-        if (ov.score) ov.score[p] = score;
-    }
+    if (ov.node_idx) ov.node_idx[p] = best;
+    if (ov.score) ov.score[p] = score;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 static uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
-static bool make_layout(uint32_t N, uint32_t W, BitparLayout* lay) {
-    const uint32_t n_tiles = (N + BP_TILE - 1) / BP_TILE;
-    const uint32_t nb = (N >> 6) + 1;
-    const uint64_t per_tile = (uint64_t)nb * 20 + 2ull * BP_TABLE_BYTES + 64ull * W * 32;
-    const uint64_t avail = BP_SMEM_MAX - BP_POD_CHUNK * 4 - 1024;
-    uint32_t nt_max = (uint32_t)std::min<uint64_t>(32, avail / per_tile);
-    if (n_tiles == 0 || nt_max == 0) return false;
-    const uint32_t ncb = (n_tiles + nt_max - 1) / nt_max;
-    const uint32_t nt = (n_tiles + ncb - 1) / ncb;
-    lay->nt = nt;
-    lay->nb = nb;
-    lay->ncb = ncb;
+static uint64_t per_tile_bytes(uint32_t nb, uint32_t W) {
+    return (uint64_t)nb * 20 + 2ull * BP_TABLE_BYTES + 64ull * W * 32;
+}
+
+static bool fill_offsets(BitparLayout* lay, uint32_t W) {
+    const uint64_t nb = lay->nb, nt = lay->nt;
+    if (per_tile_bytes(lay->nb, W) * nt + 1024 > 0xF0000000ull) return false;
     uint32_t off = 0;
     lay->off_baseC = off;
-    off += round16(nb * nt * 2);
+    off += round16((uint32_t)(nb * nt * 2));
     lay->off_baseM = off;
-    off += round16(nb * nt * 2);
+    off += round16((uint32_t)(nb * nt * 2));
     lay->off_membC = off;
-    off += round16(nb * nt * 8);
+    off += round16((uint32_t)(nb * nt * 8));
     lay->off_membM = off;
-    off += round16(nb * nt * 8);
+    off += round16((uint32_t)(nb * nt * 8));
     lay->off_tabC = off;
-    off += nt * BP_TABLE_BYTES;
+    off += (uint32_t)nt * BP_TABLE_BYTES;
     lay->off_tabM = off;
-    off += nt * BP_TABLE_BYTES;
+    off += (uint32_t)nt * BP_TABLE_BYTES;
     lay->off_pairs = off;
-    off += 64 * W * nt * 32;
+    off += 64u * W * (uint32_t)nt * 32u;
     lay->blob_bytes = (off + 127u) & ~127u;
-    return lay->blob_bytes + BP_POD_CHUNK * 4 <= (uint32_t)BP_SMEM_MAX;
+    return true;
+}
+
+// column-block layout for the mask kernel: as many tiles per block as fit in shared memory
+static bool make_layout_smem(uint32_t N, uint32_t W, BitparLayout* lay) {
+    const uint32_t n_tiles = (N + BP_TILE - 1) / BP_TILE;
+    lay->nb = (N >> 6) + 1;
+    const uint64_t avail = BP_SMEM_MAX - 1024;
+    const uint32_t nt_max = (uint32_t)std::min<uint64_t>(32, avail / per_tile_bytes(lay->nb, W));
+    if (n_tiles == 0 || nt_max == 0) return false;
+    uint32_t nt = 1; // power of two: the lanes of one pod form an aligned group of a warp
+    while (nt * 2 <= nt_max && nt < n_tiles) nt *= 2;
+    lay->nt = nt;
+    lay->ncb = (n_tiles + nt - 1) / nt;
+    return fill_offsets(lay, W) && lay->blob_bytes <= (uint32_t)BP_SMEM_MAX;
+}
+
+// flat layout for the priority-ordered index (global memory, all tiles in one blob)
+static bool make_layout_flat(uint32_t N, uint32_t W, BitparLayout* lay) {
+    lay->nb = (N >> 6) + 1;
+    lay->ncb = 1;
+    lay->nt = (N + BP_TILE - 1) / BP_TILE;
+    return lay->nt > 0 && fill_offsets(lay, W);
 }
 
 template <class T>
@@ -376,10 +469,13 @@ static cudaError_t regrow(T*& p, size_t count) {
 }
 
 void bitpar_release(BitparIndex& ix) {
-    void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc, ix.ord_fm, ix.ord_prio, ix.ord_lab,
-                    ix.ord_idx, ix.blob, ix.pod_ranks};
+    void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc,  ix.ord_fm,   ix.ord_prio,
+                    ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (ix.aux) cudaStreamDestroy(ix.aux);
+    if (ix.ev_fork) cudaEventDestroy(ix.ev_fork);
+    if (ix.ev_join) cudaEventDestroy(ix.ev_join);
     ix = BitparIndex();
 }
 
@@ -388,97 +484,132 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
     ix.N = nt.N;
     ix.W = nt.W;
     if (nt.N == 0) return cudaSuccess;
-    const uint32_t Nord = (nt.N + 31u) & ~31u;
+    const uint32_t Nord = ((nt.N + BP_TILE - 1) / BP_TILE) * BP_TILE;
     ix.Nord = Nord;
     cudaError_t e;
-    if (Nord > ix.cap_nodes || (size_t)Nord * nt.W > ix.cap_lab) {
-        const size_t cap = Nord + Nord / 8 + 32;
+    if (Nord > ix.cap_nodes) {
+        const size_t cap = Nord + Nord / 8 + BP_TILE;
         if ((e = regrow(ix.sortedC, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.sortedM, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.gposC, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.gposM, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.ord_fc, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.ord_fm, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.ord_prio, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.ord_idx, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.ord_lab, cap * nt.W)) != cudaSuccess) return e;
+        if ((e = regrow(ix.splC, 1024)) != cudaSuccess) return e;
+        if ((e = regrow(ix.splM, 1024)) != cudaSuccess) return e;
         ix.cap_nodes = cap;
-        ix.cap_lab = cap * nt.W;
     }
-    k_rank_nodes<<<(Nord + 255) / 256, 256, 0, st>>>(nt, prio, ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc,
-                                                     ix.ord_fm, ix.ord_prio, ix.ord_lab, ix.ord_idx, Nord);
+    uint32_t stride = 1;
+    while ((nt.N + stride - 1) / stride > 1024) stride <<= 1;
+    ix.spl_stride = stride;
+    ix.n_spl = (nt.N + stride - 1) / stride;
+    k_rank_nodes<<<(Nord + 255) / 256, 256, 0, st>>>(nt, prio, ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
+                                                     ix.ord_idx, Nord, ix.splC, ix.splM, stride);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    BitparLayout lay{};
-    if (!make_layout(nt.N, nt.W, &lay)) return cudaSuccess; // index does not fit: only k_first_fit is usable
+    BitparLayout lay{}, layP{};
+    if (!make_layout_smem(nt.N, nt.W, &lay) || !make_layout_flat(nt.N, nt.W, &layP)) return cudaSuccess; // direct path only
     const size_t need = (size_t)lay.ncb * lay.blob_bytes;
     if (need > ix.cap_blob) {
         if ((e = regrow(ix.blob, need + need / 8)) != cudaSuccess) return e;
         ix.cap_blob = need + need / 8;
     }
-    if ((e = cudaMemsetAsync(ix.blob, 0, need, st)) != cudaSuccess) return e;
-    k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.blob, lay);
+    if (layP.blob_bytes > ix.cap_blobP) {
+        const size_t cap = (size_t)layP.blob_bytes + layP.blob_bytes / 8;
+        if ((e = regrow(ix.blobP, cap)) != cudaSuccess) return e;
+        ix.cap_blobP = cap;
+    }
+    k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
+    g_launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ord_idx, ix.blobP, layP);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ix.lay = lay;
+    ix.layP = layP;
     ix.valid = true;
     return cudaSuccess;
 }
 
 bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
-    // below ~16M cells the per-call rank pass and blob staging outweigh the per-cell kernel
-    return ix.valid && (uint64_t)P * ix.N >= (1ull << 24);
+    // below ~16M cells the per-call rank pass and blob staging outweigh the per-cell kernel;
+    // the mask kernel indexes (pod, tile) items with 32 bits
+    return ix.valid && (uint64_t)P * ix.N >= (1ull << 24) && (uint64_t)P * ix.lay.nt < (1ull << 31);
 }
 
 template <int W>
-static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t after_mask) {
+static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
     cudaError_t e;
     const uint32_t P = L.pv.P;
+    if ((uint64_t)P * ix.lay.nt >= (1ull << 31)) return cudaErrorInvalidValue;
     const bool need_mask_pass = L.ov.mask || L.ov.cnt;
-    if (need_mask_pass) {
-        if (P > ix.cap_pods) {
-            const size_t cap = (size_t)P + P / 8 + 64;
-            if ((e = regrow(ix.pod_ranks, cap)) != cudaSuccess) return e;
-            ix.cap_pods = cap;
-        }
-        k_pod_ranks<<<(P + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.pod_ranks);
+    if (ix.sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&ix.sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((e = cudaStreamCreateWithFlags(&ix.aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ix.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ix.ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    const int sms = ix.sms;
+    if (P > ix.cap_pods) {
+        const size_t cap = (size_t)P + P / 8 + 64;
+        if ((e = regrow(ix.pod_ranks, cap)) != cudaSuccess) return e;
+        ix.cap_pods = cap;
+    }
+    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 4, ((uint64_t)P + 255) / 256);
+    k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl,
+                                                 ix.spl_stride, ix.pod_ranks,
+                                                 (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr);
+    g_launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // argmax scan on an auxiliary stream so that it overlaps the mask kernel (it needs only the pod ranks)
+    const bool want_bind = L.ov.node_idx || L.ov.score;
+    if (want_bind) {
+        if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
+        OutView ovb = L.ov;
+        ovb.cnt = nullptr; // counts are being produced concurrently: scan without the "count == 0" shortcut
+        k_first_fit_bp<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
+                                                               ix.pod_ranks, ovb);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (L.ov.cnt && ix.lay.ncb > 1)
-            if ((e = cudaMemsetAsync(L.ov.cnt, 0, (size_t)P * 4, L.stream)) != cudaSuccess) return e;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
+    }
+    if (need_mask_pass) {
+        if (before_mask)
+            if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
         const uint64_t units = (uint64_t)ix.lay.ncb * P;
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (units + 63) / 64);
-        const uint32_t smem = ix.lay.blob_bytes + BP_POD_CHUNK * 4;
         auto kern = k_mask_bitpar<W>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
-            return e;
-        kern<<<grid, BP_THREADS, smem, L.stream>>>(ix.blob, ix.lay, L.pv, ix.pod_ranks, L.ov);
+        static int smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (smem_set[W] < (int)ix.lay.blob_bytes) {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX)) != cudaSuccess)
+                return e;
+            smem_set[W] = BP_SMEM_MAX;
+        }
+        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, L.pv, ix.pod_ranks, L.ov);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (after_mask)
+            if ((e = cudaEventRecord(after_mask, L.stream)) != cudaSuccess) return e;
+    } else if (before_mask) {
+        if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
     }
-    if (after_mask && need_mask_pass)
-        if ((e = cudaEventRecord(after_mask, L.stream)) != cudaSuccess) return e;
-    if (L.ov.node_idx || L.ov.score) {
-        k_first_fit<W><<<(P + 7) / 8, 256, 0, L.stream>>>(ix.ord_fc, ix.ord_fm, ix.ord_prio, ix.ord_lab, ix.ord_idx,
-                                                          ix.Nord, L.pv, L.ov);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
+    if (want_bind)
+        if ((e = cudaStreamWaitEvent(L.stream, ix.ev_join, 0)) != cudaSuccess) return e;
     if (after_mask && !need_mask_pass)
         if ((e = cudaEventRecord(after_mask, L.stream)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-cudaError_t bitpar_select(BitparIndex& ix, const SelectLaunch& L, const int64_t*, cudaEvent_t after_mask) {
+cudaError_t bitpar_select(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
     if (!ix.valid) return cudaErrorNotSupported;
     switch (ix.W) {
-        case 1: return select_w<1>(ix, L, after_mask);
-        case 2: return select_w<2>(ix, L, after_mask);
-        case 4: return select_w<4>(ix, L, after_mask);
-        case 8: return select_w<8>(ix, L, after_mask);
+        case 1: return select_w<1>(ix, L, before_mask, after_mask);
+        case 2: return select_w<2>(ix, L, before_mask, after_mask);
+        case 4: return select_w<4>(ix, L, before_mask, after_mask);
+        case 8: return select_w<8>(ix, L, before_mask, after_mask);
         default: return cudaErrorInvalidValue;
     }
 }

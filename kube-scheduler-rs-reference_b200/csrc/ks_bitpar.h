@@ -18,7 +18,6 @@ constexpr int BP_TILE = 256;          // nodes per tile = 8 mask words = one 32-
 constexpr int BP_ROWS = BP_TILE + 1;  // prefix-table rows per tile and resource (local rank 0..256)
 constexpr int BP_TABLE_BYTES = BP_ROWS * 32;
 constexpr int BP_THREADS = 1024;
-constexpr int BP_POD_CHUNK = 1024;    // pods per shared-memory count chunk
 constexpr int BP_SMEM_MAX = 232448;   // 227 KB opt-in limit per CTA
 
 struct BitparLayout { // byte offsets inside one column-block blob
@@ -40,17 +39,24 @@ struct BitparIndex {
     int64_t* ord_prio = nullptr;
     uint64_t* ord_lab = nullptr; // word-major [W][Nord]
     int32_t* ord_idx = nullptr;
-    uint8_t* blob = nullptr;     // ncb blobs of blob_bytes
+    int64_t* splC = nullptr;     // every `spl_stride`-th element of sortedC / sortedM (<= 1024 splitters)
+    int64_t* splM = nullptr;
+    uint8_t* blob = nullptr;     // ncb blobs of lay.blob_bytes: node-index order, staged in shared memory
+    uint8_t* blobP = nullptr;    // one blob of layP.blob_bytes: priority order (tile k = priority ranks 256k..),
+                                 // read through L1/L2 by k_first_fit_bp
     uint2* pod_ranks = nullptr;  // per-call scratch [P]
-    size_t cap_nodes = 0, cap_blob = 0, cap_pods = 0, cap_lab = 0;
-    uint32_t N = 0, Nord = 0, W = 0;
-    BitparLayout lay{};
+    size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_lab = 0;
+    uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
+    BitparLayout lay{}, layP{};
     bool valid = false;
+    int sms = 0;
+    cudaStream_t aux = nullptr; // k_first_fit_bp runs here, overlapped with k_mask_bitpar
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* prio, cudaStream_t st);
 bool bitpar_profitable(const BitparIndex& ix, uint32_t P);
-cudaError_t bitpar_select(BitparIndex& ix, const SelectLaunch& L, const int64_t* prio, cudaEvent_t after_mask);
+cudaError_t bitpar_select(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask);
 void bitpar_release(BitparIndex& ix);
 
 } // namespace ks

@@ -263,7 +263,7 @@ def main():
                         policy=policy, flags=flags | (ks.KS_SELECT_TIMING if timing else 0), stream=stream.cuda_stream)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(d_all, d_bind)
+                ks.multigpu.all_gather_bindings(d_bind, d_all)  # the ONE collective of the step
 
     def step_e2e():
         hp = h_bind.data_ptr()
@@ -338,6 +338,11 @@ def main():
     # sanity: the resident and e2e passes produced the same bindings (cheap guard against a skipped pass)
     torch.cuda.synchronize()
     assert torch.equal(d_bind.cpu(), h_bind), "resident and e2e bindings differ"
+    if world > 1:  # and the all-gather delivered every shard: rank 0's own slice matches, every pod was decided
+        gi, gs, gc = ks.multigpu.unpack_bindings(d_all.cpu().numpy(), world * P, world)
+        mi, ms_, mc = ks.multigpu.unpack_bindings(d_bind.cpu().numpy(), P, 1)
+        assert np.array_equal(gi[:P], mi) and np.array_equal(gs[:P], ms_) and np.array_equal(gc[:P], mc)
+        assert np.array_equal(gi < 0, gc == 0)
 
     ab = algorithmic_bytes(P, N, W, cl.B, emit_mask)
     peak, peak_src = hbm_peak()

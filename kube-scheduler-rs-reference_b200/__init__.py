@@ -13,4 +13,4 @@ from ._capi import (  # noqa: F401
     KsError, lib, LIB_PATH, declared_symbols, mask_row_bytes, device_count, launch_count,
 )
 from .snapshot import Snapshot, SelectResult  # noqa: F401
-from . import synth, objects, host  # noqa: F401
+from . import synth, objects, host, multigpu  # noqa: F401

@@ -584,7 +584,7 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
         auto kern = k_mask_bitpar<W>;
         static int smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (smem_set[W] < (int)ix.lay.blob_bytes) {
-            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX)) != cudaSuccess)
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024)) != cudaSuccess)
                 return e;
             smem_set[W] = BP_SMEM_MAX;
         }

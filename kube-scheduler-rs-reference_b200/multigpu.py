@@ -1,0 +1,59 @@
+"""Pods-dimension sharding across ranks: the node snapshot is replicated on every GPU, rank r
+evaluates pods [lo_r, hi_r) and ONE all-gather of the packed per-pod bindings makes every rank hold all
+bindings.  torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests)."""
+import numpy as np
+
+BYTES_PER_POD = 16  # score i64 | node_idx i32 | feasible_cnt u32
+
+
+def shard_bounds(n_total, world, rank):
+    """Contiguous, balanced split: the first (n_total % world) ranks get one extra pod."""
+    base, extra = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_capacity(n_total, world):
+    return (int(n_total) + world - 1) // world
+
+
+def binding_offsets(capacity):
+    """Byte offsets of (score, node_idx, feasible_cnt) inside one shard buffer of `capacity` pods."""
+    return 0, 8 * capacity, 12 * capacity
+
+
+def pack_bindings(capacity, node_idx, score, cnt):
+    """numpy helper (tests / CPU): build the shard buffer the GPU kernels write in place."""
+    buf = np.zeros(capacity * BYTES_PER_POD, np.uint8)
+    o_s, o_i, o_c = binding_offsets(capacity)
+    n = len(node_idx)
+    buf[o_s:o_s + 8 * n] = np.ascontiguousarray(score, np.int64).view(np.uint8)
+    buf[o_i:o_i + 4 * n] = np.ascontiguousarray(node_idx, np.int32).view(np.uint8)
+    buf[o_c:o_c + 4 * n] = np.ascontiguousarray(cnt, np.uint32).view(np.uint8)
+    return buf
+
+
+def unpack_bindings(gathered, n_total, world):
+    """gathered: uint8 array of world * capacity * 16 bytes -> (node_idx, score, cnt) in global pod order."""
+    cap = shard_capacity(n_total, world)
+    g = np.asarray(gathered, np.uint8).reshape(world, cap * BYTES_PER_POD)
+    o_s, o_i, o_c = binding_offsets(cap)
+    idx, score, cnt = [], [], []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, world, r)
+        n = hi - lo
+        score.append(g[r, o_s:o_s + 8 * n].view(np.int64))
+        idx.append(g[r, o_i:o_i + 4 * n].view(np.int32))
+        cnt.append(g[r, o_c:o_c + 4 * n].view(np.uint32))
+    return np.concatenate(idx), np.concatenate(score), np.concatenate(cnt)
+
+
+def all_gather_bindings(local_buf, out_buf=None):
+    """One collective: every rank contributes its shard buffer (torch uint8 tensor, equal sizes)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    if out_buf is None:
+        out_buf = torch.empty(world * local_buf.numel(), dtype=torch.uint8, device=local_buf.device)
+    dist.all_gather_into_tensor(out_buf, local_buf)
+    return out_buf

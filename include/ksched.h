@@ -119,6 +119,24 @@ int ks_last_timings(ks_snapshot* s, float ms[3]);
 /* name of the dominant kernel path the last ks_select used: "direct" or "bitpar" */
 const char* ks_last_path(const ks_snapshot* s);
 
+/* ---- streaming reconcile (BASELINE.json config C5): micro-batches against the resident snapshot ----
+ * The reference re-LISTs bound pods for every cell (src/predicates.rs:34), so a pod always sees earlier binds.
+ * A batched pass sees one snapshot, so two pods of a batch may claim the same capacity.  K3 resolves that:
+ * claims are taken per node in arrival (array) order; a claim is accepted iff its request still fits what is
+ * left on the node, and then decrements it.  Capacity never goes negative through this path.
+ *
+ * ks_snapshot_commit_claims: host arrays; claim i = pod i wants node claim_node[i] (-1 = no claim).
+ *   out_accepted[i] = 1/0.  Accepted requests are subtracted from free[] on the device (same effect as
+ *   ks_snapshot_apply_bind per accepted claim).  Every replica that commits the same claim list in the same
+ *   order ends with the same free[] (multi-GPU streaming: all-gather the claims, commit everywhere).
+ * ks_stream_bind: the full micro-batch loop on one GPU — select (per-cell kernel, any policy) for the pending
+ *   pods, commit, re-select the losers against the updated free[], until every pod is bound or has no feasible
+ *   node.  out_node_idx[i] = bound node or -1 (= ReconcileError::NoNodeFound, src/main.rs:116-118). */
+int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n_claims, const int32_t* claim_node, const int64_t* req_cpu,
+                              const int64_t* req_mem, uint8_t* out_accepted);
+int ks_stream_bind(ks_snapshot* s, const ks_pods* pods /* host space */, int policy, int32_t* out_node_idx,
+                   int64_t* out_score, uint32_t* out_rounds);
+
 #ifdef __cplusplus
 }
 #endif

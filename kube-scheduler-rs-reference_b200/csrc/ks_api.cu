@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <vector>
 
 #include "ks_bitpar.h"
@@ -81,6 +82,19 @@ static NodeTable node_table(ks_snapshot* s) {
     nt.Npad = s->Npad;
     nt.W = s->W;
     return nt;
+}
+
+// free[] must stay inside the limits that keep scores in int64; prio[] = static node priority (KS_SCORE_LEFTOVER)
+static int check_range_and_prio(ks_snapshot* s, cudaStream_t st) {
+    if (s->N == 0) return KS_OK;
+    CU_TRY(cudaMemsetAsync(s->flag.p, 0, sizeof(int), st));
+    CU_TRY(launch_node_prio(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->prio.as<int64_t>(), s->N, s->Npad,
+                            s->flag.as<int>(), st));
+    int flag = 0;
+    CU_TRY(cudaMemcpyAsync(&flag, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (flag) return fail(KS_ERR_RANGE, "free resources of some node exceed +-2^36 millicores / +-2^55 bytes");
+    return KS_OK;
 }
 
 extern "C" {
@@ -189,7 +203,7 @@ int ks_snapshot_set_nodes(ks_snapshot* s, uint32_t n_nodes, uint32_t label_words
         for (uint32_t w = 0; w < label_words; w++) hl[(size_t)w * Npad + n] = labels[(size_t)n * label_words + w];
     CU_TRY(cudaMemcpyAsync(s->labels.p, hl.data(), nb * label_words, cudaMemcpyHostToDevice, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    return KS_OK;
+    return check_range_and_prio(s, s->stream);
 }
 
 static int reset_free_to_alloc(ks_snapshot* s) {
@@ -227,8 +241,7 @@ int ks_snapshot_set_bound(ks_snapshot* s, uint64_t n_bound, const int32_t* node_
         CU_TRY(launch_free_reduce(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->st_bnode.as<int32_t>(),
                                   s->st_bcpu.as<int64_t>(), s->st_bmem.as<int64_t>(), n_bound, s->stream));
     }
-    CU_TRY(cudaStreamSynchronize(s->stream));
-    return KS_OK;
+    return check_range_and_prio(s, s->stream);
 }
 
 int ks_snapshot_apply_bind(ks_snapshot* s, int32_t node_idx, int64_t req_cpu, int64_t req_mem) {
@@ -263,13 +276,8 @@ int ks_snapshot_get_free(ks_snapshot* s, int64_t* free_cpu, int64_t* free_mem) {
 // rebuild what depends on free[]: range check, static priorities, bit-parallel index
 static int refresh_derived(ks_snapshot* s, cudaStream_t st) {
     if (!s->derived_dirty || s->N == 0) return KS_OK;
-    CU_TRY(cudaMemsetAsync(s->flag.p, 0, sizeof(int), st));
     CU_TRY(launch_node_prio(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->prio.as<int64_t>(), s->N, s->Npad,
                             s->flag.as<int>(), st));
-    int flag = 0;
-    CU_TRY(cudaMemcpyAsync(&flag, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    if (flag) return fail(KS_ERR_RANGE, "free resources of some node exceed +-2^36 millicores / +-2^55 bytes");
     cudaError_t e = bitpar_build(s->bp, node_table(s), s->prio.as<int64_t>(), st);
     if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel index build failed: %s", cudaGetErrorString(e));
     s->derived_dirty = false;
@@ -370,8 +378,14 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
     s->timing_valid = false;
     if (timing) CU_TRY(cudaEventRecord(s->ev[0], st));
 
-    rc = refresh_derived(s, st);
-    if (rc) return rc;
+    // the per-cell kernel needs no derived state; the bit-parallel index is (re)built lazily
+    const bool may_bitpar = (flags & KS_SELECT_FORCE_BITPAR) ||
+                            (!(flags & KS_SELECT_FORCE_DIRECT) && policy == KS_SCORE_LEFTOVER &&
+                             (uint64_t)P * s->N >= (1ull << 24));
+    if (may_bitpar) {
+        rc = refresh_derived(s, st);
+        if (rc) return rc;
+    }
 
     const bool out_host = out->mem_space == KS_MEM_HOST;
     const bool mask_host = out->mask && out->mask_space == KS_MEM_HOST;
@@ -417,7 +431,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         bool use_bitpar = false;
         if (flags & KS_SELECT_FORCE_BITPAR) use_bitpar = true;
         else if (!(flags & KS_SELECT_FORCE_DIRECT))
-            use_bitpar = policy == KS_SCORE_LEFTOVER && bitpar_profitable(s->bp, L.pv.P);
+            use_bitpar = may_bitpar && bitpar_profitable(s->bp, L.pv.P);
         if (timing && !use_bitpar) CU_TRY(cudaEventRecord(s->ev[1], st));
         if (use_bitpar) {
             cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
@@ -472,5 +486,89 @@ int ks_last_timings(ks_snapshot* s, float ms[3]) {
 }
 
 const char* ks_last_path(const ks_snapshot* s) { return s ? s->last_path : "none"; }
+
+int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n, const int32_t* claim_node, const int64_t* req_cpu,
+                              const int64_t* req_mem, uint8_t* out_accepted) {
+    if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
+    if (n && (!claim_node || !req_cpu || !req_mem || !out_accepted)) return fail(KS_ERR_INVALID, "NULL claim array");
+    if (n == 0) return KS_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    s->derived_dirty = true;
+    const uint32_t chunk = stream_max_claims();
+    CU_TRY(s->st_bnode.ensure(n * 4));
+    CU_TRY(s->st_bcpu.ensure(n * 8));
+    CU_TRY(s->st_bmem.ensure(n * 8));
+    CU_TRY(s->st_codes.ensure(n));
+    CU_TRY(cudaMemcpyAsync(s->st_bnode.p, claim_node, n * 4, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(cudaMemcpyAsync(s->st_bcpu.p, req_cpu, n * 8, cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(cudaMemcpyAsync(s->st_bmem.p, req_mem, n * 8, cudaMemcpyHostToDevice, s->stream));
+    // chunks run in arrival order on one stream: per-node arrival order is preserved across chunks
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - off);
+        CU_TRY(launch_stream_resolve(s->free_cpu.as<int64_t>(), s->free_mem.as<int64_t>(), s->st_bnode.as<int32_t>() + off,
+                                     s->st_bcpu.as<int64_t>() + off, s->st_bmem.as<int64_t>() + off, m, s->N,
+                                     s->st_codes.as<uint8_t>() + off, s->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(out_accepted, s->st_codes.p, n, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out_node_idx, int64_t* out_score,
+                   uint32_t* out_rounds) {
+    int rc = check_pods(s, pods);
+    if (rc) return rc;
+    if (pods->mem_space != KS_MEM_HOST) return fail(KS_ERR_INVALID, "ks_stream_bind takes host-space pods");
+    if (pods->n && !out_node_idx) return fail(KS_ERR_INVALID, "out_node_idx is NULL");
+    const uint64_t n = pods->n;
+    const uint32_t W = s->W;
+    std::vector<uint64_t> pending(n);
+    for (uint64_t i = 0; i < n; i++) {
+        pending[i] = i;
+        out_node_idx[i] = -1;
+        if (out_score) out_score[i] = 0;
+    }
+    std::vector<int64_t> rc_, rm_, score;
+    std::vector<uint64_t> sel;
+    std::vector<int32_t> idx;
+    std::vector<uint8_t> acc;
+    uint32_t rounds = 0;
+    while (!pending.empty() && rounds <= n + 1) {
+        const uint64_t m = pending.size();
+        rc_.resize(m);
+        rm_.resize(m);
+        sel.resize(m * W);
+        idx.resize(m);
+        score.resize(m);
+        acc.resize(m);
+        for (uint64_t k = 0; k < m; k++) {
+            const uint64_t p = pending[k];
+            rc_[k] = pods->req_cpu[p];
+            rm_[k] = pods->req_mem[p];
+            for (uint32_t w = 0; w < W; w++) sel[k * W + w] = pods->sel[p * W + w];
+        }
+        ks_pods kp{m, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
+        ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST};
+        rc = ks_select(s, &kp, policy, KS_SELECT_FORCE_DIRECT, &kb, nullptr); // claims against the current free[]
+        if (rc) return rc;
+        rc = ks_snapshot_commit_claims(s, m, idx.data(), rc_.data(), rm_.data(), acc.data());
+        if (rc) return rc;
+        std::vector<uint64_t> next;
+        for (uint64_t k = 0; k < m; k++) {
+            if (idx[k] < 0) continue; // no feasible node: NoNodeFound (src/main.rs:116-118)
+            if (acc[k]) {
+                out_node_idx[pending[k]] = idx[k];
+                if (out_score) out_score[pending[k]] = score[k];
+            } else {
+                next.push_back(pending[k]); // lost the node to an earlier pod of the batch: retry
+            }
+        }
+        pending.swap(next);
+        rounds++;
+    }
+    if (out_rounds) *out_rounds = rounds;
+    return KS_OK;
+}
 
 } // extern "C"

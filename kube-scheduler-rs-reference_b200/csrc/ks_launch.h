@@ -15,3 +15,9 @@ cudaError_t launch_select_direct(const SelectLaunch& L, const PartialView& part,
                                  uint32_t tiles_per_chunk);
 
 } // namespace ks
+
+namespace ks {
+cudaError_t launch_stream_resolve(int64_t* free_cpu, int64_t* free_mem, const int32_t* claim_node, const int64_t* req_cpu,
+                                  const int64_t* req_mem, uint32_t n, uint32_t N, uint8_t* accepted, cudaStream_t st);
+uint32_t stream_max_claims();
+} // namespace ks

@@ -57,3 +57,60 @@ def all_gather_bindings(local_buf, out_buf=None):
         out_buf = torch.empty(world * local_buf.numel(), dtype=torch.uint8, device=local_buf.device)
     dist.all_gather_into_tensor(out_buf, local_buf)
     return out_buf
+
+
+def stream_bind_distributed(snap, req_cpu, req_mem, sel, arrival, policy=0, max_rounds=64):
+    """Streaming micro-batch on `world` replicas (config C5 on several GPUs).  Every rank holds a full replica of
+    the snapshot and its own arrivals (`arrival` = globally unique, ordered ids).  Per round: local select (claims
+    against the replica's free[]), ONE all-gather of the claims, and every rank commits the identical union in
+    global arrival order (ks_snapshot_commit_claims) -> replicas stay bit-identical, capacity never over-commits.
+    `snap` needs .select(...)/.commit_claims(...) (ks.Snapshot; tests substitute an oracle-backed stand-in)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n = len(req_cpu)
+    req_cpu = np.asarray(req_cpu, np.int64)
+    req_mem = np.asarray(req_mem, np.int64)
+    sel = np.asarray(sel, np.uint64).reshape(n, -1)
+    arrival = np.asarray(arrival, np.int64)
+    out_idx = np.full(n, -1, np.int32)
+    pending = np.arange(n)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    rounds = 0
+    while rounds < max_rounds:
+        m = len(pending)
+        cap_t = torch.tensor([m], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+        cap = int(cap_t.item())
+        if cap == 0:
+            break
+        if m:
+            r = snap.select(req_cpu[pending], req_mem[pending], sel[pending], policy=policy, flags=1)  # per-cell kernel
+            idx = r.node_idx
+        else:
+            idx = np.zeros(0, np.int32)
+        claim = np.full((cap, 4), -1, np.int64)  # [arrival, node, cpu, mem]; arrival -1 = padding
+        claim[:m, 0] = arrival[pending]
+        claim[:m, 1] = idx
+        claim[:m, 2] = req_cpu[pending]
+        claim[:m, 3] = req_mem[pending]
+        mine = torch.from_numpy(claim).to(dev)
+        allc = torch.empty((world * cap, 4), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        allc = allc.cpu().numpy()
+        allc = allc[allc[:, 0] >= 0]
+        order = np.argsort(allc[:, 0], kind="stable")  # global arrival order
+        allc = allc[order]
+        acc = snap.commit_claims(allc[:, 1].astype(np.int32), allc[:, 2], allc[:, 3])
+        accepted = dict(zip(allc[:, 0].tolist(), acc.tolist()))
+        keep = []
+        for k, p in enumerate(pending):
+            if idx[k] < 0:
+                continue
+            if accepted[int(arrival[p])]:
+                out_idx[p] = idx[k]
+            else:
+                keep.append(p)
+        pending = np.asarray(keep, dtype=np.int64)
+        rounds += 1
+    return out_idx, rounds

@@ -155,6 +155,30 @@ class Snapshot:
         if rc != capi.KS_OK:
             raise KsError(rc, "ks_select")
 
+    def commit_claims(self, claim_node, req_cpu, req_mem):
+        """K3: accept claims per node in arrival order while they fit; decrements free[] on the device."""
+        claim_node = _c(claim_node, np.int32)
+        req_cpu = _c(req_cpu, np.int64)
+        req_mem = _c(req_mem, np.int64)
+        acc = np.zeros(claim_node.shape[0], np.uint8)
+        rc = lib.ks_snapshot_commit_claims(self._h, claim_node.shape[0], _ptr(claim_node), _ptr(req_cpu),
+                                           _ptr(req_mem), _ptr(acc))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_snapshot_commit_claims")
+        return acc
+
+    def stream_bind(self, req_cpu, req_mem, sel, policy=capi.KS_SCORE_LEFTOVER):
+        """One streaming micro-batch: select + commit rounds until every pod is bound or infeasible."""
+        pods, keep = self._pods(req_cpu, req_mem, sel)
+        p = int(pods.n)
+        idx = np.empty(p, np.int32)
+        score = np.empty(p, np.int64)
+        rounds = C.c_uint32()
+        rc = lib.ks_stream_bind(self._h, C.byref(pods), int(policy), _ptr(idx), _ptr(score), C.byref(rounds))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_stream_bind")
+        return idx, score, rounds.value
+
     def last_timings(self):
         ms = (C.c_float * 3)()
         rc = lib.ks_last_timings(self._h, ms)

@@ -569,3 +569,67 @@ int32_t orc_select_sampling(const orc_cluster* c, const ks_pod_obj* pod, uint32_
     if (cells_evaluated) *cells_evaluated = cells;
     return node;
 }
+
+/* ---- streaming restated (see oracle.h) ---- */
+int orc_commit_claims(uint32_t n_nodes, int64_t* free_cpu, int64_t* free_mem, uint64_t n_claims,
+                      const int32_t* claim_node, const int64_t* req_cpu, const int64_t* req_mem, uint8_t* accepted) {
+    for (uint64_t i = 0; i < n_claims; i++) {
+        int32_t n = claim_node[i];
+        accepted[i] = 0;
+        if (n < 0 || (uint32_t)n >= n_nodes) continue;
+        if (req_cpu[i] <= free_cpu[n] && req_mem[i] <= free_mem[n]) { /* predicates.rs:42 on what is left */
+            accepted[i] = 1;
+            free_cpu[n] -= req_cpu[i]; /* util.rs:33 */
+            free_mem[n] -= req_mem[i]; /* util.rs:34 */
+        }
+    }
+    return ORC_OK;
+}
+
+int orc_stream_bind_packed(uint32_t n_nodes, uint32_t W, int64_t* free_cpu, int64_t* free_mem,
+                           const int64_t* alloc_cpu, const int64_t* alloc_mem, const uint64_t* node_labels,
+                           uint64_t n_pods, const int64_t* req_cpu, const int64_t* req_mem, const uint64_t* pod_sel,
+                           int policy, int32_t* out_node_idx, int64_t* out_score, uint32_t* out_rounds) {
+    uint64_t* pending = (uint64_t*)malloc(sizeof(uint64_t) * (n_pods ? n_pods : 1));
+    int64_t* rc = (int64_t*)malloc(sizeof(int64_t) * (n_pods ? n_pods : 1));
+    int64_t* rm = (int64_t*)malloc(sizeof(int64_t) * (n_pods ? n_pods : 1));
+    int64_t* sc = (int64_t*)malloc(sizeof(int64_t) * (n_pods ? n_pods : 1));
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (n_pods ? n_pods : 1));
+    uint8_t* acc = (uint8_t*)malloc(n_pods ? n_pods : 1);
+    uint64_t* sel = (uint64_t*)malloc(sizeof(uint64_t) * (n_pods ? n_pods * W : 1));
+    if (!pending || !rc || !rm || !sc || !idx || !acc || !sel) return ORC_ERR_INVALID;
+    uint64_t m = n_pods;
+    for (uint64_t i = 0; i < n_pods; i++) {
+        pending[i] = i;
+        out_node_idx[i] = -1;
+        if (out_score) out_score[i] = 0;
+    }
+    uint32_t rounds = 0;
+    int err = ORC_OK;
+    while (m > 0 && rounds <= n_pods + 1) {
+        for (uint64_t k = 0; k < m; k++) {
+            rc[k] = req_cpu[pending[k]];
+            rm[k] = req_mem[pending[k]];
+            for (uint32_t w = 0; w < W; w++) sel[k * W + w] = pod_sel[pending[k] * W + w];
+        }
+        err = orc_run_packed(n_nodes, W, free_cpu, free_mem, alloc_cpu, alloc_mem, node_labels, m, rc, rm, sel, policy,
+                             idx, sc, NULL, NULL, 0, NULL, 1);
+        if (err) break;
+        orc_commit_claims(n_nodes, free_cpu, free_mem, m, idx, rc, rm, acc);
+        uint64_t next = 0;
+        for (uint64_t k = 0; k < m; k++) {
+            if (idx[k] < 0) continue;
+            if (acc[k]) {
+                out_node_idx[pending[k]] = idx[k];
+                if (out_score) out_score[pending[k]] = sc[k];
+            } else {
+                pending[next++] = pending[k];
+            }
+        }
+        m = next;
+        rounds++;
+    }
+    if (out_rounds) *out_rounds = rounds;
+    free(pending); free(rc); free(rm); free(sc); free(idx); free(acc); free(sel);
+    return err;
+}

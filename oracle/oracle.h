@@ -104,6 +104,17 @@ int orc_run_packed(uint32_t n_nodes, uint32_t label_words, const int64_t* free_c
 int32_t orc_select_sampling(const orc_cluster*, const ks_pod_obj* pod, uint32_t attempts, uint64_t* rng_state,
                             uint32_t* cells_evaluated);
 
+/* Streaming (config C5) restated: what the reference gets from re-LISTing per cell (src/predicates.rs:34-38).
+ * orc_commit_claims: claims in arrival (array) order; claim i is accepted iff its request still fits the
+ * node's remaining free (predicates.rs:42), then free -= request (util.rs:31-36).  claim_node < 0 = no claim.
+ * orc_stream_bind_packed: repeat {select for pending pods; commit; losers stay pending} until none pending. */
+int orc_commit_claims(uint32_t n_nodes, int64_t* free_cpu, int64_t* free_mem, uint64_t n_claims,
+                      const int32_t* claim_node, const int64_t* req_cpu, const int64_t* req_mem, uint8_t* accepted);
+int orc_stream_bind_packed(uint32_t n_nodes, uint32_t label_words, int64_t* free_cpu, int64_t* free_mem,
+                           const int64_t* alloc_cpu, const int64_t* alloc_mem, const uint64_t* node_labels,
+                           uint64_t n_pods, const int64_t* req_cpu, const int64_t* req_mem, const uint64_t* pod_sel,
+                           int policy, int32_t* out_node_idx, int64_t* out_score, uint32_t* out_rounds);
+
 int orc_online_cores(void);
 
 #ifdef __cplusplus

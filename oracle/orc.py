@@ -57,6 +57,11 @@ lib.orc_run_packed.argtypes = [C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, 
 lib.orc_select_sampling.restype = C.c_int32
 lib.orc_select_sampling.argtypes = [_vp, _vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
 lib.orc_online_cores.restype = C.c_int
+lib.orc_commit_claims.restype = C.c_int
+lib.orc_commit_claims.argtypes = [C.c_uint32, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp]
+lib.orc_stream_bind_packed.restype = C.c_int
+lib.orc_stream_bind_packed.argtypes = [C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, C.c_int,
+                                       _vp, _vp, C.POINTER(C.c_uint32)]
 
 
 def parse_quantity(s):
@@ -159,3 +164,33 @@ def run_packed(free_cpu, free_mem, alloc_cpu, alloc_mem, labels, req_cpu, req_me
     if rc:
         raise RuntimeError(f"orc_run_packed -> {rc}")
     return idx, score, cnt, mask, codes
+
+
+def commit_claims(free_cpu, free_mem, claim_node, req_cpu, req_mem):
+    """In-place on free_cpu/free_mem (int64 numpy); returns accepted uint8[n]."""
+    n = len(claim_node)
+    a = [np.ascontiguousarray(claim_node, np.int32), np.ascontiguousarray(req_cpu, np.int64),
+         np.ascontiguousarray(req_mem, np.int64)]
+    acc = np.zeros(n, np.uint8)
+    rc = lib.orc_commit_claims(free_cpu.shape[0], _p(free_cpu), _p(free_mem), n, _p(a[0]), _p(a[1]), _p(a[2]), _p(acc))
+    if rc:
+        raise RuntimeError(f"orc_commit_claims -> {rc}")
+    return acc
+
+
+def stream_bind_packed(free_cpu, free_mem, alloc_cpu, alloc_mem, labels, req_cpu, req_mem, sel, policy=0):
+    """In-place on free_cpu/free_mem; returns (node_idx, score, rounds)."""
+    N = free_cpu.shape[0]
+    P = len(req_cpu)
+    labels = np.ascontiguousarray(labels, np.uint64).reshape(N, -1)
+    W = labels.shape[1]
+    sel = np.ascontiguousarray(sel, np.uint64).reshape(P, W)
+    a = [np.ascontiguousarray(x, np.int64) for x in (alloc_cpu, alloc_mem, req_cpu, req_mem)]
+    idx = np.empty(P, np.int32)
+    score = np.empty(P, np.int64)
+    rounds = C.c_uint32()
+    rc = lib.orc_stream_bind_packed(N, W, _p(free_cpu), _p(free_mem), _p(a[0]), _p(a[1]), _p(labels), P, _p(a[2]),
+                                    _p(a[3]), _p(sel), policy, _p(idx), _p(score), C.byref(rounds))
+    if rc:
+        raise RuntimeError(f"orc_stream_bind_packed -> {rc}")
+    return idx, score, rounds.value

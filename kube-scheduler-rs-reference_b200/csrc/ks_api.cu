@@ -68,6 +68,12 @@ struct ks_snapshot {
     bool derived_dirty = true; // prio + bit-parallel index must be rebuilt before the next select
     const char* last_path = "none";
     BitparIndex bp;
+    // CUDA-graph replay of the launch sequence of an all-device ks_select (same arguments, same snapshot state)
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key[14] = {0};
+    bool graph_valid = false;
+    uint64_t graph_launches = 0; // kernels inside the cached graph
+    uint64_t version = 1; // bumped whenever device-side snapshot state or buffers change
     std::mutex mu;
 };
 
@@ -151,6 +157,7 @@ void ks_snapshot_destroy(ks_snapshot* s) {
                       &s->part_key,  &s->part_idx,  &s->part_cnt};
     for (DevBuf* b : bufs) b->release();
     bitpar_release(s->bp);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     for (int i = 0; i < 4; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -179,6 +186,7 @@ int ks_snapshot_set_nodes(ks_snapshot* s, uint32_t n_nodes, uint32_t label_words
     s->Npad = Npad;
     s->W = label_words;
     s->derived_dirty = true;
+    s->version++;
     if (Npad == 0) return KS_OK;
     std::vector<int64_t> h(Npad);
     std::vector<uint64_t> hl((size_t)Npad * label_words, 0);
@@ -228,6 +236,7 @@ int ks_snapshot_set_bound(ks_snapshot* s, uint64_t n_bound, const int32_t* node_
     std::lock_guard<std::mutex> lk(s->mu);
     CU_TRY(cudaSetDevice(s->device));
     s->derived_dirty = true;
+    s->version++;
     if (s->N == 0) return KS_OK;
     int rc = reset_free_to_alloc(s);
     if (rc) return rc;
@@ -250,6 +259,7 @@ int ks_snapshot_apply_bind(ks_snapshot* s, int32_t node_idx, int64_t req_cpu, in
     std::lock_guard<std::mutex> lk(s->mu);
     CU_TRY(cudaSetDevice(s->device));
     s->derived_dirty = true;
+    s->version++;
     CU_TRY(s->st_bnode.ensure(4));
     CU_TRY(s->st_bcpu.ensure(8));
     CU_TRY(s->st_bmem.ensure(8));
@@ -281,6 +291,7 @@ static int refresh_derived(ks_snapshot* s, cudaStream_t st) {
     cudaError_t e = bitpar_build(s->bp, node_table(s), s->prio.as<int64_t>(), st);
     if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel index build failed: %s", cudaGetErrorString(e));
     s->derived_dirty = false;
+    s->version++;
     return KS_OK;
 }
 
@@ -432,19 +443,18 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         if (flags & KS_SELECT_FORCE_BITPAR) use_bitpar = true;
         else if (!(flags & KS_SELECT_FORCE_DIRECT))
             use_bitpar = may_bitpar && bitpar_profitable(s->bp, L.pv.P);
-        if (timing && !use_bitpar) CU_TRY(cudaEventRecord(s->ev[1], st));
+        // everything that allocates happens before the (possibly captured) launch sequence
+        uint32_t n_chunks = 1, tiles_per_chunk = 0;
+        PartialView part{nullptr, nullptr, nullptr};
         if (use_bitpar) {
-            cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
-            if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
-            s->last_path = "bitpar";
+            cudaError_t e = bitpar_prepare(s->bp, L.pv.P);
+            if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel prepare failed: %s", cudaGetErrorString(e));
         } else {
             const uint32_t n_tiles = s->Npad / TILE_N;
             const uint32_t pod_ctas = (L.pv.P + direct_pods_per_cta(s->W) - 1) / direct_pods_per_cta(s->W);
-            uint32_t n_chunks = 1;
             if (pod_ctas < 2 * 148) n_chunks = std::min<uint32_t>(n_tiles, (2 * 148 + pod_ctas - 1) / pod_ctas);
-            const uint32_t tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+            tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
             n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
-            PartialView part{nullptr, nullptr, nullptr};
             if (n_chunks > 1) {
                 CU_TRY(s->part_key.ensure((size_t)n_chunks * P * 8));
                 CU_TRY(s->part_idx.ensure((size_t)n_chunks * P * 4));
@@ -453,10 +463,55 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                 part.idx = s->part_idx.as<int32_t>();
                 part.cnt = s->part_cnt.as<uint32_t>();
             }
-            cudaError_t e = launch_select_direct(L, part, n_chunks, tiles_per_chunk);
-            if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct select failed: %s", cudaGetErrorString(e));
-            if (timing) CU_TRY(cudaEventRecord(s->ev[2], st));
-            s->last_path = "direct";
+            cudaError_t e = prepare_select_direct(s->W);
+            if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct prepare failed: %s", cudaGetErrorString(e));
+        }
+        s->last_path = use_bitpar ? "bitpar" : "direct";
+        auto enqueue = [&]() -> int {
+            if (use_bitpar) {
+                cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
+                if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
+            } else {
+                if (timing) CU_TRY(cudaEventRecord(s->ev[1], st));
+                cudaError_t e = launch_select_direct(L, part, n_chunks, tiles_per_chunk);
+                if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct select failed: %s", cudaGetErrorString(e));
+                if (timing) CU_TRY(cudaEventRecord(s->ev[2], st));
+            }
+            return KS_OK;
+        };
+        const bool all_device = pods->mem_space == KS_MEM_DEVICE && !out_host && !mask_host;
+        if (all_device && !timing && !(flags & KS_SELECT_NO_GRAPH)) {
+            const uint64_t key[14] = {P, (uint64_t)pods->req_cpu, (uint64_t)pods->req_mem, (uint64_t)pods->sel,
+                                      (uint64_t)out->node_idx, (uint64_t)out->score, (uint64_t)out->feasible_cnt,
+                                      (uint64_t)out->mask, out->mask_row_bytes, (uint64_t)policy, (uint64_t)flags,
+                                      (uint64_t)st, s->version, (uint64_t)use_bitpar};
+            if (!(s->graph_valid && memcmp(key, s->graph_key, sizeof(key)) == 0)) {
+                if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+                s->graph_exec = nullptr;
+                s->graph_valid = false;
+                CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const uint64_t launches_before = g_launches.load();
+                const int erc = enqueue();
+                s->graph_launches = g_launches.load() - launches_before; // captured, not executed yet
+                g_launches -= s->graph_launches;
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (erc) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return erc;
+                }
+                if (e != cudaSuccess) return fail(KS_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+                e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) return fail(KS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+                memcpy(s->graph_key, key, sizeof(key));
+                s->graph_valid = true;
+            }
+            CU_TRY(cudaGraphLaunch(s->graph_exec, st));
+            g_launches += s->graph_launches;
+        } else {
+            rc = enqueue();
+            if (rc) return rc;
         }
     }
     if (out_host) {
@@ -495,6 +550,7 @@ int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n, const int32_t* claim_n
     std::lock_guard<std::mutex> lk(s->mu);
     CU_TRY(cudaSetDevice(s->device));
     s->derived_dirty = true;
+    s->version++;
     const uint32_t chunk = stream_max_claims();
     CU_TRY(s->st_bnode.ensure(n * 4));
     CU_TRY(s->st_bcpu.ensure(n * 8));

@@ -372,37 +372,48 @@ __global__ void __launch_bounds__(256)
             reinterpret_cast<const unsigned long long*>(blobP + lay.off_membM) + (size_t)(r.y >> 6) * lay.nt;
         const unsigned long long lowC = (1ull << (r.x & 63)) - 1ull, lowM = (1ull << (r.y & 63)) - 1ull;
         const uint4* pairs = reinterpret_cast<const uint4*>(blobP + lay.off_pairs);
-        for (uint32_t k = 0; k < lay.nt; k++) {
-            const uint32_t rankC = __ldg(baseC + k) + __popcll(__ldg(membC + k) & lowC);
-            const uint32_t rankM = __ldg(baseM + k) + __popcll(__ldg(membM + k) & lowM);
-            const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + (size_t)k * BP_TABLE_BYTES);
-            const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + (size_t)k * BP_TABLE_BYTES);
-            const uint4 c0 = __ldg(tc + table_chunk(rankC, 0)), c1 = __ldg(tc + table_chunk(rankC, 1));
-            const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
-            uint32_t m[8] = {c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w,
-                             c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w};
+        // 4 tiles per step: the independent loads of the four tiles overlap (the scan is latency-bound)
+        for (uint32_t k0 = 0; k0 < lay.nt && best < 0; k0 += 4) {
+            uint32_t m[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t k = min(k0 + u, lay.nt - 1);
+                const uint32_t rankC = __ldg(baseC + k) + __popcll(__ldg(membC + k) & lowC);
+                const uint32_t rankM = __ldg(baseM + k) + __popcll(__ldg(membM + k) & lowM);
+                const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + (size_t)k * BP_TABLE_BYTES);
+                const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + (size_t)k * BP_TABLE_BYTES);
+                const uint4 c0 = __ldg(tc + table_chunk(rankC, 0)), c1 = __ldg(tc + table_chunk(rankC, 1));
+                const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
+                m[u][0] = c0.x & m0.x; m[u][1] = c0.y & m0.y; m[u][2] = c0.z & m0.z; m[u][3] = c0.w & m0.w;
+                m[u][4] = c1.x & m1.x; m[u][5] = c1.y & m1.y; m[u][6] = c1.z & m1.z; m[u][7] = c1.w & m1.w;
+            }
 #pragma unroll
             for (int w = 0; w < W; w++) {
                 unsigned long long bits = sel[w];
                 while (bits) {
                     const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
                     bits &= bits - 1;
-                    const uint4 q0 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2);
-                    const uint4 q1 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2 + 1);
-                    m[0] &= q0.x; m[1] &= q0.y; m[2] &= q0.z; m[3] &= q0.w;
-                    m[4] &= q1.x; m[5] &= q1.y; m[6] &= q1.z; m[7] &= q1.w;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t k = min(k0 + u, lay.nt - 1);
+                        const uint4 q0 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2);
+                        const uint4 q1 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2 + 1);
+                        m[u][0] &= q0.x; m[u][1] &= q0.y; m[u][2] &= q0.z; m[u][3] &= q0.w;
+                        m[u][4] &= q1.x; m[u][5] &= q1.y; m[u][6] &= q1.z; m[u][7] &= q1.w;
+                    }
                 }
             }
             int first = -1;
 #pragma unroll
-            for (int j = 7; j >= 0; j--)
-                if (m[j]) first = j * 32 + __ffs(m[j]) - 1;
+            for (int u = 3; u >= 0; u--)
+#pragma unroll
+                for (int j = 7; j >= 0; j--)
+                    if (m[u][j] && k0 + u < lay.nt) first = (u * 8 + j) * 32 + __ffs(m[u][j]) - 1;
             if (first >= 0) {
-                const uint32_t slot = k * BP_TILE + first;
+                const uint32_t slot = k0 * BP_TILE + first;
                 best = __ldg(ord_idx + slot);
                 score = __ldg(ord_prio + slot) -
                         (int64_t)(((uint64_t)__ldg(pv.req_cpu + p) << 22) + (uint64_t)__ldg(pv.req_mem + p));
-                break;
             }
         }
     }
@@ -538,11 +549,14 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
 }
 
 template <int W>
-static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
+static cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(k_mask_bitpar<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+}
+
+// everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
+cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
     cudaError_t e;
-    const uint32_t P = L.pv.P;
-    if ((uint64_t)P * ix.lay.nt >= (1ull << 31)) return cudaErrorInvalidValue;
-    const bool need_mask_pass = L.ov.mask || L.ov.cnt;
+    if (!ix.valid) return cudaErrorNotSupported;
     if (ix.sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -550,13 +564,27 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
         if ((e = cudaStreamCreateWithFlags(&ix.aux, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ix.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaEventCreateWithFlags(&ix.ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = set_smem_attr<1>()) != cudaSuccess) return e;
+        if ((e = set_smem_attr<2>()) != cudaSuccess) return e;
+        if ((e = set_smem_attr<4>()) != cudaSuccess) return e;
+        if ((e = set_smem_attr<8>()) != cudaSuccess) return e;
     }
-    const int sms = ix.sms;
     if (P > ix.cap_pods) {
         const size_t cap = (size_t)P + P / 8 + 64;
         if ((e = regrow(ix.pod_ranks, cap)) != cudaSuccess) return e;
         ix.cap_pods = cap;
     }
+    return cudaSuccess;
+}
+
+template <int W>
+static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
+    cudaError_t e;
+    const uint32_t P = L.pv.P;
+    if ((uint64_t)P * ix.lay.nt >= (1ull << 31)) return cudaErrorInvalidValue;
+    if ((e = bitpar_prepare(ix, P)) != cudaSuccess) return e; // no-op when the caller prepared already
+    const bool need_mask_pass = L.ov.mask || L.ov.cnt;
+    const int sms = ix.sms;
     const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 4, ((uint64_t)P + 255) / 256);
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl,
                                                  ix.spl_stride, ix.pod_ranks,
@@ -582,12 +610,6 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
         const uint64_t units = (uint64_t)ix.lay.ncb * P;
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (units + 63) / 64);
         auto kern = k_mask_bitpar<W>;
-        static int smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (smem_set[W] < (int)ix.lay.blob_bytes) {
-            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024)) != cudaSuccess)
-                return e;
-            smem_set[W] = BP_SMEM_MAX;
-        }
         kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, L.pv, ix.pod_ranks, L.ov);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

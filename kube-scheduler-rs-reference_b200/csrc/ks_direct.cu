@@ -304,8 +304,7 @@ static cudaError_t launch_direct_t(const SelectLaunch& L, const PartialView& par
     using Cfg = DirectCfg<W, POLICY>;
     constexpr int PW = PodsPerWarp<W>::v;
     auto kern = k_select_direct<W, POLICY, EMIT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
     const uint32_t pods_per_cta = (DIRECT_THREADS / 32) * PW;
     dim3 grid((L.pv.P + pods_per_cta - 1) / pods_per_cta, n_chunks);
     kern<<<grid, DIRECT_THREADS, Cfg::SMEM_BYTES, L.stream>>>(L.nt, L.pv, L.ov, part, tiles_per_chunk);
@@ -329,6 +328,38 @@ static cudaError_t launch_direct_w(const SelectLaunch& L, const PartialView& par
                     : launch_direct_t<W, KS_SCORE_LEFTOVER, false>(L, part, n_chunks, tiles_per_chunk);
     return emit ? launch_direct_t<W, KS_SCORE_LEAST_ALLOCATED, true>(L, part, n_chunks, tiles_per_chunk)
                 : launch_direct_t<W, KS_SCORE_LEAST_ALLOCATED, false>(L, part, n_chunks, tiles_per_chunk);
+}
+
+template <int W>
+static cudaError_t prepare_w() {
+    cudaError_t e;
+#define KS_SET(P_, M_)                                                                                            \
+    if ((e = cudaFuncSetAttribute(k_select_direct<W, P_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                  (int)DirectCfg<W, P_>::SMEM_BYTES)) != cudaSuccess)                             \
+        return e;
+    KS_SET(KS_SCORE_LEFTOVER, true)
+    KS_SET(KS_SCORE_LEFTOVER, false)
+    KS_SET(KS_SCORE_LEAST_ALLOCATED, true)
+    KS_SET(KS_SCORE_LEAST_ALLOCATED, false)
+#undef KS_SET
+    return cudaSuccess;
+}
+
+// opt-in shared memory sizes, once per label width (must not run inside a stream capture)
+cudaError_t prepare_select_direct(uint32_t W) {
+    static bool done[9] = {false, false, false, false, false, false, false, false, false};
+    if (W > 8) return cudaErrorInvalidValue;
+    if (done[W]) return cudaSuccess;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (W) {
+        case 1: e = prepare_w<1>(); break;
+        case 2: e = prepare_w<2>(); break;
+        case 4: e = prepare_w<4>(); break;
+        case 8: e = prepare_w<8>(); break;
+        default: break;
+    }
+    if (e == cudaSuccess) done[W] = true;
+    return e;
 }
 
 uint32_t direct_pods_per_cta(uint32_t W) {

@@ -11,6 +11,7 @@ cudaError_t launch_node_prio(const int64_t* free_cpu, const int64_t* free_mem, i
 cudaError_t launch_check_cells(const NodeTable& nt, const PodView& pv, uint8_t* codes, uint32_t node_begin,
                                uint32_t node_count, cudaStream_t st);
 uint32_t direct_pods_per_cta(uint32_t W);
+cudaError_t prepare_select_direct(uint32_t W);
 cudaError_t launch_select_direct(const SelectLaunch& L, const PartialView& part, uint32_t n_chunks,
                                  uint32_t tiles_per_chunk);
 

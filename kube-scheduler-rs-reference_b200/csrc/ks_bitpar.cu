@@ -9,7 +9,7 @@
 //                                   2x(base + popc(member & low)) -> 2 table rows -> AND label columns ->
 //                                   two 128-bit stores of the mask row segment; counts by segmented warp
 //                                   shuffle + one RED per (pod, warp)
-//                  k_first_fit_bp   argmax KS_SCORE_LEFTOVER = first feasible node in priority order, found
+//                  k_first_fit_head/_tail  argmax KS_SCORE_LEFTOVER = first feasible node in priority order, found
 //                                   256 nodes at a time with the same table machinery (early exit)
 // Semantics per cell are exactly predicates.rs:42 / :45-61 (see include/ksched.h); only the evaluation
 // order differs, and every output is compared bit-for-bit with the oracle in tests/.
@@ -348,77 +348,132 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     }
 }
 
-// argmax of the separable score = first feasible node in descending priority order.  One thread per pod walks
-// the priority-ordered index 256 nodes per step (same rank + table + column machinery, read through L1/L2)
-// and stops at the first non-empty tile.  Pods whose feasible count is already known to be 0 are skipped.
+// ---- argmax of the separable score = first feasible node in descending priority order ----
+// The priority-ordered index (blobP) is read through L1/L2.  Phase 1 (k_first_fit_head): one thread per pod
+// looks at the two best tiles (512 best nodes) - enough for almost every pod; the rest is appended to a list.
+// Phase 2 (k_first_fit_tail): one warp per listed pod, one tile per lane, 32 tiles per step, ballot + early exit.
+struct PodThreshold {
+    const uint16_t* baseC;
+    const uint16_t* baseM;
+    const unsigned long long* membC;
+    const unsigned long long* membM;
+    unsigned long long lowC, lowM;
+};
+
+__device__ __forceinline__ PodThreshold pod_threshold(const uint8_t* __restrict__ blobP, const BitparLayout& lay, uint2 r) {
+    PodThreshold t;
+    t.baseC = reinterpret_cast<const uint16_t*>(blobP + lay.off_baseC) + (size_t)(r.x >> 6) * lay.nt;
+    t.baseM = reinterpret_cast<const uint16_t*>(blobP + lay.off_baseM) + (size_t)(r.y >> 6) * lay.nt;
+    t.membC = reinterpret_cast<const unsigned long long*>(blobP + lay.off_membC) + (size_t)(r.x >> 6) * lay.nt;
+    t.membM = reinterpret_cast<const unsigned long long*>(blobP + lay.off_membM) + (size_t)(r.y >> 6) * lay.nt;
+    t.lowC = (1ull << (r.x & 63)) - 1ull;
+    t.lowM = (1ull << (r.y & 63)) - 1ull;
+    return t;
+}
+
 template <int W>
-__global__ void __launch_bounds__(256)
-    k_first_fit_bp(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
-                   const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pv.P) return;
+__device__ __forceinline__ void ptile_mask(const uint8_t* __restrict__ blobP, const BitparLayout& lay, const PodThreshold& t,
+                                           const unsigned long long (&sel)[W], uint32_t k, uint32_t (&m)[8]) {
+    const uint32_t rankC = __ldg(t.baseC + k) + __popcll(__ldg(t.membC + k) & t.lowC);
+    const uint32_t rankM = __ldg(t.baseM + k) + __popcll(__ldg(t.membM + k) & t.lowM);
+    const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + (size_t)k * BP_TABLE_BYTES);
+    const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + (size_t)k * BP_TABLE_BYTES);
+    const uint4 c0 = __ldg(tc + table_chunk(rankC, 0)), c1 = __ldg(tc + table_chunk(rankC, 1));
+    const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
+    m[0] = c0.x & m0.x; m[1] = c0.y & m0.y; m[2] = c0.z & m0.z; m[3] = c0.w & m0.w;
+    m[4] = c1.x & m1.x; m[5] = c1.y & m1.y; m[6] = c1.z & m1.z; m[7] = c1.w & m1.w;
+    const uint4* pairs = reinterpret_cast<const uint4*>(blobP + lay.off_pairs);
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        unsigned long long bits = sel[w];
+        while (bits) {
+            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const uint4 q0 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2);
+            const uint4 q1 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2 + 1);
+            m[0] &= q0.x; m[1] &= q0.y; m[2] &= q0.z; m[3] &= q0.w;
+            m[4] &= q1.x; m[5] &= q1.y; m[6] &= q1.z; m[7] &= q1.w;
+        }
+    }
+}
+
+__device__ __forceinline__ int first_bit_256(const uint32_t (&m)[8]) {
+    int first = -1;
+#pragma unroll
+    for (int j = 7; j >= 0; j--)
+        if (m[j]) first = j * 32 + __ffs(m[j]) - 1;
+    return first;
+}
+
+__device__ __forceinline__ void write_binding(const OutView& ov, const PodView& pv, uint32_t p, int slot,
+                                              const int32_t* __restrict__ ord_idx, const int64_t* __restrict__ ord_prio) {
     int32_t best = -1;
     int64_t score = 0;
-    if (!(ov.cnt && ov.cnt[p] == 0)) {
-        const uint2 r = __ldg(rk + p);
-        unsigned long long sel[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
-        const uint16_t* baseC = reinterpret_cast<const uint16_t*>(blobP + lay.off_baseC) + (size_t)(r.x >> 6) * lay.nt;
-        const uint16_t* baseM = reinterpret_cast<const uint16_t*>(blobP + lay.off_baseM) + (size_t)(r.y >> 6) * lay.nt;
-        const unsigned long long* membC =
-            reinterpret_cast<const unsigned long long*>(blobP + lay.off_membC) + (size_t)(r.x >> 6) * lay.nt;
-        const unsigned long long* membM =
-            reinterpret_cast<const unsigned long long*>(blobP + lay.off_membM) + (size_t)(r.y >> 6) * lay.nt;
-        const unsigned long long lowC = (1ull << (r.x & 63)) - 1ull, lowM = (1ull << (r.y & 63)) - 1ull;
-        const uint4* pairs = reinterpret_cast<const uint4*>(blobP + lay.off_pairs);
-        // 4 tiles per step: the independent loads of the four tiles overlap (the scan is latency-bound)
-        for (uint32_t k0 = 0; k0 < lay.nt && best < 0; k0 += 4) {
-            uint32_t m[4][8];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t k = min(k0 + u, lay.nt - 1);
-                const uint32_t rankC = __ldg(baseC + k) + __popcll(__ldg(membC + k) & lowC);
-                const uint32_t rankM = __ldg(baseM + k) + __popcll(__ldg(membM + k) & lowM);
-                const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + (size_t)k * BP_TABLE_BYTES);
-                const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + (size_t)k * BP_TABLE_BYTES);
-                const uint4 c0 = __ldg(tc + table_chunk(rankC, 0)), c1 = __ldg(tc + table_chunk(rankC, 1));
-                const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
-                m[u][0] = c0.x & m0.x; m[u][1] = c0.y & m0.y; m[u][2] = c0.z & m0.z; m[u][3] = c0.w & m0.w;
-                m[u][4] = c1.x & m1.x; m[u][5] = c1.y & m1.y; m[u][6] = c1.z & m1.z; m[u][7] = c1.w & m1.w;
-            }
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                unsigned long long bits = sel[w];
-                while (bits) {
-                    const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t k = min(k0 + u, lay.nt - 1);
-                        const uint4 q0 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2);
-                        const uint4 q1 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2 + 1);
-                        m[u][0] &= q0.x; m[u][1] &= q0.y; m[u][2] &= q0.z; m[u][3] &= q0.w;
-                        m[u][4] &= q1.x; m[u][5] &= q1.y; m[u][6] &= q1.z; m[u][7] &= q1.w;
-                    }
-                }
-            }
-            int first = -1;
-#pragma unroll
-            for (int u = 3; u >= 0; u--)
-#pragma unroll
-                for (int j = 7; j >= 0; j--)
-                    if (m[u][j] && k0 + u < lay.nt) first = (u * 8 + j) * 32 + __ffs(m[u][j]) - 1;
-            if (first >= 0) {
-                const uint32_t slot = k0 * BP_TILE + first;
-                best = __ldg(ord_idx + slot);
-                score = __ldg(ord_prio + slot) -
-                        (int64_t)(((uint64_t)__ldg(pv.req_cpu + p) << 22) + (uint64_t)__ldg(pv.req_mem + p));
-            }
-        }
+    if (slot >= 0) {
+        best = __ldg(ord_idx + slot);
+        score = __ldg(ord_prio + slot) - (int64_t)(((uint64_t)__ldg(pv.req_cpu + p) << 22) + (uint64_t)__ldg(pv.req_mem + p));
     }
     if (ov.node_idx) ov.node_idx[p] = best;
     if (ov.score) ov.score[p] = score;
+}
+
+constexpr uint32_t FF_HEAD_TILES = 2;
+
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_first_fit_head(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
+                     const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov,
+                     uint32_t* __restrict__ tail_list, uint32_t* __restrict__ tail_count) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pv.P) return;
+    const PodThreshold t = pod_threshold(blobP, lay, __ldg(rk + p));
+    unsigned long long sel[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+    uint32_t m0[8], m1[8];
+    ptile_mask<W>(blobP, lay, t, sel, 0, m0);
+    ptile_mask<W>(blobP, lay, t, sel, min(1u, lay.nt - 1), m1);
+    int slot = first_bit_256(m0);
+    if (slot < 0 && lay.nt > 1) {
+        const int s1 = first_bit_256(m1);
+        if (s1 >= 0) slot = BP_TILE + s1;
+    }
+    if (slot >= 0 || lay.nt <= FF_HEAD_TILES) write_binding(ov, pv, p, slot, ord_idx, ord_prio);
+    else tail_list[atomicAdd(tail_count, 1u)] = p; // order of the list does not affect any result
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_first_fit_tail(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
+                     const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov,
+                     const uint32_t* __restrict__ tail_list, const uint32_t* __restrict__ tail_count) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t n = *tail_count;
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const uint32_t p = tail_list[i];
+        const PodThreshold t = pod_threshold(blobP, lay, __ldg(rk + p));
+        unsigned long long sel[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+        int slot = -1;
+        for (uint32_t k0 = FF_HEAD_TILES; k0 < lay.nt; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            int s = -1;
+            if (k < lay.nt) {
+                uint32_t m[8];
+                ptile_mask<W>(blobP, lay, t, sel, k, m);
+                s = first_bit_256(m);
+            }
+            const uint32_t b = __ballot_sync(0xffffffffu, s >= 0);
+            if (b) { // lowest tile index = highest priority
+                const int src = __ffs(b) - 1;
+                slot = (int)((k0 + src) * BP_TILE) + __shfl_sync(0xffffffffu, s, src);
+                break;
+            }
+        }
+        if (lane == 0) write_binding(ov, pv, p, slot, ord_idx, ord_prio);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -481,7 +536,7 @@ static cudaError_t regrow(T*& p, size_t count) {
 
 void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc,  ix.ord_fm,   ix.ord_prio,
-                    ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks};
+                    ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -572,6 +627,7 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
     if (P > ix.cap_pods) {
         const size_t cap = (size_t)P + P / 8 + 64;
         if ((e = regrow(ix.pod_ranks, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.tail_list, cap + 1)) != cudaSuccess) return e; // [cap] = the list length counter
         ix.cap_pods = cap;
     }
     return cudaSuccess;
@@ -596,12 +652,18 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
     if (want_bind) {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
-        OutView ovb = L.ov;
-        ovb.cnt = nullptr; // counts are being produced concurrently: scan without the "count == 0" shortcut
-        k_first_fit_bp<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
-                                                               ix.pod_ranks, ovb);
+        uint32_t* tail_count = ix.tail_list + ix.cap_pods;
+        if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), ix.aux)) != cudaSuccess) return e;
+        k_first_fit_head<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
+                                                                 ix.pod_ranks, L.ov, ix.tail_list, tail_count);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (ix.layP.nt > FF_HEAD_TILES) {
+            k_first_fit_tail<W><<<sms * 2, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
+                                                             ix.pod_ranks, L.ov, ix.tail_list, tail_count);
+            g_launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
         if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
     }
     if (need_mask_pass) {

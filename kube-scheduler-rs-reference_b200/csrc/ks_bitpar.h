@@ -45,6 +45,7 @@ struct BitparIndex {
     uint8_t* blobP = nullptr;    // one blob of layP.blob_bytes: priority order (tile k = priority ranks 256k..),
                                  // read through L1/L2 by k_first_fit_bp
     uint2* pod_ranks = nullptr;  // per-call scratch [P]
+    uint32_t* tail_list = nullptr; // per-call scratch [cap_pods + 1]: pods left for k_first_fit_tail, then the count
     size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_lab = 0;
     uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
     BitparLayout lay{}, layP{};

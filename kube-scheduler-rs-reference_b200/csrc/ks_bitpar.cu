@@ -65,6 +65,10 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// label-pair columns: [bit][tile][32 B] with a 16-byte skew per bit, so that lanes working on the same tile with
+// different required pairs fall into different 16-byte bank groups
+__host__ __device__ __forceinline__ uint32_t pair_stride(uint32_t nt) { return nt * 32u + 16u; }
+
 __device__ __forceinline__ uint32_t table_chunk(uint32_t row, uint32_t half) {
     // 16-byte chunk index of (row, half) inside a tile table; the XOR spreads the first halves of
     // consecutive rows over all eight 16-byte bank groups
@@ -153,8 +157,8 @@ __global__ void __launch_bounds__(288)
             running += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
-    // label-pair columns, layout [bit][tile][8 words]
-    uint4* pairs = reinterpret_cast<uint4*>(B + lay.off_pairs);
+    // label-pair columns, layout [bit][tile][8 words] (+16-byte skew per bit)
+    uint8_t* pairs = B + lay.off_pairs;
     for (uint32_t bit = s; bit < 64u * nt.W; bit += blockDim.x) {
         const uint32_t w_ = bit >> 6, sh = bit & 63;
         uint32_t w[8];
@@ -164,8 +168,9 @@ __global__ void __launch_bounds__(288)
             for (int b = 0; b < 32; b++) acc |= (uint32_t)((s_lab[w_][j * 32 + b] >> sh) & 1ull) << b;
             w[j] = acc;
         }
-        pairs[((size_t)bit * lay.nt + t) * 2 + 0] = make_uint4(w[0], w[1], w[2], w[3]);
-        pairs[((size_t)bit * lay.nt + t) * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        uint4* dst = reinterpret_cast<uint4*>(pairs + (size_t)bit * pair_stride(lay.nt) + (size_t)t * 32);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
 
@@ -187,11 +192,18 @@ __device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x
 
 // rank = number of nodes with free < request; nodes at sorted positions >= rank satisfy request <= free
 // (predicates.rs:42).  Two-level search: <=1024 splitters per resource in shared memory, then a window of
-// spl_stride-1 elements of the global sorted array.
+// spl_stride-1 elements of the global sorted array.  The pod is also dropped into bucket
+// (rank_cpu >> sh_c, rank_mem >> sh_m) of a <=64k-bin histogram: the counting sort that follows places pods with
+// equal or neighbouring thresholds next to each other, which is what lets the mask kernel share table rows.
+struct BucketParams {
+    uint32_t sh_c, sh_m, nb_m, n_bins;
+};
+
 __global__ void __launch_bounds__(256)
     k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM, uint32_t N,
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
-                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero) {
+                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, BucketParams bk, uint32_t* __restrict__ hist,
+                uint32_t* __restrict__ pod_bin, uint32_t* __restrict__ pod_loc) {
     __shared__ int64_t s_spl[2][1024];
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
@@ -215,19 +227,84 @@ __global__ void __launch_bounds__(256)
         }
         rk[p] = make_uint2(out[0], out[1]);
         if (cnt_zero) cnt_zero[p] = 0; // k_mask_bitpar accumulates feasible counts with REDs
+        if (hist) {
+            const uint32_t bin = (out[0] >> bk.sh_c) * bk.nb_m + (out[1] >> bk.sh_m);
+            pod_bin[p] = bin;
+            pod_loc[p] = atomicAdd(hist + bin, 1u); // arrival order inside a bin is irrelevant to every output
+        }
     }
 }
 
+// exclusive scan of the <=64k-bin histogram: CTA c scans bins [1024c, 1024c+1024) in place and publishes its
+// total; k_pod_scatter adds the prefix over the (<=64) chunk totals
+__global__ void __launch_bounds__(1024)
+    k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_bins, uint32_t* __restrict__ chunk_total) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t v = i < n_bins ? hist[i] : 0;
+    uint32_t inc = v;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= (uint32_t)off) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= (uint32_t)off) w += o;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (i < n_bins) hist[i] = inc - v + (warp ? s_warp[warp - 1] : 0);
+    if (threadIdx.x == 1023) chunk_total[blockIdx.x] = s_warp[31];
+}
+
+// counting-sort scatter: pods in bucket order with everything the mask kernel needs, contiguous
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_pod_scatter(PodView pv, const uint2* __restrict__ rk, const uint32_t* __restrict__ start,
+                  const uint32_t* __restrict__ chunk_total, uint32_t n_chunks, const uint32_t* __restrict__ pod_bin,
+                  const uint32_t* __restrict__ pod_loc, uint2* __restrict__ rk_s, uint32_t* __restrict__ pid_s,
+                  unsigned long long* __restrict__ sel_s) {
+    __shared__ uint32_t s_chunk[64];
+    if (threadIdx.x < 64) { // exclusive prefix over the <=64 chunk totals
+        uint32_t acc = 0;
+        for (uint32_t k = 0; k < threadIdx.x && k < n_chunks; k++) acc += chunk_total[k];
+        s_chunk[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pv.P) return;
+    const uint32_t bin = pod_bin[p];
+    const uint32_t q = start[bin] + s_chunk[bin >> 10] + pod_loc[p];
+    rk_s[q] = rk[p];
+    pid_s[q] = p;
+#pragma unroll
+    for (int w = 0; w < W; w++) sel_s[(size_t)q * W + w] = __ldg(pv.sel + (size_t)p * W + w);
+}
+
+// Mask kernel.  Pods arrive bucket-sorted by threshold (k_pod_scatter).  One warp = 8 consecutive sorted pods x
+// 4 tiles, tile index fastest: lanes 4j..4j+3 are one pod's 4 tiles and write 128 contiguous bytes of its mask
+// row with one 256-bit store each.  A shared-memory phase of a 128-bit load (8 lanes) is 2 neighbouring pods x 4
+// tiles: the 4 tiles sit in distinct bank groups (tile tables are skewed by 32 bytes) and the 2 pods read the same
+// or an adjacent row (identical addresses merge; adjacent rows are conflict-free by the chunk swizzle).
 template <int W>
 __global__ void __launch_bounds__(BP_THREADS, 1)
-    k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, PodView pv, const uint2* __restrict__ rk,
-                  OutView ov) {
+    k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
+                  const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s, OutView ov) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
 
-    const uint32_t tid = threadIdx.x, nt = lay.nt, P = pv.P;
-    // static split of the (column block, pod) units over the persistent CTAs
-    const uint64_t units = (uint64_t)lay.ncb * P;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, psub = lane >> 2, tsub = lane & 3;
+    const uint32_t nt = lay.nt;
+    const uint32_t n_groups = (P + 7) / 8; // groups of 8 sorted pods
+    const uint64_t units = (uint64_t)lay.ncb * n_groups;
     uint64_t u0 = units * blockIdx.x / gridDim.x;
     const uint64_t u1 = units * (blockIdx.x + 1) / gridDim.x;
     if (tid == 0) {
@@ -242,15 +319,13 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     const uint32_t a_membC = s_base + lay.off_membC, a_membM = s_base + lay.off_membM;
     const uint32_t a_tabC = s_base + lay.off_tabC, a_tabM = s_base + lay.off_tabM;
     const uint32_t a_pairs = s_base + lay.off_pairs;
-    const uint32_t nt_log2 = 31 - __clz(nt); // nt is a power of two (make_layout_smem)
-    const uint32_t dpl = BP_THREADS >> nt_log2;
     const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
 
     while (u0 < u1) {
-        const uint32_t cb = (uint32_t)(u0 / P);
-        const uint32_t pa = (uint32_t)(u0 - (uint64_t)cb * P);
-        const uint32_t pb = (uint32_t)min((uint64_t)P, u1 - (uint64_t)cb * P);
-        u0 = (uint64_t)cb * P + pb;
+        const uint32_t cb = (uint32_t)(u0 / n_groups);
+        const uint32_t ga = (uint32_t)(u0 - (uint64_t)cb * n_groups);
+        const uint32_t gb = (uint32_t)min((uint64_t)n_groups, u1 - (uint64_t)cb * n_groups);
+        u0 = (uint64_t)cb * n_groups + gb;
 
         // ---- stage this column block's index blob: TMA bulk copies signalled on one mbarrier ----
         __syncthreads(); // all generic-proxy reads of the previous blob are done
@@ -262,86 +337,92 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                 tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
         }
 
-        const uint32_t items = (pb - pa) * nt; // item i = (pod pa + i / nt, tile i % nt): lanes = adjacent tiles
-        uint32_t i = tid, pl = tid >> nt_log2;
-        const uint32_t t = tid & (nt - 1); // BP_THREADS is a multiple of nt: a thread keeps its tile
-        bool act = i < items;
-        uint2 r = act ? __ldg(rk + pa + pl) : make_uint2(0, 0); // prefetch while the blob is in flight
+        uint32_t g = ga + warp;
+        uint32_t q = g * 8 + psub;
+        bool act = g < gb && q < P;
+        uint2 r = act ? __ldg(rk_s + q) : make_uint2(0, 0); // prefetch while the blob is in flight
+        uint32_t pid = act ? __ldg(pid_s + q) : 0;
         unsigned long long sel[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) sel[w] = act ? __ldg(pv.sel + (size_t)(pa + pl) * W + w) : 0ull;
+        for (int w = 0; w < W; w++) sel[w] = act ? __ldg(sel_s + (size_t)q * W + w) : 0ull;
 
         mbar_wait(&bar, phase);
         phase ^= 1;
 
-        while ((i & ~31u) < items) { // warp-uniform trip count (shuffles below need the whole warp)
+        while (g < gb) { // warp-uniform
             const uint2 cr = r;
-            const uint32_t cpl = pl, ct = t;
+            const uint32_t cpid = pid;
             const bool cact = act;
             unsigned long long csel[W];
 #pragma unroll
             for (int w = 0; w < W; w++) csel[w] = sel[w];
-            // software prefetch of the next item's pod data
-            i += BP_THREADS;
-            pl += dpl;
-            act = i < items;
+            // software prefetch of the next group's pod data
+            g += BP_THREADS / 32;
+            q = g * 8 + psub;
+            act = g < gb && q < P;
             if (act) {
-                r = __ldg(rk + pa + pl);
+                r = __ldg(rk_s + q);
+                pid = __ldg(pid_s + q);
 #pragma unroll
-                for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)(pa + pl) * W + w);
+                for (int w = 0; w < W; w++) sel[w] = __ldg(sel_s + (size_t)q * W + w);
             }
 
-            uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-            if (cact) {
-                // tile-local rank of each threshold = tile nodes at global positions < threshold
-                const uint32_t ec = (cr.x >> 6) * nt + ct, em = (cr.y >> 6) * nt + ct;
-                uint32_t bc, bm;
-                unsigned long long mc, mm;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bc) : "r"(a_baseC + ec * 2));
-                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mc) : "r"(a_membC + ec * 8));
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bm) : "r"(a_baseM + em * 2));
-                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mm) : "r"(a_membM + em * 8));
-                const uint32_t rankC = bc + __popcll(mc & ((1ull << (cr.x & 63)) - 1ull));
-                const uint32_t rankM = bm + __popcll(mm & ((1ull << (cr.y & 63)) - 1ull));
-                const uint32_t tc = a_tabC + ct * BP_TABLE_BYTES, tm = a_tabM + ct * BP_TABLE_BYTES;
-                uint4 c0, c1, m0, m1;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(tc + table_chunk(rankC, 0) * 16));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(tc + table_chunk(rankC, 1) * 16));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m0.x), "=r"(m0.y), "=r"(m0.z), "=r"(m0.w) : "r"(tm + table_chunk(rankM, 0) * 16));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m1.x), "=r"(m1.y), "=r"(m1.z), "=r"(m1.w) : "r"(tm + table_chunk(rankM, 1) * 16));
-                a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
-                b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
+            uint32_t c = 0;
+            const uint32_t hc = (cr.x >> 6) * nt, hm = (cr.y >> 6) * nt;
+            const unsigned long long lowC = (1ull << (cr.x & 63)) - 1ull, lowM = (1ull << (cr.y & 63)) - 1ull;
+            for (uint32_t tb = 0; tb < nt; tb += 4) {
+                const uint32_t ct = tb + tsub;
+                if (cact && ct < nt) {
+                    // tile-local rank of each threshold = tile nodes at global positions < threshold
+                    uint32_t bc, bm;
+                    unsigned long long mc, mm;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bc) : "r"(a_baseC + (hc + ct) * 2));
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mc) : "r"(a_membC + (hc + ct) * 8));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bm) : "r"(a_baseM + (hm + ct) * 2));
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mm) : "r"(a_membM + (hm + ct) * 8));
+                    const uint32_t rankC = bc + __popcll(mc & lowC);
+                    const uint32_t rankM = bm + __popcll(mm & lowM);
+                    const uint32_t tc = a_tabC + ct * BP_TABLE_BYTES, tm = a_tabM + ct * BP_TABLE_BYTES;
+                    uint4 c0, c1, m0, m1;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(tc + table_chunk(rankC, 0) * 16));
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(tc + table_chunk(rankC, 1) * 16));
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m0.x), "=r"(m0.y), "=r"(m0.z), "=r"(m0.w) : "r"(tm + table_chunk(rankM, 0) * 16));
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m1.x), "=r"(m1.y), "=r"(m1.z), "=r"(m1.w) : "r"(tm + table_chunk(rankM, 1) * 16));
+                    uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
+                    uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    unsigned long long bits = csel[w];
-                    while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
-                        const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t pa_ = a_pairs + (bit * nt + ct) * 32;
-                        uint4 q0, q1;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(pa_));
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(pa_ + 16));
-                        a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
-                        b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
+                    for (int w = 0; w < W; w++) {
+                        unsigned long long bits = csel[w];
+                        while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
+                            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+                            bits &= bits - 1;
+                            const uint32_t pa_ = a_pairs + bit * pair_stride(nt) + ct * 32;
+                            uint4 q0, q1;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(pa_));
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(pa_ + 16));
+                            a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
+                            b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
+                        }
                     }
-                }
-                if (want_mask) {
-                    const uint32_t word = (cb * nt + ct) * 8;
-                    if (word < ov.mask_valid_words) {
-                        uint4* dst = reinterpret_cast<uint4*>(ov.mask + (size_t)(pa + cpl) * ov.mask_row_words + word);
-                        __stcs(dst, a);
-                        __stcs(dst + 1, b);
+                    c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
+                         __popc(b.w);
+                    if (want_mask) {
+                        const uint32_t word = (cb * nt + ct) * 8;
+                        if (word < ov.mask_valid_words) {
+                            uint32_t* dst = ov.mask + (size_t)cpid * ov.mask_row_words + word; // 32-byte aligned
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y),
+                                         "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                                         : "memory");
+                        }
                     }
                 }
             }
-            if (want_cnt) {
-                // the nt lanes of one pod are an aligned power-of-two group: xor butterfly, one RED per pod
-                uint32_t c = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) +
-                             __popc(b.z) + __popc(b.w);
-                for (uint32_t off = 1; off < nt; off <<= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-                if (cact && ct == 0) {
-                    if (lay.ncb == 1) ov.cnt[pa + cpl] = c; // single writer, no zero-init needed
-                    else if (c) atomicAdd(&ov.cnt[pa + cpl], c);
+            if (want_cnt) { // the 4 lanes of a pod are adjacent
+                c += __shfl_xor_sync(0xffffffffu, c, 1);
+                c += __shfl_xor_sync(0xffffffffu, c, 2);
+                if (cact && tsub == 0) {
+                    if (lay.ncb == 1) ov.cnt[cpid] = c; // single writer, no zero-init needed
+                    else if (c) atomicAdd(&ov.cnt[cpid], c);
                 }
             }
         }
@@ -382,15 +463,16 @@ __device__ __forceinline__ void ptile_mask(const uint8_t* __restrict__ blobP, co
     const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
     m[0] = c0.x & m0.x; m[1] = c0.y & m0.y; m[2] = c0.z & m0.z; m[3] = c0.w & m0.w;
     m[4] = c1.x & m1.x; m[5] = c1.y & m1.y; m[6] = c1.z & m1.z; m[7] = c1.w & m1.w;
-    const uint4* pairs = reinterpret_cast<const uint4*>(blobP + lay.off_pairs);
+    const uint8_t* pairs = blobP + lay.off_pairs;
 #pragma unroll
     for (int w = 0; w < W; w++) {
         unsigned long long bits = sel[w];
         while (bits) {
             const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
             bits &= bits - 1;
-            const uint4 q0 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2);
-            const uint4 q1 = __ldg(pairs + ((size_t)bit * lay.nt + k) * 2 + 1);
+            const uint4* col = reinterpret_cast<const uint4*>(pairs + (size_t)bit * pair_stride(lay.nt) + (size_t)k * 32);
+            const uint4 q0 = __ldg(col);
+            const uint4 q1 = __ldg(col + 1);
             m[0] &= q0.x; m[1] &= q0.y; m[2] &= q0.z; m[3] &= q0.w;
             m[4] &= q1.x; m[5] &= q1.y; m[6] &= q1.z; m[7] &= q1.w;
         }
@@ -480,7 +562,7 @@ __global__ void __launch_bounds__(256)
 static uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
 static uint64_t per_tile_bytes(uint32_t nb, uint32_t W) {
-    return (uint64_t)nb * 20 + 2ull * BP_TABLE_BYTES + 64ull * W * 32;
+    return (uint64_t)nb * 20 + 2ull * BP_TABLE_BYTES + 64ull * W * 32 + 64ull * W * 16; // last term: pair-column skew
 }
 
 static bool fill_offsets(BitparLayout* lay, uint32_t W) {
@@ -500,7 +582,7 @@ static bool fill_offsets(BitparLayout* lay, uint32_t W) {
     lay->off_tabM = off;
     off += (uint32_t)nt * BP_TABLE_BYTES;
     lay->off_pairs = off;
-    off += 64u * W * (uint32_t)nt * 32u;
+    off += 64u * W * pair_stride((uint32_t)nt);
     lay->blob_bytes = (off + 127u) & ~127u;
     return true;
 }
@@ -536,7 +618,8 @@ static cudaError_t regrow(T*& p, size_t count) {
 
 void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc,  ix.ord_fm,   ix.ord_prio,
-                    ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list};
+                    ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
+                    ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -628,8 +711,20 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         const size_t cap = (size_t)P + P / 8 + 64;
         if ((e = regrow(ix.pod_ranks, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.tail_list, cap + 1)) != cudaSuccess) return e; // [cap] = the list length counter
+        if ((e = regrow(ix.pod_bin, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.pod_loc, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_s, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.pid_s, cap)) != cudaSuccess) return e;
         ix.cap_pods = cap;
+        ix.cap_sel = 0;
     }
+    if ((size_t)P * ix.W > ix.cap_sel) {
+        const size_t cap = ((size_t)P + P / 8 + 64) * ix.W;
+        if ((e = regrow(ix.sel_s, cap)) != cudaSuccess) return e;
+        ix.cap_sel = cap;
+    }
+    if (!ix.hist)
+        if ((e = regrow(ix.hist, 65536 + 64)) != cudaSuccess) return e; // bins + chunk totals
     return cudaSuccess;
 }
 
@@ -641,10 +736,23 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
     if ((e = bitpar_prepare(ix, P)) != cudaSuccess) return e; // no-op when the caller prepared already
     const bool need_mask_pass = L.ov.mask || L.ov.cnt;
     const int sms = ix.sms;
+    // bucket grid over (rank_cpu, rank_mem): <= 64k bins, the finest shifts that fit
+    BucketParams bk{0, 0, 0, 0};
+    {
+        uint32_t sh = 0;
+        while ((uint64_t)((ix.N >> sh) + 1) * ((ix.N >> sh) + 1) > 65536ull) sh++;
+        bk.sh_c = sh;
+        bk.sh_m = (sh > 0 && (uint64_t)((ix.N >> sh) + 1) * ((ix.N >> (sh - 1)) + 1) <= 65536ull) ? sh - 1 : sh;
+        bk.nb_m = (ix.N >> bk.sh_m) + 1;
+        bk.n_bins = ((ix.N >> bk.sh_c) + 1) * bk.nb_m;
+    }
+    if (need_mask_pass)
+        if ((e = cudaMemsetAsync(ix.hist, 0, (size_t)bk.n_bins * 4, L.stream)) != cudaSuccess) return e;
     const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 4, ((uint64_t)P + 255) / 256);
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl,
                                                  ix.spl_stride, ix.pod_ranks,
-                                                 (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr);
+                                                 (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, bk,
+                                                 need_mask_pass ? ix.hist : nullptr, ix.pod_bin, ix.pod_loc);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // argmax scan on an auxiliary stream so that it overlaps the mask kernel (it needs only the pod ranks)
@@ -667,12 +775,20 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
         if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
     }
     if (need_mask_pass) {
+        const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 64
+        k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, ix.hist + 65536);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        k_pod_scatter<W><<<(P + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.pod_ranks, ix.hist, ix.hist + 65536, n_chunks,
+                                                                ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-        const uint64_t units = (uint64_t)ix.lay.ncb * P;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (units + 63) / 64);
+        const uint64_t units = (uint64_t)ix.lay.ncb * ((P + 7) / 8);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (units + 31) / 32);
         auto kern = k_mask_bitpar<W>;
-        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, L.pv, ix.pod_ranks, L.ov);
+        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)

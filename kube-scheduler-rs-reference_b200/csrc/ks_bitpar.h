@@ -46,7 +46,13 @@ struct BitparIndex {
                                  // read through L1/L2 by k_first_fit_bp
     uint2* pod_ranks = nullptr;  // per-call scratch [P]
     uint32_t* tail_list = nullptr; // per-call scratch [cap_pods + 1]: pods left for k_first_fit_tail, then the count
-    size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_lab = 0;
+    uint32_t* pod_bin = nullptr;   // per-call scratch: threshold bucket of each pod, slot inside the bucket
+    uint32_t* pod_loc = nullptr;
+    uint2* rk_s = nullptr;         // pods in bucket order: thresholds, original pod index, selector words
+    uint32_t* pid_s = nullptr;
+    unsigned long long* sel_s = nullptr;
+    uint32_t* hist = nullptr;      // [65536] bucket histogram -> exclusive scan
+    size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_lab = 0, cap_sel = 0;
     uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
     BitparLayout lay{}, layP{};
     bool valid = false;

@@ -314,11 +314,13 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     __syncthreads();
     uint32_t phase = 0;
 
-    const uint32_t s_base = smem_u32(smem);
-    const uint32_t a_baseC = s_base + lay.off_baseC, a_baseM = s_base + lay.off_baseM;
-    const uint32_t a_membC = s_base + lay.off_membC, a_membM = s_base + lay.off_membM;
-    const uint32_t a_tabC = s_base + lay.off_tabC, a_tabM = s_base + lay.off_tabM;
-    const uint32_t a_pairs = s_base + lay.off_pairs;
+    // plain shared-memory loads (not volatile asm): the two tile passes of a thread may overlap; the mbarrier wait
+    // below carries a memory clobber, so nothing is hoisted above it
+    const uint16_t* s_baseC = reinterpret_cast<const uint16_t*>(smem + lay.off_baseC);
+    const uint16_t* s_baseM = reinterpret_cast<const uint16_t*>(smem + lay.off_baseM);
+    const unsigned long long* s_membC = reinterpret_cast<const unsigned long long*>(smem + lay.off_membC);
+    const unsigned long long* s_membM = reinterpret_cast<const unsigned long long*>(smem + lay.off_membM);
+    const uint8_t* s_pairs = smem + lay.off_pairs;
     const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
 
     while (u0 < u1) {
@@ -374,20 +376,14 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                 const uint32_t ct = tb + tsub;
                 if (cact && ct < nt) {
                     // tile-local rank of each threshold = tile nodes at global positions < threshold
-                    uint32_t bc, bm;
-                    unsigned long long mc, mm;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bc) : "r"(a_baseC + (hc + ct) * 2));
-                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mc) : "r"(a_membC + (hc + ct) * 8));
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(bm) : "r"(a_baseM + (hm + ct) * 2));
-                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(mm) : "r"(a_membM + (hm + ct) * 8));
+                    const uint32_t bc = s_baseC[hc + ct], bm = s_baseM[hm + ct];
+                    const unsigned long long mc = s_membC[hc + ct], mm = s_membM[hm + ct];
                     const uint32_t rankC = bc + __popcll(mc & lowC);
                     const uint32_t rankM = bm + __popcll(mm & lowM);
-                    const uint32_t tc = a_tabC + ct * BP_TABLE_BYTES, tm = a_tabM + ct * BP_TABLE_BYTES;
-                    uint4 c0, c1, m0, m1;
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(tc + table_chunk(rankC, 0) * 16));
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(tc + table_chunk(rankC, 1) * 16));
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m0.x), "=r"(m0.y), "=r"(m0.z), "=r"(m0.w) : "r"(tm + table_chunk(rankM, 0) * 16));
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m1.x), "=r"(m1.y), "=r"(m1.z), "=r"(m1.w) : "r"(tm + table_chunk(rankM, 1) * 16));
+                    const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + ct * BP_TABLE_BYTES);
+                    const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + ct * BP_TABLE_BYTES);
+                    const uint4 c0 = tc[table_chunk(rankC, 0)], c1 = tc[table_chunk(rankC, 1)];
+                    const uint4 m0 = tm[table_chunk(rankM, 0)], m1 = tm[table_chunk(rankM, 1)];
                     uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
                     uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
 #pragma unroll
@@ -396,10 +392,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                         while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
                             const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
                             bits &= bits - 1;
-                            const uint32_t pa_ = a_pairs + bit * pair_stride(nt) + ct * 32;
-                            uint4 q0, q1;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(pa_));
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(pa_ + 16));
+                            const uint4* col = reinterpret_cast<const uint4*>(s_pairs + bit * pair_stride(nt) + ct * 32);
+                            const uint4 q0 = col[0], q1 = col[1];
                             a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
                             b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
                         }

@@ -295,6 +295,26 @@ static int refresh_derived(ks_snapshot* s, cudaStream_t st) {
     return KS_OK;
 }
 
+static int copy_pods_in(ks_snapshot* s, const ks_pods* pods, cudaStream_t st) {
+    if (pods->mem_space == KS_MEM_DEVICE) return KS_OK;
+    const uint64_t P = pods->n;
+    CU_TRY(cudaMemcpyAsync(s->st_rc.p, pods->req_cpu, P * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(s->st_rm.p, pods->req_mem, P * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(s->st_sel.p, pods->sel, P * 8 * s->W, cudaMemcpyHostToDevice, st));
+    return KS_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// passing st == nullptr only prepares (allocates staging, fills *pv); the copies are enqueued by copy_pods_in
 static int stage_pods(ks_snapshot* s, const ks_pods* pods, cudaStream_t st, PodView* pv) {
     const uint64_t P = pods->n;
     pv->P = (uint32_t)P;
@@ -307,13 +327,11 @@ static int stage_pods(ks_snapshot* s, const ks_pods* pods, cudaStream_t st, PodV
     CU_TRY(s->st_rc.ensure(P * 8));
     CU_TRY(s->st_rm.ensure(P * 8));
     CU_TRY(s->st_sel.ensure(P * 8 * s->W));
-    CU_TRY(cudaMemcpyAsync(s->st_rc.p, pods->req_cpu, P * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(s->st_rm.p, pods->req_mem, P * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(s->st_sel.p, pods->sel, P * 8 * s->W, cudaMemcpyHostToDevice, st));
     pv->req_cpu = s->st_rc.as<int64_t>();
     pv->req_mem = s->st_rm.as<int64_t>();
     pv->sel = s->st_sel.as<uint64_t>();
-    return KS_OK;
+    if (st == nullptr) return KS_OK; // prepare only: the caller enqueues the copies itself (copy_pods_in)
+    return copy_pods_in(s, pods, st);
 }
 
 static int check_pods(const ks_snapshot* s, const ks_pods* pods) {
@@ -430,11 +448,16 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         if (ov.node_idx) CU_TRY(cudaMemsetAsync(ov.node_idx, 0xff, P * 4, st));
         if (ov.score) CU_TRY(cudaMemsetAsync(ov.score, 0, P * 8, st));
         if (ov.cnt) CU_TRY(cudaMemsetAsync(ov.cnt, 0, P * 4, st));
+        if (out_host) {
+            if (out->node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
+            if (out->score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
+            if (out->feasible_cnt) CU_TRY(cudaMemcpyAsync(out->feasible_cnt, ov.cnt, P * 4, cudaMemcpyDeviceToHost, st));
+        }
         s->last_path = "empty";
     } else {
         SelectLaunch L;
         L.nt = node_table(s);
-        rc = stage_pods(s, pods, st, &L.pv);
+        rc = stage_pods(s, pods, nullptr, &L.pv); // prepare; copies are part of the (possibly captured) sequence
         if (rc) return rc;
         L.ov = ov;
         L.policy = policy;
@@ -468,6 +491,8 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         }
         s->last_path = use_bitpar ? "bitpar" : "direct";
         auto enqueue = [&]() -> int {
+            int crc = copy_pods_in(s, pods, st);
+            if (crc) return crc;
             if (use_bitpar) {
                 cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
                 if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
@@ -477,15 +502,35 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                 if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct select failed: %s", cudaGetErrorString(e));
                 if (timing) CU_TRY(cudaEventRecord(s->ev[2], st));
             }
+            if (out_host) {
+                if (out->node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
+                if (out->score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
+                if (out->feasible_cnt)
+                    CU_TRY(cudaMemcpyAsync(out->feasible_cnt, ov.cnt, P * 4, cudaMemcpyDeviceToHost, st));
+            }
+            if (mask_host)
+                CU_TRY(cudaMemcpyAsync(out->mask, ov.mask, P * out->mask_row_bytes, cudaMemcpyDeviceToHost, st));
             return KS_OK;
         };
-        const bool all_device = pods->mem_space == KS_MEM_DEVICE && !out_host && !mask_host;
-        if (all_device && !timing && !(flags & KS_SELECT_NO_GRAPH)) {
-            const uint64_t key[14] = {P, (uint64_t)pods->req_cpu, (uint64_t)pods->req_mem, (uint64_t)pods->sel,
-                                      (uint64_t)out->node_idx, (uint64_t)out->score, (uint64_t)out->feasible_cnt,
-                                      (uint64_t)out->mask, out->mask_row_bytes, (uint64_t)policy, (uint64_t)flags,
-                                      (uint64_t)st, s->version, (uint64_t)use_bitpar};
-            if (!(s->graph_valid && memcmp(key, s->graph_key, sizeof(key)) == 0)) {
+        // Replay from a cached CUDA graph when the call repeats (same buffers, same snapshot state).  Host buffers
+        // qualify only if they are pinned (a captured copy from pageable memory is not allowed).
+        const uint64_t key[14] = {P, (uint64_t)pods->req_cpu, (uint64_t)pods->req_mem, (uint64_t)pods->sel,
+                                  (uint64_t)out->node_idx, (uint64_t)out->score, (uint64_t)out->feasible_cnt,
+                                  (uint64_t)out->mask, out->mask_row_bytes,
+                                  (uint64_t)policy | ((uint64_t)pods->mem_space << 8) | ((uint64_t)out->mem_space << 9) |
+                                      ((uint64_t)out->mask_space << 10),
+                                  (uint64_t)flags, (uint64_t)st, s->version, (uint64_t)use_bitpar};
+        const bool key_hit = s->graph_valid && memcmp(key, s->graph_key, sizeof(key)) == 0;
+        bool graph_ok = !timing && !(flags & KS_SELECT_NO_GRAPH);
+        if (graph_ok && !key_hit) {
+            if (pods->mem_space == KS_MEM_HOST)
+                graph_ok = is_pinned_host(pods->req_cpu) && is_pinned_host(pods->req_mem) && is_pinned_host(pods->sel);
+            if (graph_ok && out_host)
+                graph_ok = is_pinned_host(out->node_idx) && is_pinned_host(out->score) && is_pinned_host(out->feasible_cnt);
+            if (graph_ok && mask_host) graph_ok = is_pinned_host(out->mask);
+        }
+        if (graph_ok) {
+            if (!key_hit) {
                 if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
                 s->graph_exec = nullptr;
                 s->graph_valid = false;
@@ -514,13 +559,6 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
             if (rc) return rc;
         }
     }
-    if (out_host) {
-        if (out->node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
-        if (out->score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
-        if (out->feasible_cnt) CU_TRY(cudaMemcpyAsync(out->feasible_cnt, ov.cnt, P * 4, cudaMemcpyDeviceToHost, st));
-    }
-    if (mask_host)
-        CU_TRY(cudaMemcpyAsync(out->mask, ov.mask, P * out->mask_row_bytes, cudaMemcpyDeviceToHost, st));
     if (timing) {
         CU_TRY(cudaEventRecord(s->ev[3], st));
         s->timing_valid = s->N != 0;

@@ -263,3 +263,59 @@ def test_config_c3_full_size_properties(ks, orc):
     o = _oracle(orc, sample, 0)
     assert np.array_equal(slab.node_idx[:2000], o[0]) and np.array_equal(slab.mask[:2000], o[3])
     assert np.array_equal(slab.feasible_cnt[:2000], o[2]) and np.array_equal(slab.score[:2000], o[1])
+
+
+def test_graph_replay_tracks_snapshot_changes(ks, orc):
+    """Repeated calls with identical buffers replay a cached CUDA graph (device and pinned-host buffers); any
+    snapshot mutation must invalidate it, and changed pod values in the same buffers must be honoured."""
+    import torch
+    cl = ks.synth.make(3000, 6000, seed=21)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    dev = torch.device("cuda:0")
+    row = ks.mask_row_bytes(cl.N)
+
+    def buffers(space):
+        if space == ks.KS_MEM_DEVICE:
+            mk = lambda a: torch.from_numpy(np.ascontiguousarray(a.view(np.int64))).to(dev)
+            out = lambda n, dt: torch.empty(n, dtype=dt, device=dev)
+        else:
+            mk = lambda a: torch.from_numpy(np.ascontiguousarray(a.view(np.int64))).pin_memory()
+            out = lambda n, dt: torch.empty(n, dtype=dt).pin_memory()
+        return [mk(rc), mk(rm), mk(sel)], out(cl.P, torch.int32), out(cl.P, torch.int64), out(cl.P, torch.int32)
+
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes(ac, am, lab)
+        snap.set_bound(bn, bc, bm)
+        mask = torch.zeros((cl.P, row), dtype=torch.uint8, device=dev)
+        for space in (ks.KS_MEM_DEVICE, ks.KS_MEM_HOST):
+            t, idx, score, cnt = buffers(space)
+            st = torch.cuda.Stream()
+
+            def run():
+                snap.select_raw(cl.P, t[0], t[1], t[2], space, idx, score, cnt, space, mask=mask, mask_row_bytes=row,
+                                mask_space=ks.KS_MEM_DEVICE, flags=ks.KS_SELECT_FORCE_BITPAR, stream=st.cuda_stream)
+                st.synchronize()
+                return idx.cpu().numpy().copy(), score.cpu().numpy().copy(), cnt.cpu().numpy().view(np.uint32).copy()
+
+            fc, fm = snap.free()
+            o = orc.run_packed(fc, fm, ac, am, lab, rc, rm, sel, want_mask=False)
+            for _ in range(3):  # capture, replay, replay
+                g = run()
+                assert all(np.array_equal(a, b) for a, b in zip(g, o[:3]))
+            # mutate the snapshot: the next call must see it
+            snap.apply_bind(int(o[0][o[0] >= 0][0]), 10_000_000, 1 << 40)
+            fc, fm = snap.free()
+            o2 = orc.run_packed(fc, fm, ac, am, lab, rc, rm, sel, want_mask=False)
+            g = run()
+            assert all(np.array_equal(a, b) for a, b in zip(g, o2[:3]))
+            assert not np.array_equal(o2[0], o[0])
+            # same buffers, new pod values: the graph replays with the new contents
+            rc2 = rc.copy()
+            rc2[::2] += 50
+            t[0].copy_(torch.from_numpy(rc2))
+            torch.cuda.synchronize()
+            o3 = orc.run_packed(fc, fm, ac, am, lab, rc2, rm, sel, want_mask=False)
+            g = run()
+            assert all(np.array_equal(a, b) for a, b in zip(g, o3[:3]))
+            t[0].copy_(torch.from_numpy(rc))
+            torch.cuda.synchronize()

@@ -52,16 +52,21 @@ def main():
     bound = 0
     nxt = 0
     t0 = time.perf_counter()
-    while nxt < len(ids):
+    while True:
         now = time.perf_counter() - t0
         hi = int(np.searchsorted(t_arr[ids], now, side="right"))
-        if hi == nxt and world == 1:
-            continue  # nothing has arrived yet
+        if world == 1:
+            if nxt >= len(ids):
+                break
+            if hi == nxt:
+                continue  # nothing has arrived yet
         b = ids[nxt:hi]
+        all_done = False
         if world == 1:
             idx, _, rounds = snap.stream_bind(rc[b], rm[b], sel[b], policy=policy)
-        else:
-            idx, rounds = ks.multigpu.stream_bind_distributed(snap, rc[b], rm[b], sel[b], b, policy=policy)
+        else:  # lockstep over ranks: a rank without arrivals takes part with an empty batch
+            idx, rounds, all_done = ks.multigpu.stream_bind_distributed(snap, rc[b], rm[b], sel[b], b, policy=policy,
+                                                                        done=hi >= len(ids))
         done = time.perf_counter() - t0
         if len(b):
             lat.extend((done - t_arr[b]).tolist())
@@ -69,10 +74,8 @@ def main():
             rounds_l.append(rounds)
             bound += int((idx >= 0).sum())
         nxt = hi
-    if world > 1:
-        # drain: the other ranks may still have rounds to run
-        for _ in range(3):
-            ks.multigpu.stream_bind_distributed(snap, rc[:0], rm[:0], sel[:0], ids[:0], policy=policy)
+        if world > 1 and all_done:
+            break
     total = time.perf_counter() - t0
     lat_ms = np.asarray(lat) * 1e3
     fc, fm = snap.free()

@@ -59,11 +59,13 @@ def all_gather_bindings(local_buf, out_buf=None):
     return out_buf
 
 
-def stream_bind_distributed(snap, req_cpu, req_mem, sel, arrival, policy=0, max_rounds=64):
+def stream_bind_distributed(snap, req_cpu, req_mem, sel, arrival, policy=0, max_rounds=64, done=True):
     """Streaming micro-batch on `world` replicas (config C5 on several GPUs).  Every rank holds a full replica of
     the snapshot and its own arrivals (`arrival` = globally unique, ordered ids).  Per round: local select (claims
     against the replica's free[]), ONE all-gather of the claims, and every rank commits the identical union in
     global arrival order (ks_snapshot_commit_claims) -> replicas stay bit-identical, capacity never over-commits.
+    All ranks must call this in lockstep (a rank without arrivals passes empty arrays); `done` says that this rank
+    has no further arrivals.  Returns (node_idx, rounds, all_ranks_done).
     `snap` needs .select(...)/.commit_claims(...) (ks.Snapshot; tests substitute an oracle-backed stand-in)."""
     import torch
     import torch.distributed as dist
@@ -71,17 +73,19 @@ def stream_bind_distributed(snap, req_cpu, req_mem, sel, arrival, policy=0, max_
     n = len(req_cpu)
     req_cpu = np.asarray(req_cpu, np.int64)
     req_mem = np.asarray(req_mem, np.int64)
-    sel = np.asarray(sel, np.uint64).reshape(n, -1)
+    sel = np.asarray(sel, np.uint64)
+    sel = sel.reshape(n, sel.shape[-1] if sel.ndim > 1 else 1)
     arrival = np.asarray(arrival, np.int64)
     out_idx = np.full(n, -1, np.int32)
     pending = np.arange(n)
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     rounds = 0
+    all_done = False
     while rounds < max_rounds:
         m = len(pending)
-        cap_t = torch.tensor([m], dtype=torch.int64, device=dev)
-        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
-        cap = int(cap_t.item())
+        head = torch.tensor([m, 0 if done else 1], dtype=torch.int64, device=dev)
+        dist.all_reduce(head, op=dist.ReduceOp.MAX)
+        cap, all_done = int(head[0].item()), int(head[1].item()) == 0
         if cap == 0:
             break
         if m:
@@ -113,4 +117,4 @@ def stream_bind_distributed(snap, req_cpu, req_mem, sel, arrival, policy=0, max_
                 keep.append(p)
         pending = np.asarray(keep, dtype=np.int64)
         rounds += 1
-    return out_idx, rounds
+    return out_idx, rounds, all_done

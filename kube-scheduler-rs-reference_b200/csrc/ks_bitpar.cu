@@ -285,21 +285,8 @@ __global__ void __launch_bounds__(256)
     const uint32_t q = start[bin] + s_chunk[bin >> 10] + pod_loc[p];
     rk_s[q] = rk[p];
     pid_s[q] = p;
-    // required (key,value) bits as a packed list: [count:4 | 6 x 10-bit indices]; count 15 = more than 6 bits,
-    // the mask kernel then walks the selector words of the pod itself
-    unsigned long long lst = 0;
-    uint32_t n = 0;
 #pragma unroll
-    for (int w = 0; w < W; w++) {
-        unsigned long long bits = __ldg(pv.sel + (size_t)p * W + w);
-        while (bits) {
-            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            if (n < 6) lst |= (unsigned long long)bit << (10 * n);
-            n++;
-        }
-    }
-    sel_s[q] = lst | ((unsigned long long)(n <= 6 ? n : 15) << 60);
+    for (int w = 0; w < W; w++) sel_s[(size_t)q * W + w] = __ldg(pv.sel + (size_t)p * W + w);
 }
 
 // Mask kernel.  Pods arrive bucket-sorted by threshold (k_pod_scatter).  One warp = 8 consecutive sorted pods x
@@ -310,8 +297,7 @@ __global__ void __launch_bounds__(256)
 template <int W>
 __global__ void __launch_bounds__(BP_THREADS, 1)
     k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
-                  const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s,
-                  const unsigned long long* __restrict__ sel_words, OutView ov) {
+                  const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s, OutView ov) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
 
@@ -353,64 +339,57 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                 tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
         }
 
-        // Pod data of group g (8 sorted pods, one per 4 lanes).  Indices are clamped instead of predicated so that the
-        // loop body is branch-free: only the stores depend on `act`.
         uint32_t g = ga + warp;
-        uint32_t q = min(g * 8 + psub, P - 1);
-        bool act = g < gb && g * 8 + psub < P;
-        uint2 r = __ldg(rk_s + q); // prefetch while the blob is in flight
-        uint32_t pid = __ldg(pid_s + q);
-        unsigned long long lst = __ldg(sel_s + q);
+        uint32_t q = g * 8 + psub;
+        bool act = g < gb && q < P;
+        uint2 r = act ? __ldg(rk_s + q) : make_uint2(0, 0); // prefetch while the blob is in flight
+        uint32_t pid = act ? __ldg(pid_s + q) : 0;
+        unsigned long long sel[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) sel[w] = act ? __ldg(sel_s + (size_t)q * W + w) : 0ull;
 
         mbar_wait(&bar, phase);
         phase ^= 1;
 
-        const uint32_t word0 = (cb * nt + tsub) * 8; // first mask word of this lane's tile in pass 0
-        while (g < gb) {                             // warp-uniform
+        while (g < gb) { // warp-uniform
             const uint2 cr = r;
             const uint32_t cpid = pid;
             const bool cact = act;
-            const unsigned long long clst = lst;
+            unsigned long long csel[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) csel[w] = sel[w];
             // software prefetch of the next group's pod data
             g += BP_THREADS / 32;
-            q = min(g * 8 + psub, P - 1);
-            act = g < gb && g * 8 + psub < P;
-            r = __ldg(rk_s + q);
-            pid = __ldg(pid_s + q);
-            lst = __ldg(sel_s + q);
+            q = g * 8 + psub;
+            act = g < gb && q < P;
+            if (act) {
+                r = __ldg(rk_s + q);
+                pid = __ldg(pid_s + q);
+#pragma unroll
+                for (int w = 0; w < W; w++) sel[w] = __ldg(sel_s + (size_t)q * W + w);
+            }
 
             uint32_t c = 0;
             const uint32_t hc = (cr.x >> 6) * nt, hm = (cr.y >> 6) * nt;
             const unsigned long long lowC = (1ull << (cr.x & 63)) - 1ull, lowM = (1ull << (cr.y & 63)) - 1ull;
-            const uint32_t n_bits = (uint32_t)(clst >> 60);
-            uint32_t* const row = ov.mask + (size_t)cpid * ov.mask_row_words + word0;
             for (uint32_t tb = 0; tb < nt; tb += 4) {
-                const uint32_t ct = min(tb + tsub, nt - 1); // nt < 4 only for tiny clusters: redundant lanes, not stored
-                // tile-local rank of each threshold = tile nodes at global positions < threshold
-                const uint32_t bc = s_baseC[hc + ct], bm = s_baseM[hm + ct];
-                const unsigned long long mc = s_membC[hc + ct], mm = s_membM[hm + ct];
-                const uint32_t rankC = bc + __popcll(mc & lowC);
-                const uint32_t rankM = bm + __popcll(mm & lowM);
-                const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + ct * BP_TABLE_BYTES);
-                const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + ct * BP_TABLE_BYTES);
-                const uint4 c0 = tc[table_chunk(rankC, 0)], c1 = tc[table_chunk(rankC, 1)];
-                const uint4 m0 = tm[table_chunk(rankM, 0)], m1 = tm[table_chunk(rankM, 1)];
-                uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
-                uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
-                // AND the node column of every required (key,value) pair (predicates.rs:48-53)
-                if (n_bits != 15) {
-                    unsigned long long l = clst;
-                    for (uint32_t j = 0; j < n_bits; j++, l >>= 10) {
-                        const uint4* col = reinterpret_cast<const uint4*>(s_pairs + ((uint32_t)l & 1023u) * pair_stride(nt) + ct * 32);
-                        const uint4 q0 = col[0], q1 = col[1];
-                        a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
-                        b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
-                    }
-                } else {
-#pragma unroll 1
+                const uint32_t ct = tb + tsub;
+                if (cact && ct < nt) {
+                    // tile-local rank of each threshold = tile nodes at global positions < threshold
+                    const uint32_t bc = s_baseC[hc + ct], bm = s_baseM[hm + ct];
+                    const unsigned long long mc = s_membC[hc + ct], mm = s_membM[hm + ct];
+                    const uint32_t rankC = bc + __popcll(mc & lowC);
+                    const uint32_t rankM = bm + __popcll(mm & lowM);
+                    const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + ct * BP_TABLE_BYTES);
+                    const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + ct * BP_TABLE_BYTES);
+                    const uint4 c0 = tc[table_chunk(rankC, 0)], c1 = tc[table_chunk(rankC, 1)];
+                    const uint4 m0 = tm[table_chunk(rankM, 0)], m1 = tm[table_chunk(rankM, 1)];
+                    uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
+                    uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
+#pragma unroll
                     for (int w = 0; w < W; w++) {
-                        unsigned long long bits = __ldg(sel_words + (size_t)cpid * W + w);
-                        while (bits) {
+                        unsigned long long bits = csel[w];
+                        while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
                             const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
                             bits &= bits - 1;
                             const uint4* col = reinterpret_cast<const uint4*>(s_pairs + bit * pair_stride(nt) + ct * 32);
@@ -419,15 +398,18 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                             b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
                         }
                     }
+                    c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
+                         __popc(b.w);
+                    if (want_mask) {
+                        const uint32_t word = (cb * nt + ct) * 8;
+                        if (word < ov.mask_valid_words) {
+                            uint32_t* dst = ov.mask + (size_t)cpid * ov.mask_row_words + word; // 32-byte aligned
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y),
+                                         "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                                         : "memory");
+                        }
+                    }
                 }
-                const bool keep = cact && tb + tsub < nt;
-                c += keep ? __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
-                                __popc(b.w)
-                          : 0u;
-                if (want_mask && keep && word0 + tb * 8 < ov.mask_valid_words)
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(row + tb * 8), "r"(a.x), "r"(a.y),
-                                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                                 : "memory");
             }
             if (want_cnt) { // the 4 lanes of a pod are adjacent
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -730,8 +712,8 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         ix.cap_pods = cap;
         ix.cap_sel = 0;
     }
-    if ((size_t)P > ix.cap_sel) { // one packed selector list per pod
-        const size_t cap = (size_t)P + P / 8 + 64;
+    if ((size_t)P * ix.W > ix.cap_sel) {
+        const size_t cap = ((size_t)P + P / 8 + 64) * ix.W;
         if ((e = regrow(ix.sel_s, cap)) != cudaSuccess) return e;
         ix.cap_sel = cap;
     }
@@ -800,8 +782,7 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
         const uint64_t units = (uint64_t)ix.lay.ncb * ((P + 7) / 8);
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (units + 31) / 32);
         auto kern = k_mask_bitpar<W>;
-        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s,
-                                                                reinterpret_cast<const unsigned long long*>(L.pv.sel), L.ov);
+        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)

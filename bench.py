@@ -355,8 +355,14 @@ def main():
     peak, peak_src = hbm_peak()
     k_ms = sum(kern_ms) / len(kern_ms)
     achieved = ab["dominant_kernel"] / (k_ms * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}_{snap.last_path()}")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": snap.last_path(), "kernel_ms": k_ms, "rest_of_step_ms": sum(scan_ms) / len(scan_ms),
+                "traffic": traffic, "kernel": snap.last_path(), "kernel_ms": k_ms, "rest_of_step_ms": sum(scan_ms) / len(scan_ms),
                 "algorithmic_bytes": ab["dominant_kernel"], "peak_source": peak_src}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -283,6 +283,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident(False)
         step_e2e()
+    # The timed region lasts only a few ms, shorter than nvidia-smi's sampling period, so the same step is kept
+    # running (untimed) for ~0.4 s right before it: the clock / throttle samples are taken under exactly this load.
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < 0.4:
+        step_resident(False)
+        stream.synchronize()
     barrier()
 
     # ---- timed: K resident steps (CUDA events on the launching stream, L2 flushed between iterations) ----
@@ -374,6 +380,7 @@ def main():
             "label_words": W, "bound_pods": cl.B, "seed": hex(seed), "path": snap.last_path(),
             "parallelism": f"pods sharded x{world}, node table replicated" + (", 1 NCCL all-gather of bindings/step" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": t_wall,
+            "clocks_window": "0.4 s untimed soak of the same step + both timed loops (timed region alone is a few ms)",
             "call_ms_inside_library": sum(call_ms) / len(call_ms),
         },
         "clocks": clocks,

@@ -493,6 +493,8 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         auto enqueue = [&]() -> int {
             int crc = copy_pods_in(s, pods, st);
             if (crc) return crc;
+            L.host_node_idx = out_host ? out->node_idx : nullptr; // served early by the launcher when it can
+            L.host_score = out_host ? out->score : nullptr;
             if (use_bitpar) {
                 cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
                 if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
@@ -503,8 +505,8 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                 if (timing) CU_TRY(cudaEventRecord(s->ev[2], st));
             }
             if (out_host) {
-                if (out->node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
-                if (out->score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
+                if (L.host_node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
+                if (L.host_score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
                 if (out->feasible_cnt)
                     CU_TRY(cudaMemcpyAsync(out->feasible_cnt, ov.cnt, P * 4, cudaMemcpyDeviceToHost, st));
             }

@@ -196,7 +196,8 @@ __device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x
 // (rank_cpu >> sh_c, rank_mem >> sh_m) of a <=64k-bin histogram: the counting sort that follows places pods with
 // equal or neighbouring thresholds next to each other, which is what lets the mask kernel share table rows.
 struct BucketParams {
-    uint32_t sh_c, sh_m, nb_m, n_bins;
+    uint32_t sh_c, sh_m, nb_m, n_bins; // n_bins = 4 selector classes x threshold grid
+    uint32_t grid_bins, W;
 };
 
 __global__ void __launch_bounds__(256)
@@ -228,7 +229,11 @@ __global__ void __launch_bounds__(256)
         rk[p] = make_uint2(out[0], out[1]);
         if (cnt_zero) cnt_zero[p] = 0; // k_mask_bitpar accumulates feasible counts with REDs
         if (hist) {
-            const uint32_t bin = (out[0] >> bk.sh_c) * bk.nb_m + (out[1] >> bk.sh_m);
+            // most significant key: number of required label pairs (0,1,2,3+), so that the lanes of a warp run the
+            // same number of column ANDs in the mask kernel (no divergence in its selector loop)
+            uint32_t n_req = 0;
+            for (uint32_t w = 0; w < bk.W; w++) n_req += __popcll(__ldg(pv.sel + (size_t)p * bk.W + w));
+            const uint32_t bin = min(n_req, 3u) * bk.grid_bins + (out[0] >> bk.sh_c) * bk.nb_m + (out[1] >> bk.sh_m);
             pod_bin[p] = bin;
             pod_loc[p] = atomicAdd(hist + bin, 1u); // arrival order inside a bin is irrelevant to every output
         }
@@ -723,7 +728,7 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
 }
 
 template <int W>
-static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
+static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
     cudaError_t e;
     const uint32_t P = L.pv.P;
     if ((uint64_t)P * ix.lay.nt >= (1ull << 31)) return cudaErrorInvalidValue;
@@ -731,14 +736,15 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
     const bool need_mask_pass = L.ov.mask || L.ov.cnt;
     const int sms = ix.sms;
     // bucket grid over (rank_cpu, rank_mem): <= 64k bins, the finest shifts that fit
-    BucketParams bk{0, 0, 0, 0};
+    BucketParams bk{0, 0, 0, 0, 0, ix.W};
     {
         uint32_t sh = 0;
-        while ((uint64_t)((ix.N >> sh) + 1) * ((ix.N >> sh) + 1) > 65536ull) sh++;
+        while ((uint64_t)((ix.N >> sh) + 1) * ((ix.N >> sh) + 1) > 16384ull) sh++;
         bk.sh_c = sh;
-        bk.sh_m = (sh > 0 && (uint64_t)((ix.N >> sh) + 1) * ((ix.N >> (sh - 1)) + 1) <= 65536ull) ? sh - 1 : sh;
+        bk.sh_m = (sh > 0 && (uint64_t)((ix.N >> sh) + 1) * ((ix.N >> (sh - 1)) + 1) <= 16384ull) ? sh - 1 : sh;
         bk.nb_m = (ix.N >> bk.sh_m) + 1;
-        bk.n_bins = ((ix.N >> bk.sh_c) + 1) * bk.nb_m;
+        bk.grid_bins = ((ix.N >> bk.sh_c) + 1) * bk.nb_m;
+        bk.n_bins = 4 * bk.grid_bins; // <= 65536
     }
     if (need_mask_pass)
         if ((e = cudaMemsetAsync(ix.hist, 0, (size_t)bk.n_bins * 4, L.stream)) != cudaSuccess) return e;
@@ -765,6 +771,15 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
                                                              ix.pod_ranks, L.ov, ix.tail_list, tail_count);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        // bindings are final here: start their device-to-host copy now, under the mask kernel
+        if (L.host_node_idx && L.ov.node_idx) {
+            if ((e = cudaMemcpyAsync(L.host_node_idx, L.ov.node_idx, (size_t)P * 4, cudaMemcpyDeviceToHost, ix.aux)) != cudaSuccess) return e;
+            L.host_node_idx = nullptr;
+        }
+        if (L.host_score && L.ov.score) {
+            if ((e = cudaMemcpyAsync(L.host_score, L.ov.score, (size_t)P * 8, cudaMemcpyDeviceToHost, ix.aux)) != cudaSuccess) return e;
+            L.host_score = nullptr;
         }
         if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
     }
@@ -797,7 +812,7 @@ static cudaError_t select_w(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t 
     return cudaSuccess;
 }
 
-cudaError_t bitpar_select(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
+cudaError_t bitpar_select(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask) {
     if (!ix.valid) return cudaErrorNotSupported;
     switch (ix.W) {
         case 1: return select_w<1>(ix, L, before_mask, after_mask);

@@ -64,7 +64,7 @@ struct BitparIndex {
 cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* prio, cudaStream_t st);
 bool bitpar_profitable(const BitparIndex& ix, uint32_t P);
 cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P);
-cudaError_t bitpar_select(BitparIndex& ix, const SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask);
+cudaError_t bitpar_select(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask);
 void bitpar_release(BitparIndex& ix);
 
 } // namespace ks

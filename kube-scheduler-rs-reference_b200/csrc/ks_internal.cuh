@@ -100,6 +100,10 @@ struct SelectLaunch {
     OutView ov;
     int policy;
     cudaStream_t stream;
+    // host-space outputs: when set, the launcher may copy these results back as soon as they exist (the bindings
+    // are ready long before the mask kernel ends) and clears the pointer it has served
+    int32_t* host_node_idx = nullptr;
+    int64_t* host_score = nullptr;
 };
 
 } // namespace ks

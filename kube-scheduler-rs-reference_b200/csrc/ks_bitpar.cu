@@ -302,16 +302,18 @@ __global__ void __launch_bounds__(256)
 template <int W>
 __global__ void __launch_bounds__(BP_THREADS, 1)
     k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
-                  const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s, OutView ov) {
+                  const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s, OutView ov,
+                  uint32_t ctas_per_cb) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, psub = lane >> 2, tsub = lane & 3;
     const uint32_t nt = lay.nt;
     const uint32_t n_groups = (P + 7) / 8; // groups of 8 sorted pods
-    const uint64_t units = (uint64_t)lay.ncb * n_groups;
-    uint64_t u0 = units * blockIdx.x / gridDim.x;
-    const uint64_t u1 = units * (blockIdx.x + 1) / gridDim.x;
+    // k = ctas_per_cb CTAs share one column block and take its pod groups round-robin (the sort order clusters
+    // pods by selector size, so contiguous ranges would be unbalanced); with more column blocks than CTAs, k = 1
+    // and a CTA walks several column blocks
+    const uint32_t cta_in_cb = blockIdx.x % ctas_per_cb;
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -328,11 +330,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     const uint8_t* s_pairs = smem + lay.off_pairs;
     const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
 
-    while (u0 < u1) {
-        const uint32_t cb = (uint32_t)(u0 / n_groups);
-        const uint32_t ga = (uint32_t)(u0 - (uint64_t)cb * n_groups);
-        const uint32_t gb = (uint32_t)min((uint64_t)n_groups, u1 - (uint64_t)cb * n_groups);
-        u0 = (uint64_t)cb * n_groups + gb;
+    for (uint32_t cb = blockIdx.x / ctas_per_cb; cb < lay.ncb; cb += gridDim.x / ctas_per_cb) {
+        const uint32_t gb = n_groups;
 
         // ---- stage this column block's index blob: TMA bulk copies signalled on one mbarrier ----
         __syncthreads(); // all generic-proxy reads of the previous blob are done
@@ -344,7 +343,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                 tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
         }
 
-        uint32_t g = ga + warp;
+        const uint32_t g_step = ctas_per_cb * (BP_THREADS / 32);
+        uint32_t g = cta_in_cb * (BP_THREADS / 32) + warp;
         uint32_t q = g * 8 + psub;
         bool act = g < gb && q < P;
         uint2 r = act ? __ldg(rk_s + q) : make_uint2(0, 0); // prefetch while the blob is in flight
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
 #pragma unroll
             for (int w = 0; w < W; w++) csel[w] = sel[w];
             // software prefetch of the next group's pod data
-            g += BP_THREADS / 32;
+            g += g_step;
             q = g * 8 + psub;
             act = g < gb && q < P;
             if (act) {
@@ -794,10 +794,13 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-        const uint64_t units = (uint64_t)ix.lay.ncb * ((P + 7) / 8);
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (units + 31) / 32);
+        const uint32_t n_groups = (P + 7) / 8;
+        uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
+        ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
+        const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
         auto kern = k_mask_bitpar<W>;
-        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov);
+        kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov,
+                                                                ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)

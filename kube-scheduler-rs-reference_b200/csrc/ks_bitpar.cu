@@ -1,6 +1,7 @@
 // ks_bitpar.cu — bit-parallel fused feasibility pass for sm_100a (design notes in ks_bitpar.h).
 //
-//   per snapshot   k_rank_nodes     global rank of every node in free_cpu / free_mem / priority order
+//   per snapshot   k_node_splitters/_bucket/_scatter/_rank  sample sort: global rank of every node in free_cpu /
+//                                   free_mem / priority order
 //                  k_build_tile     per-tile prefix tables, bucket base+membership, label-pair columns
 //                                   (built twice: node-index order for the mask, priority order for argmax)
 //   per call       k_pod_ranks      request -> global rank threshold (splitters in smem + short global search)
@@ -20,45 +21,148 @@
 namespace ks {
 
 // ------------------------------------------------------------------------------------------------ build
+// ---- node ranking: sample sort ------------------------------------------------------------------------------
+// Three total orders over the N nodes are needed: ascending free_cpu, ascending free_mem, descending priority,
+// ties always by node index.  All three are "ascending (v', index)" with v' = free_cpu, free_mem, -priority.
+// k_node_splitters sorts 1024 sampled keys per order in shared memory and keeps 255 splitters; k_node_bucket drops
+// every node into one of 256 buckets per order; k_node_rank counts, inside the bucket only, the keys below the
+// node's own: position = bucket start + that count.  O(N * (log 256 + N/256)) instead of O(N^2).
+struct NodeKey {
+    int64_t v;
+    uint32_t idx;
+};
+__device__ __forceinline__ bool key_less(int64_t av, uint32_t ai, int64_t bv, uint32_t bi) {
+    return av < bv || (av == bv && ai < bi);
+}
+__device__ __forceinline__ int64_t order_value(const NodeTable& nt, const int64_t* __restrict__ prio, int k, uint32_t n) {
+    return k == 0 ? nt.free_cpu[n] : (k == 1 ? nt.free_mem[n] : -prio[n]);
+}
+
+constexpr int RANK_SAMPLES = 1024, RANK_BUCKETS = 256;
+
+__global__ void __launch_bounds__(RANK_SAMPLES)
+    k_node_splitters(NodeTable nt, const int64_t* __restrict__ prio, int64_t* __restrict__ spl_v,
+                     uint32_t* __restrict__ spl_i, uint32_t* __restrict__ hist) {
+    __shared__ int64_t s_v[RANK_SAMPLES];
+    __shared__ uint32_t s_i[RANK_SAMPLES];
+    const uint32_t t = threadIdx.x, k = blockIdx.x; // one CTA per order
+    const uint32_t n = (uint32_t)(((uint64_t)t * nt.N) / RANK_SAMPLES);
+    s_v[t] = order_value(nt, prio, k, n);
+    s_i[t] = n;
+    if (t < RANK_BUCKETS) hist[k * RANK_BUCKETS + t] = 0;
+    __syncthreads();
+    for (uint32_t size = 2; size <= RANK_SAMPLES; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            if (t < RANK_SAMPLES / 2) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const int64_t av = s_v[lo], bv = s_v[hi];
+                const uint32_t ai = s_i[lo], bi = s_i[hi];
+                if (key_less(bv, bi, av, ai) == up) {
+                    s_v[lo] = bv; s_i[lo] = bi;
+                    s_v[hi] = av; s_i[hi] = ai;
+                }
+            }
+            __syncthreads();
+        }
+    if (t < RANK_BUCKETS - 1) { // splitter j = sample 4(j+1)-1
+        spl_v[k * RANK_BUCKETS + t] = s_v[4 * (t + 1) - 1];
+        spl_i[k * RANK_BUCKETS + t] = s_i[4 * (t + 1) - 1];
+    }
+}
+
 __global__ void __launch_bounds__(256)
-    k_rank_nodes(NodeTable nt, const int64_t* __restrict__ prio, int64_t* __restrict__ sortedC,
-                 int64_t* __restrict__ sortedM, uint32_t* __restrict__ gposC, uint32_t* __restrict__ gposM,
-                 int64_t* __restrict__ ord_prio, int32_t* __restrict__ ord_idx, uint32_t Nord,
-                 int64_t* __restrict__ splC, int64_t* __restrict__ splM, uint32_t spl_stride) {
-    __shared__ int64_t s_fc[1024], s_fm[1024], s_pr[1024];
+    k_node_bucket(NodeTable nt, const int64_t* __restrict__ prio, const int64_t* __restrict__ spl_v,
+                  const uint32_t* __restrict__ spl_i, uint32_t* __restrict__ hist, uint8_t* __restrict__ bkt,
+                  uint32_t* __restrict__ loc) {
+    __shared__ int64_t s_v[3][RANK_BUCKETS];
+    __shared__ uint32_t s_i[3][RANK_BUCKETS];
+    for (uint32_t j = threadIdx.x; j < 3 * (RANK_BUCKETS - 1); j += blockDim.x) {
+        const uint32_t k = j / (RANK_BUCKETS - 1), q = j % (RANK_BUCKETS - 1);
+        s_v[k][q] = spl_v[k * RANK_BUCKETS + q];
+        s_i[k][q] = spl_i[k * RANK_BUCKETS + q];
+    }
+    __syncthreads();
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nt.N) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int64_t v = order_value(nt, prio, k, n);
+        uint32_t lo = 0, len = RANK_BUCKETS - 1; // number of splitters < key
+        while (len > 0) {
+            const uint32_t half = len >> 1;
+            if (key_less(s_v[k][lo + half], s_i[k][lo + half], v, n)) {
+                lo += half + 1;
+                len -= half + 1;
+            } else {
+                len = half;
+            }
+        }
+        bkt[(size_t)k * nt.N + n] = (uint8_t)lo;
+        loc[(size_t)k * nt.N + n] = atomicAdd(&hist[k * RANK_BUCKETS + lo], 1u);
+    }
+}
+
+// bucket-ordered node lists (order inside a bucket is arbitrary; k_node_rank fixes the final positions)
+__global__ void __launch_bounds__(256)
+    k_node_scatter(uint32_t N, const uint32_t* __restrict__ hist, const uint8_t* __restrict__ bkt,
+                   const uint32_t* __restrict__ loc, uint32_t* __restrict__ perm) {
+    __shared__ uint32_t s_start[3][RANK_BUCKETS];
+    if (threadIdx.x < 3) {
+        uint32_t acc = 0;
+        for (int b = 0; b < RANK_BUCKETS; b++) {
+            s_start[threadIdx.x][b] = acc;
+            acc += hist[threadIdx.x * RANK_BUCKETS + b];
+        }
+    }
+    __syncthreads();
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        perm[(size_t)k * N + s_start[k][bkt[(size_t)k * N + n]] + loc[(size_t)k * N + n]] = n;
+}
+
+__global__ void __launch_bounds__(256)
+    k_node_rank(NodeTable nt, const int64_t* __restrict__ prio, const uint32_t* __restrict__ hist,
+                const uint8_t* __restrict__ bkt, const uint32_t* __restrict__ perm, int64_t* __restrict__ sortedC,
+                int64_t* __restrict__ sortedM, uint32_t* __restrict__ gposC, uint32_t* __restrict__ gposM,
+                int64_t* __restrict__ ord_prio, int32_t* __restrict__ ord_idx, uint32_t Nord,
+                int64_t* __restrict__ splC, int64_t* __restrict__ splM, uint32_t spl_stride) {
+    __shared__ uint32_t s_start[3][RANK_BUCKETS + 1];
+    if (threadIdx.x < 3) {
+        uint32_t acc = 0;
+        for (int b = 0; b < RANK_BUCKETS; b++) {
+            s_start[threadIdx.x][b] = acc;
+            acc += hist[threadIdx.x * RANK_BUCKETS + b];
+        }
+        s_start[threadIdx.x][RANK_BUCKETS] = acc;
+    }
+    __syncthreads();
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t N = nt.N;
-    const bool real = n < N;
-    const int64_t fc = real ? nt.free_cpu[n] : 0, fm = real ? nt.free_mem[n] : 0, pr = real ? prio[n] : 0;
-    uint32_t cC = 0, cM = 0, cP = 0;
-    for (uint32_t j0 = 0; j0 < N; j0 += 1024) {
-        for (uint32_t k = threadIdx.x; k < 1024; k += blockDim.x) {
-            const uint32_t j = j0 + k;
-            s_fc[k] = j < N ? nt.free_cpu[j] : 0;
-            s_fm[k] = j < N ? nt.free_mem[j] : 0;
-            s_pr[k] = j < N ? prio[j] : 0;
+    if (n < N) {
+        uint32_t pos[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int64_t v = order_value(nt, prio, k, n);
+            const uint32_t b = bkt[(size_t)k * N + n];
+            uint32_t c = 0;
+            for (uint32_t j = s_start[k][b]; j < s_start[k][b + 1]; j++) {
+                const uint32_t m = perm[(size_t)k * N + j];
+                c += key_less(order_value(nt, prio, k, m), m, v, n);
+            }
+            pos[k] = s_start[k][b] + c;
         }
-        __syncthreads();
-        const uint32_t lim = min(1024u, N - j0);
-        for (uint32_t k = 0; k < lim; k++) {
-            const uint32_t j = j0 + k;
-            const bool before = j < n;
-            const int64_t vc = s_fc[k], vm = s_fm[k], vp = s_pr[k];
-            cC += (vc < fc) || (vc == fc && before);
-            cM += (vm < fm) || (vm == fm && before);
-            cP += (vp > pr) || (vp == pr && before); // descending priority, ties -> lower node index first
-        }
-        __syncthreads();
-    }
-    if (real) {
-        gposC[n] = cC;
-        gposM[n] = cM;
-        sortedC[cC] = fc;
-        sortedM[cM] = fm;
-        if (cC % spl_stride == 0) splC[cC / spl_stride] = fc;
-        if (cM % spl_stride == 0) splM[cM / spl_stride] = fm;
-        ord_prio[cP] = pr;
-        ord_idx[cP] = (int32_t)n;
+        const int64_t fc = nt.free_cpu[n], fm = nt.free_mem[n];
+        gposC[n] = pos[0];
+        gposM[n] = pos[1];
+        sortedC[pos[0]] = fc;
+        sortedM[pos[1]] = fm;
+        if (pos[0] % spl_stride == 0) splC[pos[0] / spl_stride] = fc;
+        if (pos[1] % spl_stride == 0) splM[pos[1] / spl_stride] = fm;
+        ord_prio[pos[2]] = prio[n];
+        ord_idx[pos[2]] = (int32_t)n;
     } else if (n < Nord) { // padding of the priority order
         ord_prio[n] = INT64_MIN;
         ord_idx[n] = -1;
@@ -618,7 +722,8 @@ static cudaError_t regrow(T*& p, size_t count) {
 void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc,  ix.ord_fm,   ix.ord_prio,
                     ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
-                    ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist};
+                    ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist,
+                    ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -645,15 +750,27 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
         if ((e = regrow(ix.ord_idx, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.splC, 1024)) != cudaSuccess) return e;
         if ((e = regrow(ix.splM, 1024)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_bkt, 3 * cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_loc, 3 * cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_perm, 3 * cap)) != cudaSuccess) return e;
         ix.cap_nodes = cap;
     }
     uint32_t stride = 1;
     while ((nt.N + stride - 1) / stride > 1024) stride <<= 1;
     ix.spl_stride = stride;
     ix.n_spl = (nt.N + stride - 1) / stride;
-    k_rank_nodes<<<(Nord + 255) / 256, 256, 0, st>>>(nt, prio, ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
-                                                     ix.ord_idx, Nord, ix.splC, ix.splM, stride);
-    g_launches++;
+    if (!ix.rk_hist) {
+        if ((e = regrow(ix.rk_hist, 3 * RANK_BUCKETS)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_spl_v, 3 * RANK_BUCKETS)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_spl_i, 3 * RANK_BUCKETS)) != cudaSuccess) return e;
+    }
+    k_node_splitters<<<3, RANK_SAMPLES, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist);
+    k_node_bucket<<<(nt.N + 255) / 256, 256, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist, ix.rk_bkt, ix.rk_loc);
+    k_node_scatter<<<(nt.N + 255) / 256, 256, 0, st>>>(nt.N, ix.rk_hist, ix.rk_bkt, ix.rk_loc, ix.rk_perm);
+    k_node_rank<<<(Nord + 255) / 256, 256, 0, st>>>(nt, prio, ix.rk_hist, ix.rk_bkt, ix.rk_perm, ix.sortedC, ix.sortedM,
+                                                    ix.gposC, ix.gposM, ix.ord_prio, ix.ord_idx, Nord, ix.splC, ix.splM,
+                                                    stride);
+    g_launches += 4;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     BitparLayout lay{}, layP{};
     if (!make_layout_smem(nt.N, nt.W, &lay) || !make_layout_flat(nt.N, nt.W, &layP)) return cudaSuccess; // direct path only

@@ -52,6 +52,12 @@ struct BitparIndex {
     uint32_t* pid_s = nullptr;
     unsigned long long* sel_s = nullptr;
     uint32_t* hist = nullptr;      // [65536] bucket histogram -> exclusive scan
+    uint32_t* rk_hist = nullptr;   // node sample sort scratch: [3][256] bucket counts, splitters, per-node bucket / slot, lists
+    int64_t* rk_spl_v = nullptr;
+    uint32_t* rk_spl_i = nullptr;
+    uint8_t* rk_bkt = nullptr;
+    uint32_t* rk_loc = nullptr;
+    uint32_t* rk_perm = nullptr;
     size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_lab = 0, cap_sel = 0;
     uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
     BitparLayout lay{}, layP{};

@@ -173,11 +173,14 @@ __global__ void __launch_bounds__(256)
 // different required pairs fall into different 16-byte bank groups
 __host__ __device__ __forceinline__ uint32_t pair_stride(uint32_t nt) { return nt * 32u + 16u; }
 
-__device__ __forceinline__ uint32_t table_chunk(uint32_t row, uint32_t half) {
-    // 16-byte chunk index of (row, half) inside a tile table; the XOR spreads the first halves of
-    // consecutive rows over all eight 16-byte bank groups
-    return 2u * row + (half ^ ((row >> 2) & 1u));
+// Prefix tables are interleaved by QUADS of tiles: row r of tiles 4k..4k+3 forms one 128-byte line
+//   [tile 4k row r | tile 4k+1 row r | tile 4k+2 row r | tile 4k+3 row r]
+// so the four tiles that the 8 lanes of a shared-memory phase work on always sit in four different pairs of 16-byte
+// bank groups, whatever their (unrelated) ranks are.  Byte offset of (tile, row) inside a table area:
+__host__ __device__ __forceinline__ uint32_t table_row_offset(uint32_t tile, uint32_t row) {
+    return (tile >> 2) * (uint32_t)(BP_ROWS * 128) + row * 128u + (tile & 3u) * 32u;
 }
+__host__ __device__ __forceinline__ uint32_t table_area_bytes(uint32_t nt) { return ((nt + 3u) / 4u) * (uint32_t)(BP_ROWS * 128); }
 
 // One CTA builds the index of one 256-slot tile.  slot_node maps slot -> node (nullptr = identity, i.e. the
 // node-index order used for the mask; ord_idx = priority order used for the argmax).
@@ -222,9 +225,9 @@ __global__ void __launch_bounds__(288)
                 }
                 w[j] = acc;
             }
-            uint4* tab = reinterpret_cast<uint4*>(B + (r ? lay.off_tabM : lay.off_tabC) + (size_t)t * BP_TABLE_BYTES);
-            tab[table_chunk(s, 0)] = make_uint4(w[0], w[1], w[2], w[3]);
-            tab[table_chunk(s, 1)] = make_uint4(w[4], w[5], w[6], w[7]);
+            uint4* tab = reinterpret_cast<uint4*>(B + (r ? lay.off_tabM : lay.off_tabC) + table_row_offset(t, s));
+            tab[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            tab[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
     }
     // bucket membership + base counts, layout [bucket][tile]
@@ -489,10 +492,10 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                     const unsigned long long mc = s_membC[hc + ct], mm = s_membM[hm + ct];
                     const uint32_t rankC = bc + __popcll(mc & lowC);
                     const uint32_t rankM = bm + __popcll(mm & lowM);
-                    const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + ct * BP_TABLE_BYTES);
-                    const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + ct * BP_TABLE_BYTES);
-                    const uint4 c0 = tc[table_chunk(rankC, 0)], c1 = tc[table_chunk(rankC, 1)];
-                    const uint4 m0 = tm[table_chunk(rankM, 0)], m1 = tm[table_chunk(rankM, 1)];
+                    const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + table_row_offset(ct, rankC));
+                    const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + table_row_offset(ct, rankM));
+                    const uint4 c0 = tc[0], c1 = tc[1];
+                    const uint4 m0 = tm[0], m1 = tm[1];
                     uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
                     uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
 #pragma unroll
@@ -560,10 +563,10 @@ __device__ __forceinline__ void ptile_mask(const uint8_t* __restrict__ blobP, co
                                            const unsigned long long (&sel)[W], uint32_t k, uint32_t (&m)[8]) {
     const uint32_t rankC = __ldg(t.baseC + k) + __popcll(__ldg(t.membC + k) & t.lowC);
     const uint32_t rankM = __ldg(t.baseM + k) + __popcll(__ldg(t.membM + k) & t.lowM);
-    const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + (size_t)k * BP_TABLE_BYTES);
-    const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + (size_t)k * BP_TABLE_BYTES);
-    const uint4 c0 = __ldg(tc + table_chunk(rankC, 0)), c1 = __ldg(tc + table_chunk(rankC, 1));
-    const uint4 m0 = __ldg(tm + table_chunk(rankM, 0)), m1 = __ldg(tm + table_chunk(rankM, 1));
+    const uint4* tc = reinterpret_cast<const uint4*>(blobP + lay.off_tabC + table_row_offset(k, rankC));
+    const uint4* tm = reinterpret_cast<const uint4*>(blobP + lay.off_tabM + table_row_offset(k, rankM));
+    const uint4 c0 = __ldg(tc), c1 = __ldg(tc + 1);
+    const uint4 m0 = __ldg(tm), m1 = __ldg(tm + 1);
     m[0] = c0.x & m0.x; m[1] = c0.y & m0.y; m[2] = c0.z & m0.z; m[3] = c0.w & m0.w;
     m[4] = c1.x & m1.x; m[5] = c1.y & m1.y; m[6] = c1.z & m1.z; m[7] = c1.w & m1.w;
     const uint8_t* pairs = blobP + lay.off_pairs;
@@ -666,6 +669,7 @@ static uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
 static uint64_t per_tile_bytes(uint32_t nb, uint32_t W) {
     return (uint64_t)nb * 20 + 2ull * BP_TABLE_BYTES + 64ull * W * 32 + 64ull * W * 16; // last term: pair-column skew
+    // (tables are allocated per quad of tiles: make_layout_smem re-checks the exact blob size)
 }
 
 static bool fill_offsets(BitparLayout* lay, uint32_t W) {
@@ -680,10 +684,11 @@ static bool fill_offsets(BitparLayout* lay, uint32_t W) {
     off += round16((uint32_t)(nb * nt * 8));
     lay->off_membM = off;
     off += round16((uint32_t)(nb * nt * 8));
+    off = (off + 127u) & ~127u; // table lines are 128 bytes
     lay->off_tabC = off;
-    off += (uint32_t)nt * BP_TABLE_BYTES;
+    off += table_area_bytes((uint32_t)nt);
     lay->off_tabM = off;
-    off += (uint32_t)nt * BP_TABLE_BYTES;
+    off += table_area_bytes((uint32_t)nt);
     lay->off_pairs = off;
     off += 64u * W * pair_stride((uint32_t)nt);
     lay->blob_bytes = (off + 127u) & ~127u;

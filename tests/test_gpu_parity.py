@@ -82,6 +82,7 @@ def test_gv1_objects_vs_faithful_oracle(ks, orc):
 SHAPES = [
     (1, 1, 8), (5, 31, 8), (33, 32, 8), (100, 1024, 8), (257, 1025, 8), (1000, 3000, 8), (300, 2049, 16),
     (64, 2500, 32), (40, 1300, 64), (2000, 256, 8), (3, 20000, 8),
+    (300, 150_000, 8),  # more column blocks than SMs: every CTA walks several column blocks
 ]
 
 

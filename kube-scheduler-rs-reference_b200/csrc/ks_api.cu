@@ -64,6 +64,9 @@ struct ks_snapshot {
     DevBuf st_rc, st_rm, st_sel, st_idx, st_score, st_cnt, st_mask, st_codes, st_bnode, st_bcpu, st_bmem;
     DevBuf part_key, part_idx, part_cnt;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // host-space calls are pipelined in pod chunks: chunk c+1 is copied in on copy_stream while chunk c computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_cfork = nullptr, ev_in[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
     bool derived_dirty = true; // prio + bit-parallel index must be rebuilt before the next select
     const char* last_path = "none";
@@ -138,6 +141,9 @@ int ks_snapshot_create(int device, ks_snapshot** out) {
     s->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_cfork, cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = s->flag.ensure(sizeof(int));
     if (e != cudaSuccess) {
         ks_snapshot_destroy(s);
@@ -160,6 +166,10 @@ void ks_snapshot_destroy(ks_snapshot* s) {
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     for (int i = 0; i < 4; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < 4; i++)
+        if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+    if (s->ev_cfork) cudaEventDestroy(s->ev_cfork);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -490,9 +500,55 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
             if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct prepare failed: %s", cudaGetErrorString(e));
         }
         s->last_path = use_bitpar ? "bitpar" : "direct";
+        // Host-space batches on the bit-parallel path are pipelined in two pod chunks: the second chunk is copied in
+        // on copy_stream while the first computes, and the bindings of a chunk travel back under the next chunk's
+        // mask kernel.  (Each chunk is an independent select over its pod range; scratch is reused because a chunk
+        // starts only after the previous chunk's auxiliary-stream work has joined.)
+        const uint32_t n_pipe = (use_bitpar && pods->mem_space == KS_MEM_HOST && out_host && !mask_host && !timing &&
+                                 P >= 65536)
+                                    ? 2u
+                                    : 1u;
         auto enqueue = [&]() -> int {
-            int crc = copy_pods_in(s, pods, st);
-            if (crc) return crc;
+            if (n_pipe == 1) {
+                int crc = copy_pods_in(s, pods, st);
+                if (crc) return crc;
+            } else {
+                CU_TRY(cudaEventRecord(s->ev_cfork, st));
+                CU_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_cfork, 0));
+                for (uint32_t c = 0; c < n_pipe; c++) {
+                    const uint64_t c0 = P * c / n_pipe, c1 = P * (c + 1) / n_pipe, m = c1 - c0;
+                    CU_TRY(cudaMemcpyAsync(s->st_rc.as<int64_t>() + c0, pods->req_cpu + c0, m * 8, cudaMemcpyHostToDevice,
+                                           s->copy_stream));
+                    CU_TRY(cudaMemcpyAsync(s->st_rm.as<int64_t>() + c0, pods->req_mem + c0, m * 8, cudaMemcpyHostToDevice,
+                                           s->copy_stream));
+                    CU_TRY(cudaMemcpyAsync(s->st_sel.as<uint64_t>() + c0 * s->W, pods->sel + c0 * s->W, m * 8 * s->W,
+                                           cudaMemcpyHostToDevice, s->copy_stream));
+                    CU_TRY(cudaEventRecord(s->ev_in[c], s->copy_stream));
+                }
+                for (uint32_t c = 0; c < n_pipe; c++) {
+                    const uint64_t c0 = P * c / n_pipe, c1 = P * (c + 1) / n_pipe, m = c1 - c0;
+                    CU_TRY(cudaStreamWaitEvent(st, s->ev_in[c], 0));
+                    SelectLaunch Lc = L;
+                    Lc.pv.req_cpu += c0;
+                    Lc.pv.req_mem += c0;
+                    Lc.pv.sel += c0 * s->W;
+                    Lc.pv.P = (uint32_t)m;
+                    if (Lc.ov.node_idx) Lc.ov.node_idx += c0;
+                    if (Lc.ov.score) Lc.ov.score += c0;
+                    if (Lc.ov.cnt) Lc.ov.cnt += c0;
+                    if (Lc.ov.mask) Lc.ov.mask += c0 * Lc.ov.mask_row_words;
+                    Lc.host_node_idx = out->node_idx ? out->node_idx + c0 : nullptr;
+                    Lc.host_score = out->score ? out->score + c0 : nullptr;
+                    cudaError_t e = bitpar_select(s->bp, Lc, nullptr, nullptr);
+                    if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
+                    if (Lc.host_node_idx)
+                        CU_TRY(cudaMemcpyAsync(Lc.host_node_idx, Lc.ov.node_idx, m * 4, cudaMemcpyDeviceToHost, st));
+                    if (Lc.host_score) CU_TRY(cudaMemcpyAsync(Lc.host_score, Lc.ov.score, m * 8, cudaMemcpyDeviceToHost, st));
+                    if (out->feasible_cnt)
+                        CU_TRY(cudaMemcpyAsync(out->feasible_cnt + c0, Lc.ov.cnt, m * 4, cudaMemcpyDeviceToHost, st));
+                }
+                return KS_OK;
+            }
             L.host_node_idx = out_host ? out->node_idx : nullptr; // served early by the launcher when it can
             L.host_score = out_host ? out->score : nullptr;
             if (use_bitpar) {

@@ -505,7 +505,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         // mask kernel.  (Each chunk is an independent select over its pod range; scratch is reused because a chunk
         // starts only after the previous chunk's auxiliary-stream work has joined.)
         const uint32_t n_pipe = (use_bitpar && pods->mem_space == KS_MEM_HOST && out_host && !mask_host && !timing &&
-                                 P >= 65536)
+                                 P >= 262144) // below that the per-chunk launch overhead outweighs the overlap (measured at 100k pods)
                                     ? 2u
                                     : 1u;
         auto enqueue = [&]() -> int {

@@ -390,10 +390,21 @@ def main():
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
+        # second CPU figure (BASELINE.md §3 "CPU-packed"): the same SoA int64 + bitmask algorithm the GPU runs, C,
+        # all host threads, on a pod sample — what a well-written CPU scheduler core could do with packed inputs
+        from oracle import orc
+        n_pk = min(P, 20000)
+        fc_h, fm_h = cl.free()
+        t0 = time.perf_counter()
+        orc.run_packed(fc_h, fm_h, ac, am, lab, rc[:n_pk], rm[:n_pk], sel[:n_pk], policy=policy, want_mask=True, nthreads=0)
+        t_pk = time.perf_counter() - t0
         cps, cores, n, t = cpu_reference_arm(cl, ks, args.cpu_seconds, policy)
         line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"first {n} pods x {N} nodes ({n * N} cells, {t:.1f} s) of the same workload, "
-                                          f"faithful per-cell path (quantity parse + bound-pod re-sum per cell)"}
+                                          f"faithful per-cell path (quantity parse + bound-pod re-sum per cell)",
+                                "packed_soa": {"value": n_pk * N / t_pk, "unit": UNIT, "cores": cores,
+                                               "sample": f"first {n_pk} pods x {N} nodes, same SoA/bitmask algorithm in C "
+                                                         f"(oracle packed flavour), mask + argmax, {t_pk:.2f} s"}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -250,7 +250,15 @@ def main():
     p_idx = p_score + 8 * P
     p_cnt = p_idx + 4 * P
     d_mask = torch.empty((P, row), dtype=torch.uint8, device=dev) if emit_mask else None
-    d_all = torch.empty(world * P * 16, dtype=torch.uint8, device=dev) if world > 1 else None
+    # the all-gather moves the bindings proper (score i64 | node_idx i32 = the first 12 B per pod of the shard buffer);
+    # feasible counts and the mask stay sharded
+    d_all = torch.empty(world * P * 12, dtype=torch.uint8, device=dev) if world > 1 else None
+    side = torch.cuda.Stream() if world > 1 else None
+    ev_ready = torch.cuda.Event() if world > 1 else None
+    ev_gathered = torch.cuda.Event() if world > 1 else None
+    if world > 1:
+        ev_ready.record(stream)  # materialise the underlying cudaEvent handles
+        ev_gathered.record(stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     h_rc = torch.from_numpy(rc).pin_memory()
     h_rm = torch.from_numpy(rm).pin_memory()
@@ -260,10 +268,16 @@ def main():
     def step_resident(timing):
         snap.select_raw(P, d_rc, d_rm, d_sel, ks.KS_MEM_DEVICE, p_idx, p_score, p_cnt, ks.KS_MEM_DEVICE,
                         mask=d_mask, mask_row_bytes=row if emit_mask else 0, mask_space=ks.KS_MEM_DEVICE,
-                        policy=policy, flags=flags | (ks.KS_SELECT_TIMING if timing else 0), stream=stream.cuda_stream)
+                        policy=policy, flags=flags | (ks.KS_SELECT_TIMING if timing else 0), stream=stream.cuda_stream,
+                        ready_event=ev_ready.cuda_event if world > 1 else None)
         if world > 1:
-            with torch.cuda.stream(stream):
-                ks.multigpu.all_gather_bindings(d_bind, d_all)  # the ONE collective of the step
+            # the ONE collective of the step runs on a side stream as soon as the library signals that node_idx and
+            # score are final, i.e. under the mask kernel; the step ends when both the select and the gather are done
+            side.wait_event(ev_ready)
+            with torch.cuda.stream(side):
+                ks.multigpu.all_gather_bindings(d_bind[:12 * P], d_all)
+                ev_gathered.record(side)
+            stream.wait_event(ev_gathered)
 
     def step_e2e():
         hp = h_bind.data_ptr()
@@ -352,10 +366,15 @@ def main():
     torch.cuda.synchronize()
     assert torch.equal(d_bind.cpu(), h_bind), "resident and e2e bindings differ"
     if world > 1:  # and the all-gather delivered every shard: rank 0's own slice matches, every pod was decided
-        gi, gs, gc = ks.multigpu.unpack_bindings(d_all.cpu().numpy(), world * P, world)
-        mi, ms_, mc = ks.multigpu.unpack_bindings(d_bind.cpu().numpy(), P, 1)
-        assert np.array_equal(gi[:P], mi) and np.array_equal(gs[:P], ms_) and np.array_equal(gc[:P], mc)
-        assert np.array_equal(gi < 0, gc == 0)
+        g = d_all.cpu().numpy().reshape(world, 12 * P)
+        mine = d_bind.cpu().numpy()
+        assert np.array_equal(g[0], mine[:12 * P]), "all-gather did not deliver rank 0's own bindings"
+        mi, _, mc = ks.multigpu.unpack_bindings(mine, P, 1)
+        assert np.array_equal(mi < 0, mc == 0)
+        for r in range(world):  # every shard arrived: node indices are in range, scores of unbound pods are zero
+            gi = g[r, 8 * P:12 * P].view(np.int32)
+            gs = g[r, :8 * P].view(np.int64)
+            assert gi.min() >= -1 and gi.max() < N and (gs[gi < 0] == 0).all()
 
     ab = algorithmic_bytes(P, N, W, cl.B, emit_mask)
     peak, peak_src = hbm_peak()
@@ -378,7 +397,7 @@ def main():
             "workload": f"{args.workload}: {P} pods/GPU x {N} nodes ({P * N:.3g} cells/GPU), resource_fits + nodeSelector "
                         f"+ argmax score ({args.policy}), mask {'emitted' if emit_mask else 'not emitted'}",
             "label_words": W, "bound_pods": cl.B, "seed": hex(seed), "path": snap.last_path(),
-            "parallelism": f"pods sharded x{world}, node table replicated" + (", 1 NCCL all-gather of bindings/step" if world > 1 else ""),
+            "parallelism": f"pods sharded x{world}, node table replicated" + (", 1 NCCL all-gather of bindings/step (side stream, under the mask kernel)" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": t_wall,
             "clocks_window": "0.4 s untimed soak of the same step + both timed loops (timed region alone is a few ms)",
             "call_ms_inside_library": sum(call_ms) / len(call_ms),

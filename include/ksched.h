@@ -82,6 +82,9 @@ typedef struct ks_bindings { /* outputs; any pointer may be NULL to skip that ou
     uint8_t* mask;           /* [n rows] feasible bit-mask, bit (n%8) of byte n/8 of the row */
     uint64_t mask_row_bytes; /* row pitch; multiple of 32, >= ks_mask_row_bytes(N) */
     int32_t mask_space;      /* space of mask (may differ: keep a 6 GB mask in HBM, bindings on host) */
+    void* bindings_ready_event; /* optional cudaEvent_t (NULL = none), device-space outputs only: recorded as soon as
+                                   node_idx and score are final - on the bit-parallel path that is well before the
+                                   mask/count pass ends, so a collective over the bindings can overlap it */
 } ks_bindings;
 
 const char* ks_last_error(void);

@@ -17,7 +17,7 @@ lib = C.CDLL(LIB_PATH)
 KS_OK = 0
 KS_MEM_HOST, KS_MEM_DEVICE = 0, 1
 KS_SCORE_LEFTOVER, KS_SCORE_LEAST_ALLOCATED = 0, 1
-KS_SELECT_AUTO, KS_SELECT_FORCE_DIRECT, KS_SELECT_FORCE_BITPAR, KS_SELECT_TIMING = 0, 1, 2, 4
+KS_SELECT_AUTO, KS_SELECT_FORCE_DIRECT, KS_SELECT_FORCE_BITPAR, KS_SELECT_TIMING, KS_SELECT_NO_GRAPH = 0, 1, 2, 4, 8
 KS_CELL_OK, KS_CELL_NOT_ENOUGH_RESOURCES, KS_CELL_NODE_SELECTOR_MISMATCH = 0, 1, 2
 KS_ERR_NO_DEVICE = -8
 
@@ -37,7 +37,7 @@ class ks_pods(C.Structure):
 class ks_bindings(C.Structure):
     _fields_ = [("node_idx", C.c_void_p), ("score", C.c_void_p), ("feasible_cnt", C.c_void_p),
                 ("mem_space", C.c_int32), ("mask", C.c_void_p), ("mask_row_bytes", C.c_uint64),
-                ("mask_space", C.c_int32)]
+                ("mask_space", C.c_int32), ("bindings_ready_event", C.c_void_p)]
 
 
 def _proto(name, restype, *argtypes):

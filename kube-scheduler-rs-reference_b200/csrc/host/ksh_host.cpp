@@ -387,7 +387,7 @@ int ksh_select_nodes(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int pol
     int rc = pack_and_upload(c, pods, n, rc_, rm_, sel);
     if (rc) return rc;
     ks_pods kp{n, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
-    ks_bindings kb{out_node_idx, out_score, out_cnt, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST};
+    ks_bindings kb{out_node_idx, out_score, out_cnt, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr};
     return ks_select(c->snap, &kp, policy, KS_SELECT_AUTO, &kb, nullptr);
 }
 

@@ -551,6 +551,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
             }
             L.host_node_idx = out_host ? out->node_idx : nullptr; // served early by the launcher when it can
             L.host_score = out_host ? out->score : nullptr;
+            L.ready_event = out_host ? nullptr : (cudaEvent_t)out->bindings_ready_event;
             if (use_bitpar) {
                 cudaError_t e = bitpar_select(s->bp, L, timing ? s->ev[1] : nullptr, timing ? s->ev[2] : nullptr);
                 if (e != cudaSuccess) return fail(KS_ERR_CUDA, "bit-parallel select failed: %s", cudaGetErrorString(e));
@@ -568,6 +569,12 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
             }
             if (mask_host)
                 CU_TRY(cudaMemcpyAsync(out->mask, ov.mask, P * out->mask_row_bytes, cudaMemcpyDeviceToHost, st));
+            if (L.ready_event) { // not served earlier (per-cell path): the bindings are final here
+                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                CU_TRY(cudaStreamIsCapturing(st, &cs));
+                CU_TRY(cudaEventRecordWithFlags(L.ready_event, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
+                                                                                                   : cudaEventRecordDefault));
+            }
             return KS_OK;
         };
         // Replay from a cached CUDA graph when the call repeats (same buffers, same snapshot state).  Host buffers
@@ -577,7 +584,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                                   (uint64_t)out->mask, out->mask_row_bytes,
                                   (uint64_t)policy | ((uint64_t)pods->mem_space << 8) | ((uint64_t)out->mem_space << 9) |
                                       ((uint64_t)out->mask_space << 10),
-                                  (uint64_t)flags, (uint64_t)st, s->version, (uint64_t)use_bitpar};
+                                  (uint64_t)flags ^ ((uint64_t)out->bindings_ready_event << 8), (uint64_t)st, s->version, (uint64_t)use_bitpar};
         const bool key_hit = s->graph_valid && memcmp(key, s->graph_key, sizeof(key)) == 0;
         bool graph_ok = !timing && !(flags & KS_SELECT_NO_GRAPH);
         if (graph_ok && !key_hit) {
@@ -701,7 +708,7 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
             for (uint32_t w = 0; w < W; w++) sel[k * W + w] = pods->sel[p * W + w];
         }
         ks_pods kp{m, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
-        ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST};
+        ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr};
         rc = ks_select(s, &kp, policy, KS_SELECT_FORCE_DIRECT, &kb, nullptr); // claims against the current free[]
         if (rc) return rc;
         rc = ks_snapshot_commit_claims(s, m, idx.data(), rc_.data(), rm_.data(), acc.data());

@@ -903,6 +903,14 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
             if ((e = cudaMemcpyAsync(L.host_score, L.ov.score, (size_t)P * 8, cudaMemcpyDeviceToHost, ix.aux)) != cudaSuccess) return e;
             L.host_score = nullptr;
         }
+        if (L.ready_event) { // tell the caller that node_idx / score are final (the mask pass is still running)
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if ((e = cudaStreamIsCapturing(ix.aux, &cs)) != cudaSuccess) return e;
+            e = cudaEventRecordWithFlags(L.ready_event, ix.aux,
+                                         cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+            if (e != cudaSuccess) return e;
+            L.ready_event = nullptr;
+        }
         if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
     }
     if (need_mask_pass) {

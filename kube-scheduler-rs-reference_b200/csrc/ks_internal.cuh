@@ -104,6 +104,7 @@ struct SelectLaunch {
     // are ready long before the mask kernel ends) and clears the pointer it has served
     int32_t* host_node_idx = nullptr;
     int64_t* host_score = nullptr;
+    cudaEvent_t ready_event = nullptr; // caller's "bindings are final" event (ks_bindings.bindings_ready_event)
 };
 
 } // namespace ks

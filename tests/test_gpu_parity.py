@@ -320,3 +320,41 @@ def test_graph_replay_tracks_snapshot_changes(ks, orc):
             assert all(np.array_equal(a, b) for a, b in zip(g, o3[:3]))
             t[0].copy_(torch.from_numpy(rc))
             torch.cuda.synchronize()
+
+
+def test_bindings_ready_event_orders_a_side_stream(ks, orc):
+    """ks_bindings.bindings_ready_event: a consumer on another stream that waits for the event must see the final
+    node_idx/score of THIS call (also when the call is replayed from the cached CUDA graph with new pod values)."""
+    import torch
+    cl = ks.synth.make(40000, 3000, seed=33)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    dev = torch.device("cuda:0")
+    row = ks.mask_row_bytes(cl.N)
+    t = [torch.from_numpy(np.ascontiguousarray(x.view(np.int64))).to(dev) for x in (rc, rm, sel)]
+    idx = torch.full((cl.P,), -9, dtype=torch.int32, device=dev)
+    score = torch.zeros(cl.P, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(cl.P, dtype=torch.int32, device=dev)
+    mask = torch.zeros((cl.P, row), dtype=torch.uint8, device=dev)
+    st, side = torch.cuda.Stream(), torch.cuda.Stream()
+    ev = torch.cuda.Event()
+    ev.record(st)
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes(ac, am, lab)
+        snap.set_bound(bn, bc, bm)
+        fc, fm = snap.free()
+        for it in range(4):
+            rc_it = rc + 50 * it
+            t[0].copy_(torch.from_numpy(rc_it))
+            torch.cuda.synchronize()
+            snap.select_raw(cl.P, t[0], t[1], t[2], ks.KS_MEM_DEVICE, idx, score, cnt, ks.KS_MEM_DEVICE, mask=mask,
+                            mask_row_bytes=row, mask_space=ks.KS_MEM_DEVICE, flags=ks.KS_SELECT_FORCE_BITPAR,
+                            stream=st.cuda_stream, ready_event=ev.cuda_event)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                early_idx, early_score = idx.clone(), score.clone()
+            side.synchronize()
+            st.synchronize()
+            o = orc.run_packed(fc, fm, ac, am, lab, rc_it, rm, sel, want_mask=False)
+            assert np.array_equal(early_idx.cpu().numpy(), o[0]), it
+            assert np.array_equal(early_score.cpu().numpy(), o[1]), it
+            assert np.array_equal(cnt.cpu().numpy().view(np.uint32), o[2]), it

@@ -299,10 +299,18 @@ def main():
         step_e2e()
     # The timed region lasts only a few ms, shorter than nvidia-smi's sampling period, so the same step is kept
     # running (untimed) for ~0.4 s right before it: the clock / throttle samples are taken under exactly this load.
+    # (the iteration count is fixed by rank 0 and broadcast: every rank must issue the same number of collectives)
     t_soak = time.perf_counter()
-    while time.perf_counter() - t_soak < 0.4:
+    for _ in range(5):
         step_resident(False)
-        stream.synchronize()
+    stream.synchronize()
+    n_soak = torch.tensor([max(5, min(20000, int(0.4 / max((time.perf_counter() - t_soak) / 5, 1e-6))))],
+                          dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(n_soak, src=0)
+    for _ in range(int(n_soak.item())):
+        step_resident(False)
+    stream.synchronize()
     barrier()
 
     # ---- timed: K resident steps (CUDA events on the launching stream, L2 flushed between iterations) ----

@@ -329,7 +329,9 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ks.launch_count() - launches0
-    # same K steps again with per-kernel CUDA events inside the library (dominant-kernel duration for the roofline)
+    # same K steps again with per-kernel CUDA events inside the library (dominant-kernel duration for the roofline;
+    # in this mode the library runs the argmax scan after the mask kernel instead of beside it, so the event pair
+    # times k_mask_bitpar alone - the measured HBM peak it is compared with is also a kernel timed alone)
     for k in range(args.steps):
         with torch.cuda.stream(stream):
             flush.fill_(k & 0xFF)

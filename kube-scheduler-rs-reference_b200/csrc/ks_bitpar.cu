@@ -877,9 +877,12 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
                                                  need_mask_pass ? ix.hist : nullptr, ix.pod_bin, ix.pod_loc);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // argmax scan on an auxiliary stream so that it overlaps the mask kernel (it needs only the pod ranks)
+    // argmax scan (needs only the pod ranks).  Normally it runs on an auxiliary stream so that it overlaps the mask
+    // kernel; with per-kernel timing requested it runs after the mask kernel instead, so that the event pair around
+    // the mask kernel times that kernel alone.
     const bool want_bind = L.ov.node_idx || L.ov.score;
-    if (want_bind) {
+    const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
+    auto enqueue_bind = [&]() -> cudaError_t {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
         uint32_t* tail_count = ix.tail_list + ix.cap_pods;
@@ -903,7 +906,7 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
             if ((e = cudaMemcpyAsync(L.host_score, L.ov.score, (size_t)P * 8, cudaMemcpyDeviceToHost, ix.aux)) != cudaSuccess) return e;
             L.host_score = nullptr;
         }
-        if (L.ready_event) { // tell the caller that node_idx / score are final (the mask pass is still running)
+        if (L.ready_event) { // tell the caller that node_idx / score are final (the mask pass may still be running)
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             if ((e = cudaStreamIsCapturing(ix.aux, &cs)) != cudaSuccess) return e;
             e = cudaEventRecordWithFlags(L.ready_event, ix.aux,
@@ -911,8 +914,10 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
             if (e != cudaSuccess) return e;
             L.ready_event = nullptr;
         }
-        if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
-    }
+        return cudaEventRecord(ix.ev_join, ix.aux);
+    };
+    if (want_bind && overlap_bind)
+        if ((e = enqueue_bind()) != cudaSuccess) return e;
     if (need_mask_pass) {
         const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 64
         k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, ix.hist + 65536);
@@ -940,6 +945,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     } else if (before_mask) {
         if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
     }
+    if (want_bind && !overlap_bind)
+        if ((e = enqueue_bind()) != cudaSuccess) return e;
     if (want_bind)
         if ((e = cudaStreamWaitEvent(L.stream, ix.ev_join, 0)) != cudaSuccess) return e;
     if (after_mask && !need_mask_pass)

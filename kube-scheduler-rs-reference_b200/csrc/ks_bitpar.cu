@@ -725,8 +725,8 @@ static cudaError_t regrow(T*& p, size_t count) {
 }
 
 void bitpar_release(BitparIndex& ix) {
-    void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_fc,  ix.ord_fm,   ix.ord_prio,
-                    ix.ord_lab, ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
+    void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
+                    ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
                     ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist,
                     ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm};
     for (void* p : ptrs)

@@ -34,10 +34,7 @@ struct BitparIndex {
     int64_t* sortedM = nullptr;  // [N] free_mem ascending
     uint32_t* gposC = nullptr;   // [N] position of node n in sortedC (ties by node index)
     uint32_t* gposM = nullptr;
-    int64_t* ord_fc = nullptr;   // nodes in descending priority order (ties by node index), padded to 32
-    int64_t* ord_fm = nullptr;
-    int64_t* ord_prio = nullptr;
-    uint64_t* ord_lab = nullptr; // word-major [W][Nord]
+    int64_t* ord_prio = nullptr; // nodes in descending priority order (ties by node index), padded to a tile
     int32_t* ord_idx = nullptr;
     int64_t* splC = nullptr;     // every `spl_stride`-th element of sortedC / sortedM (<= 1024 splitters)
     int64_t* splM = nullptr;
@@ -58,7 +55,7 @@ struct BitparIndex {
     uint8_t* rk_bkt = nullptr;
     uint32_t* rk_loc = nullptr;
     uint32_t* rk_perm = nullptr;
-    size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_lab = 0, cap_sel = 0;
+    size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_sel = 0;
     uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
     BitparLayout lay{}, layP{};
     bool valid = false;

@@ -358,3 +358,44 @@ def test_bindings_ready_event_orders_a_side_stream(ks, orc):
             assert np.array_equal(early_idx.cpu().numpy(), o[0]), it
             assert np.array_equal(early_score.cpu().numpy(), o[1]), it
             assert np.array_equal(cnt.cpu().numpy().view(np.uint32), o[2]), it
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("seed,P,N,W", [(1, 3000, 700, 1), (2, 20000, 1100, 2), (3, 9000, 5000, 1), (4, 70000, 300, 4)])
+def test_adversarial_values(ks, orc, path, seed, P, N, W):
+    """Unstructured inputs: heavy ties in free values, negative and zero requests, values at the API limits, dense
+    random selector words (many required bits, bits no node carries), nodes with negative free - vs the oracle."""
+    rng = np.random.default_rng(seed)
+    lim_c, lim_m = 1 << 36, 1 << 55
+    pool_c = np.array([-5, 0, 1, 250, 1000, 1000, 4000, 64000, lim_c], np.int64)
+    pool_m = np.array([-1, 0, 1, 1 << 20, 1 << 30, 1 << 30, 1 << 34, lim_m], np.int64)
+    ac = rng.choice(pool_c, N)
+    am = rng.choice(pool_m, N)
+    lab = rng.integers(0, 1 << 63, size=(N, W), dtype=np.uint64) & rng.integers(0, 1 << 63, size=(N, W), dtype=np.uint64)
+    B = 3 * N
+    bn = rng.integers(0, N, B).astype(np.int32)
+    bc = rng.choice(np.array([0, 0, 100, 1000, -100], np.int64), B)
+    bm = rng.choice(np.array([0, 1, 1 << 20, 1 << 28, -1], np.int64), B)
+    rc = rng.choice(np.array([-1000, 0, 0, 1, 250, 1000, 1001, 4000, 63999, lim_c], np.int64), P)
+    rm = rng.choice(np.array([-1, 0, 1, (1 << 20) - 1, 1 << 20, 1 << 30, (1 << 30) + 1, lim_m], np.int64), P)
+    sel = np.zeros((P, W), np.uint64)
+    k = rng.integers(0, 10, P)  # 0..9 required bits per pod, taken from some node's labels or random
+    for p in np.nonzero(k)[0]:
+        src = lab[rng.integers(0, N)] if rng.random() < 0.7 else rng.integers(0, 1 << 63, size=W, dtype=np.uint64)
+        bits = [(w, b) for w in range(W) for b in range(64) if (int(src[w]) >> b) & 1]
+        for i in rng.permutation(len(bits))[:k[p]]:
+            w, b = bits[i]
+            sel[p, w] |= np.uint64(1) << np.uint64(b)
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes(ac, am, lab)
+        snap.set_bound(bn, bc, bm)
+        fc, fm = snap.free()
+        ofc, ofm = orc.free_reduce(ac, am, bn, bc, bm)
+        assert np.array_equal(fc, ofc) and np.array_equal(fm, ofm)
+        r = snap.select(rc, rm, sel, flags=PATHS[path], want_mask=True)
+        o = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel)
+        _assert_same(r, o, f"adversarial {path} seed {seed}")
+        if path == "direct":
+            r1 = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, want_mask=False)
+            o1 = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=1, want_mask=False)
+            assert np.array_equal(r1.node_idx, o1[0]) and np.array_equal(r1.score, o1[1])

@@ -367,8 +367,8 @@ def test_adversarial_values(ks, orc, path, seed, P, N, W):
     random selector words (many required bits, bits no node carries), nodes with negative free - vs the oracle."""
     rng = np.random.default_rng(seed)
     lim_c, lim_m = 1 << 36, 1 << 55
-    pool_c = np.array([-5, 0, 1, 250, 1000, 1000, 4000, 64000, lim_c], np.int64)
-    pool_m = np.array([-1, 0, 1, 1 << 20, 1 << 30, 1 << 30, 1 << 34, lim_m], np.int64)
+    pool_c = np.array([-5, 0, 1, 250, 1000, 1000, 4000, 64000, lim_c // 2], np.int64)  # free must stay within the limits
+    pool_m = np.array([-1, 0, 1, 1 << 20, 1 << 30, 1 << 30, 1 << 34, lim_m // 2], np.int64)
     ac = rng.choice(pool_c, N)
     am = rng.choice(pool_m, N)
     lab = rng.integers(0, 1 << 63, size=(N, W), dtype=np.uint64) & rng.integers(0, 1 << 63, size=(N, W), dtype=np.uint64)

@@ -51,6 +51,19 @@ int ksh_context_set_nodes(ksh_context* ctx, const ks_node_obj* nodes, uint32_t n
 /* every pod object the API server holds; those with spec.nodeName naming a known node are the LIST results
  * of src/predicates.rs:22-34 (any phase) and are charged to that node; the rest are ignored here. */
 int ksh_context_set_cluster_pods(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods);
+/* Incremental node-store / informer events (what the reflector applies between reconciles, src/main.rs:133-139):
+ * - upsert: add a node or replace the one with the same metadata.name; *out_idx = its index
+ * - remove: delete by name; later nodes move down by one index (indices are positions in the current store;
+ *   ksh_context_node_name maps an index back to the name a Binding needs)
+ * - pod_bound / pod_deleted: a pod with spec.nodeName appeared / went away; capacity is charged / returned.
+ *   Pods are identified by namespace/name; unknown pods or nodes are ignored (KS_OK), like a LIST that no
+ *   longer shows them.
+ * The device snapshot is refreshed lazily on the next select/check call. */
+int ksh_context_upsert_node(ksh_context* ctx, const ks_node_obj* node, uint32_t* out_idx);
+int ksh_context_remove_node(ksh_context* ctx, const char* name);
+int ksh_context_pod_bound(ksh_context* ctx, const ks_pod_obj* pod);
+int ksh_context_pod_deleted(ksh_context* ctx, const ks_pod_obj* pod);
+const char* ksh_context_node_name(const ksh_context* ctx, uint32_t node_idx); /* NULL if out of range */
 uint32_t ksh_context_num_nodes(const ksh_context* ctx);
 uint32_t ksh_context_label_words(const ksh_context* ctx);
 ks_snapshot* ksh_context_snapshot(ksh_context* ctx); /* borrowed; valid until the next ksh_context_* mutation */

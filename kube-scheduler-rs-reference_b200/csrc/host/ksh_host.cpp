@@ -139,8 +139,77 @@ struct ksh_context {
     std::vector<int64_t> alloc_cpu, alloc_mem;
     std::vector<int32_t> bnode;
     std::vector<int64_t> bcpu, bmem;
+    std::vector<std::string> bkey;                    // "namespace/name" of each bound pod ("" = unknown)
+    std::unordered_map<std::string, size_t> bkey2pos; // bound pod -> position in the four lists above
     bool dirty = true; // device snapshot must be re-uploaded
 };
+
+static std::string pod_key(const ks_pod_obj* pod) {
+    std::string k(pod->ns ? pod->ns : "");
+    k.push_back('/');
+    k.append(pod->name ? pod->name : "");
+    return k;
+}
+
+static void bound_push(ksh_context* c, const std::string& key, int32_t node, int64_t cpu, int64_t mem) {
+    if (!key.empty() && key != "/") c->bkey2pos[key] = c->bnode.size();
+    c->bnode.push_back(node);
+    c->bcpu.push_back(cpu);
+    c->bmem.push_back(mem);
+    c->bkey.push_back(key);
+}
+
+static void bound_erase(ksh_context* c, size_t pos) { // swap-remove
+    const size_t last = c->bnode.size() - 1;
+    c->bkey2pos.erase(c->bkey[pos]);
+    if (pos != last) {
+        c->bnode[pos] = c->bnode[last];
+        c->bcpu[pos] = c->bcpu[last];
+        c->bmem[pos] = c->bmem[last];
+        c->bkey[pos] = c->bkey[last];
+        if (!c->bkey[pos].empty() && c->bkey[pos] != "/") c->bkey2pos[c->bkey[pos]] = pos;
+    }
+    c->bnode.pop_back();
+    c->bcpu.pop_back();
+    c->bmem.pop_back();
+    c->bkey.pop_back();
+}
+
+// parse one node object into (allocatable, label pairs); mirrors src/predicates.rs:27-32
+static int parse_node(const ks_node_obj& nd, std::string* name, int64_t* ac, int64_t* am, std::vector<std::string>* pairs) {
+    *name = nd.name ? nd.name : "";
+    *ac = 0;
+    *am = 0; // status/allocatable None => PodResources::new() = (0,0)   (predicates.rs:27-28)
+    if (nd.has_allocatable) {
+        const char* q = kv_find(nd.allocatable, nd.n_allocatable, "cpu");
+        if (!q) return fail(KS_ERR_MISSING, "node '" + *name + "': allocatable has no cpu (reference panics, predicates.rs:29)");
+        int rc = ksh_parse_cpu_millicores(q, ac);
+        if (rc) return rc;
+        q = kv_find(nd.allocatable, nd.n_allocatable, "memory");
+        if (!q) return fail(KS_ERR_MISSING, "node '" + *name + "': allocatable has no memory (reference panics, predicates.rs:30)");
+        rc = ksh_parse_memory_bytes(q, am);
+        if (rc) return rc;
+        if (*ac > KS_MAX_CPU_MILLI || *ac < -KS_MAX_CPU_MILLI || *am > KS_MAX_MEM_BYTES || *am < -KS_MAX_MEM_BYTES)
+            return fail(KS_ERR_RANGE, "node '" + *name + "': allocatable out of range");
+    }
+    pairs->clear();
+    if (nd.has_labels)
+        for (uint32_t l = 0; l < nd.n_labels; l++) pairs->push_back(pair_key(nd.labels[l].key, nd.labels[l].val));
+    return KS_OK;
+}
+
+// pairs carried by at least one node, and dictionary bits restricted to them
+static void rebuild_pair_universe(ksh_context* c) {
+    c->all_pairs.clear();
+    for (const auto& v : c->node_pairs)
+        for (const auto& p : v) c->all_pairs.insert(p);
+    std::unordered_map<std::string, uint32_t> kept;
+    for (auto& kv : c->dict)
+        if (c->all_pairs.count(kv.first)) kept.emplace(kv.first, (uint32_t)kept.size());
+    c->dict.swap(kept);
+    c->W = 1;
+    while ((uint64_t)c->W * 64 < (uint64_t)c->dict.size() + 1) c->W <<= 1;
+}
 
 static uint32_t words_for_bits(uint32_t real_bits) {
     // +1: the last bit of the last word is the shared "no node carries this pair" bit
@@ -308,28 +377,115 @@ int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) 
     c->bnode.clear();
     c->bcpu.clear();
     c->bmem.clear();
+    c->bkey.clear();
+    c->bkey2pos.clear();
     c->dirty = true;
     return KS_OK;
 }
 
+int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* out_idx) {
+    if (!c || !node) return fail(KS_ERR_INVALID, "NULL argument");
+    std::string name;
+    int64_t ac, am;
+    std::vector<std::string> pairs;
+    int rc = parse_node(*node, &name, &ac, &am, &pairs);
+    if (rc) return rc;
+    auto it = c->name2idx.find(name);
+    uint32_t idx;
+    if (it == c->name2idx.end()) {
+        idx = c->N++;
+        c->node_names.push_back(name);
+        c->alloc_cpu.push_back(ac);
+        c->alloc_mem.push_back(am);
+        c->node_pairs.push_back(pairs);
+        c->name2idx.emplace(name, idx);
+    } else {
+        idx = it->second;
+        c->alloc_cpu[idx] = ac;
+        c->alloc_mem[idx] = am;
+        c->node_pairs[idx] = pairs;
+    }
+    rebuild_pair_universe(c);
+    c->dirty = true;
+    if (out_idx) *out_idx = idx;
+    return KS_OK;
+}
+
+int ksh_context_remove_node(ksh_context* c, const char* name) {
+    if (!c || !name) return fail(KS_ERR_INVALID, "NULL argument");
+    auto it = c->name2idx.find(name);
+    if (it == c->name2idx.end()) return KS_OK;
+    const uint32_t idx = it->second;
+    c->node_names.erase(c->node_names.begin() + idx);
+    c->alloc_cpu.erase(c->alloc_cpu.begin() + idx);
+    c->alloc_mem.erase(c->alloc_mem.begin() + idx);
+    c->node_pairs.erase(c->node_pairs.begin() + idx);
+    c->N--;
+    c->name2idx.clear();
+    for (uint32_t i = 0; i < c->N; i++) c->name2idx.emplace(c->node_names[i], i);
+    // pods bound to the removed node disappear from every later LIST; indices above it move down
+    for (size_t p = 0; p < c->bnode.size();) {
+        if ((uint32_t)c->bnode[p] == idx) {
+            bound_erase(c, p);
+        } else {
+            if ((uint32_t)c->bnode[p] > idx) c->bnode[p]--;
+            p++;
+        }
+    }
+    rebuild_pair_universe(c);
+    c->dirty = true;
+    return KS_OK;
+}
+
+int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
+    if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
+    if (!ksh_is_pod_bound(pod)) return KS_OK;
+    auto it = c->name2idx.find(pod->node_name);
+    if (it == c->name2idx.end()) return KS_OK;
+    int64_t cpu, mem;
+    int rc = ksh_total_pod_resources(pod, &cpu, &mem);
+    if (rc) return rc;
+    const std::string key = pod_key(pod);
+    auto old = c->bkey2pos.find(key);
+    if (old != c->bkey2pos.end()) bound_erase(c, old->second); // update of a pod already known
+    bound_push(c, key, (int32_t)it->second, cpu, mem);
+    c->dirty = true;
+    return KS_OK;
+}
+
+int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
+    if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
+    auto it = c->bkey2pos.find(pod_key(pod));
+    if (it == c->bkey2pos.end()) return KS_OK;
+    bound_erase(c, it->second);
+    c->dirty = true;
+    return KS_OK;
+}
+
+const char* ksh_context_node_name(const ksh_context* c, uint32_t idx) {
+    return (c && idx < c->N) ? c->node_names[idx].c_str() : nullptr;
+}
+
 int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
-    std::vector<int32_t> bn;
-    std::vector<int64_t> bc, bm;
+    // validate first, then replace
+    std::vector<int64_t> cpus(n), mems(n);
+    for (uint64_t p = 0; p < n; p++) {
+        if (!ksh_is_pod_bound(&pods[p]) || !c->name2idx.count(pods[p].node_name)) continue;
+        int rc = ksh_total_pod_resources(&pods[p], &cpus[p], &mems[p]); // predicates.rs:37
+        if (rc) return rc;
+    }
+    c->bnode.clear();
+    c->bcpu.clear();
+    c->bmem.clear();
+    c->bkey.clear();
+    c->bkey2pos.clear();
     for (uint64_t p = 0; p < n; p++) {
         if (!ksh_is_pod_bound(&pods[p])) continue;
         auto it = c->name2idx.find(pods[p].node_name); // field selector spec.nodeName=<node> (predicates.rs:22-25)
         if (it == c->name2idx.end()) continue;
-        int64_t cpu, mem;
-        int rc = ksh_total_pod_resources(&pods[p], &cpu, &mem); // predicates.rs:37
-        if (rc) return rc;
-        bn.push_back((int32_t)it->second);
-        bc.push_back(cpu);
-        bm.push_back(mem);
+        bound_push(c, pod_key(&pods[p]), (int32_t)it->second, cpus[p], mems[p]);
     }
-    c->bnode.swap(bn);
-    c->bcpu.swap(bc);
-    c->bmem.swap(bm);
     c->dirty = true;
     return KS_OK;
 }
@@ -410,9 +566,7 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
     // what the next LIST would report once the binding is accepted (src/predicates.rs:34 after src/main.rs:103)
     rc = ks_snapshot_apply_bind(c->snap, idx, cpu, mem);
     if (rc) return rc;
-    c->bnode.push_back(idx);
-    c->bcpu.push_back(cpu);
-    c->bmem.push_back(mem);
+    bound_push(c, pod_key(pod), idx, cpu, mem);
     *node_idx = idx;
     if (json && cap) { // corev1::Binding{metadata, target: ObjectReference{name}}  (src/main.rs:83-91)
         std::string s = "{\"apiVersion\":\"v1\",\"kind\":\"Binding\",\"metadata\":{\"name\":\"";

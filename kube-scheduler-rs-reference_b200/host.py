@@ -18,6 +18,11 @@ for _name, _res, _args in [
     ("ksh_context_destroy", None, [_vp]),
     ("ksh_context_set_nodes", C.c_int, [_vp, _vp, C.c_uint32]),
     ("ksh_context_set_cluster_pods", C.c_int, [_vp, _vp, C.c_uint64]),
+    ("ksh_context_upsert_node", C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
+    ("ksh_context_remove_node", C.c_int, [_vp, C.c_char_p]),
+    ("ksh_context_pod_bound", C.c_int, [_vp, _vp]),
+    ("ksh_context_pod_deleted", C.c_int, [_vp, _vp]),
+    ("ksh_context_node_name", C.c_char_p, [_vp, C.c_uint32]),
     ("ksh_context_num_nodes", C.c_uint32, [_vp]),
     ("ksh_context_label_words", C.c_uint32, [_vp]),
     ("ksh_context_snapshot", _vp, [_vp]),
@@ -99,6 +104,36 @@ class Context:
     @property
     def label_words(self):
         return int(lib.ksh_context_label_words(self._h))
+
+    @property
+    def n_nodes(self):
+        return int(lib.ksh_context_num_nodes(self._h))
+
+    def upsert_node(self, nodes, i=0):
+        idx = C.c_uint32()
+        rc = lib.ksh_context_upsert_node(self._h, _addr(nodes, i), C.byref(idx))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_context_upsert_node")
+        return idx.value
+
+    def remove_node(self, name):
+        rc = lib.ksh_context_remove_node(self._h, name.encode())
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_context_remove_node")
+
+    def pod_bound(self, pods, i=0):
+        rc = lib.ksh_context_pod_bound(self._h, _addr(pods, i))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_context_pod_bound")
+
+    def pod_deleted(self, pods, i=0):
+        rc = lib.ksh_context_pod_deleted(self._h, _addr(pods, i))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_context_pod_deleted")
+
+    def node_name(self, idx):
+        n = lib.ksh_context_node_name(self._h, int(idx))
+        return None if n is None else n.decode()
 
     def pack_pods(self, pods, n):
         rc_ = np.empty(n, np.int64)

@@ -143,3 +143,49 @@ def test_reconcile_mirror(ks, orc):
         assert ctx.reconcile(pods, 2)[:2] == (ks.host.KSH_RECONCILE_NO_NODE_FOUND, -1)
         assert ctx.reconcile(pods, 3) == (0, -1, "")          # already bound -> await_change, no binding
         assert ctx.reconcile(pods, 4)[:2] == (ks.host.KSH_RECONCILE_NO_NODE_FOUND, -1)
+
+
+@pytest.mark.gpu
+def test_incremental_node_and_pod_events_equal_a_rebuilt_context(ks, orc):
+    """upsert/remove node and pod bound/deleted events must leave the context in the state a full rebuild from the
+    final objects gives (compared through the faithful oracle on that final cluster)."""
+    cl = ks.synth.make(120, 40, seed=11, bound_per_node=2)
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    pods = arena.pods(pods_s)
+    # start from the first 30 nodes and their bound pods
+    first_nodes = arena.nodes(nodes_s[:30])
+    first_bound_s = [b for b in bound_s if int(b["node_name"].split("-")[1]) < 30]
+    first_bound = arena.pods(first_bound_s)
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(first_nodes, 30)
+        ctx.set_cluster_pods(first_bound, len(first_bound_s))
+        # events: 10 more nodes, their bound pods, one node changes size, one node goes away, two pods are deleted
+        rest_nodes = arena.nodes(nodes_s[30:])
+        for i in range(10):
+            assert ctx.upsert_node(rest_nodes, i) == 30 + i
+        rest_bound_s = [b for b in bound_s if int(b["node_name"].split("-")[1]) >= 30]
+        rest_bound = arena.pods(rest_bound_s)
+        for i in range(len(rest_bound_s)):
+            ctx.pod_bound(rest_bound, i)
+        changed = dict(nodes_s[5])
+        changed["allocatable"] = {"cpu": "128", "memory": str(1 << 40)}
+        assert ctx.upsert_node(arena.nodes([changed])) == 5
+        ctx.remove_node("node-7")
+        gone = [b for b in first_bound_s if b["node_name"] == "node-3"][:2]
+        gone_objs = arena.pods(gone)
+        for i in range(len(gone)):
+            ctx.pod_deleted(gone_objs, i)
+        ctx.pod_deleted(arena.pods([{"name": "never-seen", "ns": "x", "node_name": "node-1"}]))  # ignored
+        assert ctx.n_nodes == 39 and ctx.node_name(7) == "node-8" and ctx.node_name(39) is None
+        idx, score, cnt = ctx.select_nodes(pods, cl.P)
+        names = [ctx.node_name(i) if i >= 0 else None for i in idx]
+    # the same final cluster, built from scratch, through the faithful oracle
+    final_nodes_s = [changed if n["name"] == "node-5" else n for n in nodes_s if n["name"] != "node-7"]
+    gone_names = {g["name"] for g in gone}
+    final_bound_s = [b for b in bound_s if b["node_name"] != "node-7" and b["name"] not in gone_names]
+    fn, fb = arena.nodes(final_nodes_s), arena.pods(final_bound_s)
+    oc = orc.Cluster(fn, len(final_nodes_s), fb, len(final_bound_s))
+    oidx, oscore, ocnt, _, _ = oc.run(pods, cl.P)
+    assert np.array_equal(idx, oidx) and np.array_equal(score, oscore) and np.array_equal(cnt, ocnt)
+    assert names == [final_nodes_s[i]["name"] if i >= 0 else None for i in oidx]

@@ -19,7 +19,7 @@ import numpy as np  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rate", type=float, default=10000.0)
-    ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--seconds", type=float, default=10.0)  # >= 10 s of arrivals
     ap.add_argument("--nodes", type=int, default=50000)
     ap.add_argument("--policy", default="leftover")
     args = ap.parse_args()

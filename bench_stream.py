@@ -79,12 +79,14 @@ def main():
     total = time.perf_counter() - t0
     lat_ms = np.asarray(lat) * 1e3
     fc, fm = snap.free()
+    fc0, fm0 = cl.free()  # the synthetic cluster starts with a few oversubscribed nodes by construction
+    newly_over = int((((fc < 0) & (fc0 >= 0)) | ((fm < 0) & (fm0 >= 0))).sum())
     line = {"metric": "stream_bind_latency_ms", "config": {"workload": f"c5: Poisson {args.rate:.0f} pods/s for {args.seconds}s vs {args.nodes} nodes",
             "world": world, "rank": rank, "policy": args.policy},
             "p50_ms": float(np.percentile(lat_ms, 50)), "p99_ms": float(np.percentile(lat_ms, 99)), "max_ms": float(lat_ms.max()),
             "pods": int(len(ids)), "bound": bound, "binds_per_s": bound / total, "mean_batch": float(np.mean(batches)),
             "max_batch": int(np.max(batches)), "mean_rounds": float(np.mean(rounds_l)),
-            "min_free_cpu_after": int(fc.min()), "replica_checksum": int((fc.sum() * 31 + fm.sum()) % (1 << 61)),
+            "nodes_oversubscribed_by_stream": newly_over, "min_free_cpu_after": int(fc.min()), "min_free_cpu_before": int(fc0.min()), "replica_checksum": int((fc.sum() * 31 + fm.sum()) % (1 << 61)),
             "gpu_launches": ks.launch_count()}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -418,6 +418,17 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if world == 1:
+        # for information: the reference's own policy (<=5 seeded draws per pod, src/main.rs:49-71) on the same batch,
+        # host buffers in and out; it evaluates <=5 cells per pod, so it is quoted in pods/s, not cells/s
+        snap.select_sampling(rc[:1024], rm[:1024], sel[:1024], seed=seed)
+        t0 = time.perf_counter()
+        s_idx, s_used, _, _ = snap.select_sampling(rc, rm, sel, seed=seed)
+        t_s = time.perf_counter() - t0
+        a_idx = h_bind[8 * P:12 * P].numpy().view(np.int32)
+        line["reference_policy"] = {"pods_per_s": P / t_s, "cells_evaluated": int(s_used.sum()),
+                                    "bound_frac": float((s_idx >= 0).mean()), "argmax_bound_frac": float((a_idx >= 0).mean()),
+                                    "note": "ks_select_sampling, ATTEMPTS=5, seeded; not part of value/e2e"}
     if world == 1 and not args.no_cpu_baseline:
         # second CPU figure (BASELINE.md §3 "CPU-packed"): the same SoA int64 + bitmask algorithm the GPU runs, C,
         # all host threads, on a pod sample — what a well-written CPU scheduler core could do with packed inputs

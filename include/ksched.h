@@ -141,6 +141,22 @@ int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n_claims, const int32_t* 
 int ks_stream_bind(ks_snapshot* s, const ks_pods* pods /* host space */, int policy, int32_t* out_node_idx,
                    int64_t* out_score, uint32_t* out_rounds);
 
+/* ---- the reference's own selection policy, seeded (src/main.rs:49-71; ATTEMPTS = 5 at :49) ----
+ * For every pod: up to `attempts` draws, uniform with replacement over the snapshot's nodes (:56-57); the first
+ * draw whose cell is KS_CELL_OK wins (:61-66); none -> -1 (= None -> ReconcileError::NoNodeFound, :70, :116-118)
+ * even when a feasible node exists.  The reference draws from thread_rng; here draw k of pod p is
+ * splitmix64 step k of a stream whose state starts at KS_SAMPLING_STREAM(seed, p), node = draw % N, so a run is
+ * reproducible and replicas agree.  An empty snapshot wastes every attempt (:56,60): -1, 0 cells.
+ * Host output arrays; all but out_node_idx may be NULL:
+ *   out_node_idx[P]; out_attempts[P] = cells evaluated; out_draw_node[P*attempts] = node of each draw (-1 = not
+ *   made); out_draw_code[P*attempts] = that cell's code, i.e. the InvalidNodeReason the reference logs at :62
+ *   (0xff = not made).  first_pod_index offsets p in the stream id (pod i of this call is stream
+ *   first_pod_index + i), so a sharded or chunked caller reproduces the single-call result. */
+#define KS_REFERENCE_ATTEMPTS 5u
+#define KS_SAMPLING_STREAM(seed, p) ((uint64_t)(seed) ^ (((uint64_t)(p) + 1ull) * 0xD1B54A32D192ED03ull))
+int ks_select_sampling(ks_snapshot* s, const ks_pods* pods, uint32_t attempts, uint64_t seed, uint64_t first_pod_index,
+                       int32_t* out_node_idx, uint32_t* out_attempts, int32_t* out_draw_node, uint8_t* out_draw_code);
+
 #ifdef __cplusplus
 }
 #endif

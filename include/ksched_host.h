@@ -9,6 +9,7 @@
  *   ksh_context               <- Context{client,node_store}     src/util.rs:12-15 (+ the LIST of src/predicates.rs:21-38)
  *   ksh_check_node_validity   <- check_node_validity            src/predicates.rs:63-77
  *   ksh_select_nodes          <- select_node_for_pod, batched   src/main.rs:51-71 (argmax score instead of 5 random draws)
+ *   ksh_select_node_for_pod   <- select_node_for_pod, seeded    src/main.rs:49-71 (the reference's own 5-draw policy)
  *   ksh_reconcile             <- reconcile                      src/main.rs:73-120 (builds the Binding, does not POST it)
  *   KSH_RECONCILE_*           <- ReconcileError                 src/error.rs:5-15
  * The layer packs objects into the SoA/bitmask form of ksched.h and calls the CUDA core; it never evaluates
@@ -77,6 +78,13 @@ int ksh_pack_pods(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int
 int ksh_check_node_validity(ksh_context* ctx, const ks_pod_obj* pod, uint32_t node_idx);
 int ksh_select_nodes(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int policy, int32_t* out_node_idx,
                      int64_t* out_score, uint32_t* out_feasible_cnt);
+
+/* select_node_for_pod with the reference's OWN policy (src/main.rs:49-71): <= attempts seeded random draws per pod,
+ * first valid draw wins, -1 = None.  Arguments as ks_select_sampling (ksched.h); pass KS_REFERENCE_ATTEMPTS for the
+ * reference's ATTEMPTS.  out_draw_code holds the InvalidNodeReason of each failed draw (what src/main.rs:62 logs). */
+int ksh_select_node_for_pod(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, uint32_t attempts, uint64_t seed,
+                            uint64_t first_pod_index, int32_t* out_node_idx, uint32_t* out_attempts,
+                            int32_t* out_draw_node, uint8_t* out_draw_code);
 
 /* One reconcile: skip bound pods, select, emit `POST /api/v1/namespaces/{ns}/pods/{name}/binding` body, and
  * charge the pod to the chosen node in the snapshot (what the next LIST would show).  *node_idx = -1 if none.

@@ -12,5 +12,6 @@ from ._capi import (  # noqa: F401
     KS_CELL_OK, KS_CELL_NOT_ENOUGH_RESOURCES, KS_CELL_NODE_SELECTOR_MISMATCH,
     KsError, lib, LIB_PATH, declared_symbols, mask_row_bytes, device_count, launch_count,
 )
+from . import _capi as capi  # noqa: F401
 from .snapshot import Snapshot, SelectResult  # noqa: F401
 from . import synth, objects, host, multigpu  # noqa: F401

@@ -69,6 +69,16 @@ _proto("ks_snapshot_commit_claims", C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
 _proto("ks_stream_bind", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_int, C.c_void_p, C.c_void_p,
        C.POINTER(C.c_uint32))
 
+_proto("ks_select_sampling", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p,
+       C.c_void_p, C.c_void_p, C.c_void_p)
+KS_REFERENCE_ATTEMPTS = 5
+_SAMPLING_MULT = 0xD1B54A32D192ED03
+
+
+def sampling_stream(seed, p):
+    """KS_SAMPLING_STREAM(seed, p) of include/ksched.h: start state of pod p's splitmix64 draw stream."""
+    return (seed ^ (((p + 1) * _SAMPLING_MULT) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+
 
 def declared_symbols():
     """Every function name declared in include/*.h (used by the CPU test that checks the export table)."""

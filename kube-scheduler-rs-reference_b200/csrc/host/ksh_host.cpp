@@ -547,6 +547,20 @@ int ksh_select_nodes(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int pol
     return ks_select(c->snap, &kp, policy, KS_SELECT_AUTO, &kb, nullptr);
 }
 
+int ksh_select_node_for_pod(ksh_context* c, const ks_pod_obj* pods, uint64_t n, uint32_t attempts, uint64_t seed,
+                            uint64_t first_pod_index, int32_t* out_node_idx, uint32_t* out_attempts,
+                            int32_t* out_draw_node, uint8_t* out_draw_code) {
+    if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
+    if (n == 0) return KS_OK;
+    std::vector<int64_t> rc_, rm_;
+    std::vector<uint64_t> sel;
+    int rc = pack_and_upload(c, pods, n, rc_, rm_, sel);
+    if (rc) return rc;
+    ks_pods kp{n, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
+    return ks_select_sampling(c->snap, &kp, attempts, seed, first_pod_index, out_node_idx, out_attempts, out_draw_node,
+                              out_draw_code);
+}
+
 int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* json, size_t cap) {
     if (!c || !pod || !node_idx) return fail(KS_ERR_INVALID, "NULL argument");
     *node_idx = -1;

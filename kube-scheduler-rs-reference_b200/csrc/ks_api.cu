@@ -62,7 +62,7 @@ struct ks_snapshot {
     uint32_t N = 0, Npad = 0, W = 1;
     DevBuf alloc_cpu, alloc_mem, free_cpu, free_mem, prio, labels, flag;
     DevBuf st_rc, st_rm, st_sel, st_idx, st_score, st_cnt, st_mask, st_codes, st_bnode, st_bcpu, st_bmem;
-    DevBuf part_key, part_idx, part_cnt;
+    DevBuf part_key, part_idx, part_cnt, st_samp;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host-space calls are pipelined in pod chunks: chunk c+1 is copied in on copy_stream while chunk c computes
     cudaStream_t copy_stream = nullptr;
@@ -160,7 +160,7 @@ void ks_snapshot_destroy(ks_snapshot* s) {
     DevBuf* bufs[] = {&s->alloc_cpu, &s->alloc_mem, &s->free_cpu, &s->free_mem, &s->prio,     &s->labels,
                       &s->flag,      &s->st_rc,     &s->st_rm,    &s->st_sel,   &s->st_idx,   &s->st_score,
                       &s->st_cnt,    &s->st_mask,   &s->st_codes, &s->st_bnode, &s->st_bcpu,  &s->st_bmem,
-                      &s->part_key,  &s->part_idx,  &s->part_cnt};
+                      &s->part_key,  &s->part_idx,  &s->part_cnt, &s->st_samp};
     for (DevBuf* b : bufs) b->release();
     bitpar_release(s->bp);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -670,6 +670,43 @@ int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n, const int32_t* claim_n
                                      s->st_codes.as<uint8_t>() + off, s->stream));
     }
     CU_TRY(cudaMemcpyAsync(out_accepted, s->st_codes.p, n, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KS_OK;
+}
+
+int ks_select_sampling(ks_snapshot* s, const ks_pods* pods, uint32_t attempts, uint64_t seed, uint64_t first_pod_index,
+                       int32_t* out_node_idx, uint32_t* out_attempts, int32_t* out_draw_node, uint8_t* out_draw_code) {
+    int rc = check_pods(s, pods);
+    if (rc) return rc;
+    const uint64_t P = pods->n;
+    if (P && !out_node_idx) return fail(KS_ERR_INVALID, "out_node_idx is NULL");
+    if (attempts > 64) return fail(KS_ERR_RANGE, "attempts must be <= 64 (the reference uses %u)", KS_REFERENCE_ATTEMPTS);
+    if (P == 0) return KS_OK;
+    const uint64_t draws = P * (uint64_t)attempts;
+    if (s->N == 0 || attempts == 0) { // choose() on an empty store is None for every attempt (main.rs:56,60)
+        for (uint64_t i = 0; i < P; i++) out_node_idx[i] = -1;
+        if (out_attempts) memset(out_attempts, 0, P * 4);
+        if (out_draw_node) memset(out_draw_node, 0xff, draws * 4);
+        if (out_draw_code) memset(out_draw_code, 0xff, draws);
+        return KS_OK;
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    PodView pv;
+    rc = stage_pods(s, pods, s->stream, &pv);
+    if (rc) return rc;
+    // one scratch buffer: node_idx[P] | attempts[P] | draw_node[P*attempts] | draw_code[P*attempts]
+    const size_t off_att = P * 4, off_dn = off_att + P * 4, off_dc = off_dn + draws * 4;
+    CU_TRY(s->st_samp.ensure(off_dc + draws));
+    uint8_t* base = s->st_samp.as<uint8_t>();
+    CU_TRY(launch_select_sampling(node_table(s), pv, attempts, seed, first_pod_index, reinterpret_cast<int32_t*>(base),
+                                  reinterpret_cast<uint32_t*>(base + off_att),
+                                  out_draw_node ? reinterpret_cast<int32_t*>(base + off_dn) : nullptr,
+                                  out_draw_code ? base + off_dc : nullptr, s->stream));
+    CU_TRY(cudaMemcpyAsync(out_node_idx, base, P * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (out_attempts) CU_TRY(cudaMemcpyAsync(out_attempts, base + off_att, P * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (out_draw_node) CU_TRY(cudaMemcpyAsync(out_draw_node, base + off_dn, draws * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (out_draw_code) CU_TRY(cudaMemcpyAsync(out_draw_code, base + off_dc, draws, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
     return KS_OK;
 }

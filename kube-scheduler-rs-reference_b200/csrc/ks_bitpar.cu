@@ -171,7 +171,15 @@ __global__ void __launch_bounds__(256)
 
 // label-pair columns: [bit][tile][32 B] with a 16-byte skew per bit, so that lanes working on the same tile with
 // different required pairs fall into different 16-byte bank groups
-__host__ __device__ __forceinline__ uint32_t pair_stride(uint32_t nt) { return nt * 32u + 16u; }
+// KS_BP_VARIANT=0 (A/B switch, read once): 16-byte skew per bit and both pods of a phase load the same half first
+static int bp_variant() {
+    static const int v = [] {
+        const char* e = getenv("KS_BP_VARIANT");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+static uint32_t pair_stride(uint32_t nt) { return bp_variant() ? nt * 32u : nt * 32u + 16u; }
 
 // Prefix tables are interleaved by QUADS of tiles: row r of tiles 4k..4k+3 forms one 128-byte line
 //   [tile 4k row r | tile 4k+1 row r | tile 4k+2 row r | tile 4k+3 row r]
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(288)
             for (int b = 0; b < 32; b++) acc |= (uint32_t)((s_lab[w_][j * 32 + b] >> sh) & 1ull) << b;
             w[j] = acc;
         }
-        uint4* dst = reinterpret_cast<uint4*>(pairs + (size_t)bit * pair_stride(lay.nt) + (size_t)t * 32);
+        uint4* dst = reinterpret_cast<uint4*>(pairs + (size_t)bit * lay.pstride + (size_t)t * 32);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
         dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(256)
 // row with one 256-bit store each.  A shared-memory phase of a 128-bit load (8 lanes) is 2 neighbouring pods x 4
 // tiles: the 4 tiles sit in distinct bank groups (tile tables are skewed by 32 bytes) and the 2 pods read the same
 // or an adjacent row (identical addresses merge; adjacent rows are conflict-free by the chunk swizzle).
-template <int W>
+template <int W, bool SWAP>
 __global__ void __launch_bounds__(BP_THREADS, 1)
     k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
                   const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s, OutView ov,
@@ -436,6 +444,11 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     const unsigned long long* s_membM = reinterpret_cast<const unsigned long long*>(smem + lay.off_membM);
     const uint8_t* s_pairs = smem + lay.off_pairs;
     const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
+    // SWAP: the odd pod of a phase reads the upper 16 bytes of every 32-byte row first, the even pod the lower 16:
+    // the 8 lanes of a phase then always hit 8 different 16-byte bank groups (tile x half), whatever rows and
+    // label-pair columns the two pods need.  h0/h1 = index of the half loaded first / second.
+    const uint32_t h0 = SWAP ? (psub & 1u) : 0u, h1 = h0 ^ 1u;
+    const uint32_t pstride = lay.pstride;
 
     for (uint32_t cb = blockIdx.x / ctas_per_cb; cb < lay.ncb; cb += gridDim.x / ctas_per_cb) {
         const uint32_t gb = n_groups;
@@ -494,8 +507,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                     const uint32_t rankM = bm + __popcll(mm & lowM);
                     const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + table_row_offset(ct, rankC));
                     const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + table_row_offset(ct, rankM));
-                    const uint4 c0 = tc[0], c1 = tc[1];
-                    const uint4 m0 = tm[0], m1 = tm[1];
+                    const uint4 c0 = tc[h0], c1 = tc[h1];
+                    const uint4 m0 = tm[h0], m1 = tm[h1];
                     uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
                     uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
 #pragma unroll
@@ -504,8 +517,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                         while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
                             const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
                             bits &= bits - 1;
-                            const uint4* col = reinterpret_cast<const uint4*>(s_pairs + bit * pair_stride(nt) + ct * 32);
-                            const uint4 q0 = col[0], q1 = col[1];
+                            const uint4* col = reinterpret_cast<const uint4*>(s_pairs + bit * pstride + ct * 32);
+                            const uint4 q0 = col[h0], q1 = col[h1];
                             a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
                             b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
                         }
@@ -516,9 +529,17 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                         const uint32_t word = (cb * nt + ct) * 8;
                         if (word < ov.mask_valid_words) {
                             uint32_t* dst = ov.mask + (size_t)cpid * ov.mask_row_words + word; // 32-byte aligned
-                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y),
-                                         "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                                         : "memory");
+                            if (SWAP) // a = half h0, b = half h1: two predicated stores, each lane runs one
+                                asm volatile("{ .reg .pred p; setp.ne.u32 p, %9, 0;\n\t"
+                                             "@p st.global.v8.b32 [%0], {%5,%6,%7,%8,%1,%2,%3,%4};\n\t"
+                                             "@!p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}; }" ::"l"(dst),
+                                             "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w),
+                                             "r"(h0)
+                                             : "memory");
+                            else
+                                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x),
+                                             "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                                             : "memory");
                         }
                     }
                 }
@@ -576,7 +597,7 @@ __device__ __forceinline__ void ptile_mask(const uint8_t* __restrict__ blobP, co
         while (bits) {
             const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
             bits &= bits - 1;
-            const uint4* col = reinterpret_cast<const uint4*>(pairs + (size_t)bit * pair_stride(lay.nt) + (size_t)k * 32);
+            const uint4* col = reinterpret_cast<const uint4*>(pairs + (size_t)bit * lay.pstride + (size_t)k * 32);
             const uint4 q0 = __ldg(col);
             const uint4 q1 = __ldg(col + 1);
             m[0] &= q0.x; m[1] &= q0.y; m[2] &= q0.z; m[3] &= q0.w;
@@ -690,7 +711,8 @@ static bool fill_offsets(BitparLayout* lay, uint32_t W) {
     lay->off_tabM = off;
     off += table_area_bytes((uint32_t)nt);
     lay->off_pairs = off;
-    off += 64u * W * pair_stride((uint32_t)nt);
+    lay->pstride = pair_stride((uint32_t)nt);
+    off += 64u * W * lay->pstride;
     lay->blob_bytes = (off + 127u) & ~127u;
     return true;
 }
@@ -809,7 +831,9 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
 
 template <int W>
 static cudaError_t set_smem_attr() {
-    return cudaFuncSetAttribute(k_mask_bitpar<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_mask_bitpar<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -934,7 +958,7 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
         const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
         {
-            auto kern = k_mask_bitpar<W>;
+            auto kern = bp_variant() ? k_mask_bitpar<W, true> : k_mask_bitpar<W, false>;
             kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov,
                                                                     ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
         }

@@ -25,6 +25,7 @@ struct BitparLayout { // byte offsets inside one column-block blob
     uint32_t nb;       // buckets of 64 global positions: (N >> 6) + 1
     uint32_t ncb;      // column blocks
     uint32_t off_baseC, off_membC, off_baseM, off_membM, off_tabC, off_tabM, off_pairs;
+    uint32_t pstride;  // bytes between two label-pair columns
     uint32_t blob_bytes;
 };
 

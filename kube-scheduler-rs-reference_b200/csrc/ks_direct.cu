@@ -96,6 +96,56 @@ cudaError_t launch_check_cells(const NodeTable& nt, const PodView& pv, uint8_t* 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ K1s
+// The reference's own selection policy (/root/reference/src/main.rs:49-71) with a seeded generator: up to
+// `attempts` uniform draws with replacement per pod, the first draw whose cell passes check_node_validity wins.
+// One thread per pod; the node rows it touches are random gathers served by L2 (the node table is a few MB).
+__device__ __forceinline__ uint64_t splitmix64_next(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_select_sampling(NodeTable nt, PodView pv, uint32_t attempts, uint64_t seed, uint64_t pod_offset,
+                                  int32_t* __restrict__ node_idx, uint32_t* __restrict__ n_attempts,
+                                  int32_t* __restrict__ draw_node, uint8_t* __restrict__ draw_code) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pv.P) return;
+    uint64_t state = KS_SAMPLING_STREAM(seed, pod_offset + p);
+    const int64_t rc = pv.req_cpu[p], rm = pv.req_mem[p];
+    const uint64_t* sel = pv.sel + (uint64_t)p * nt.W;
+    int32_t chosen = -1;
+    uint32_t a = 0;
+    for (; a < attempts; a++) {                                         // main.rs:53
+        const uint32_t n = (uint32_t)(splitmix64_next(state) % nt.N); // :56-57 choose()
+        const int code = cell_code(rc, rm, sel, nt.free_cpu[n], nt.free_mem[n], nt.labels, n, nt.Npad, nt.W); // :61
+        if (draw_node) draw_node[(uint64_t)p * attempts + a] = (int32_t)n;
+        if (draw_code) draw_code[(uint64_t)p * attempts + a] = (uint8_t)code; // the reason main.rs:62 logs
+        if (code == KS_CELL_OK) {                                     // :63-65
+            chosen = (int32_t)n;
+            a++;
+            break;
+        }
+    }
+    for (uint32_t r = a; r < attempts; r++) { // attempts never made
+        if (draw_node) draw_node[(uint64_t)p * attempts + r] = -1;
+        if (draw_code) draw_code[(uint64_t)p * attempts + r] = 0xff;
+    }
+    node_idx[p] = chosen;
+    if (n_attempts) n_attempts[p] = a;
+}
+
+cudaError_t launch_select_sampling(const NodeTable& nt, const PodView& pv, uint32_t attempts, uint64_t seed,
+                                   uint64_t pod_offset, int32_t* node_idx, uint32_t* n_attempts, int32_t* draw_node,
+                                   uint8_t* draw_code, cudaStream_t st) {
+    if (pv.P == 0) return cudaSuccess;
+    k_select_sampling<<<(pv.P + 255) / 256, 256, 0, st>>>(nt, pv, attempts, seed, pod_offset, node_idx, n_attempts,
+                                                          draw_node, draw_code);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ K2 direct
 template <int W>
 struct PodsPerWarp {

@@ -29,6 +29,7 @@ for _name, _res, _args in [
     ("ksh_pack_pods", C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, _vp, C.c_uint32]),
     ("ksh_check_node_validity", C.c_int, [_vp, _vp, C.c_uint32]),
     ("ksh_select_nodes", C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp]),
+    ("ksh_select_node_for_pod", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     ("ksh_reconcile", C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
 ]:
     _f = getattr(lib, _name)
@@ -159,6 +160,18 @@ class Context:
         if rc != capi.KS_OK:
             raise KsError(rc, "ksh_select_nodes")
         return idx, score, cnt
+
+    def select_node_for_pod(self, pods, n, attempts=capi.KS_REFERENCE_ATTEMPTS, seed=0, first=0):
+        """select_node_for_pod with the reference's own seeded <=attempts-draw policy (src/main.rs:49-71)."""
+        idx = np.empty(n, np.int32)
+        used = np.empty(n, np.uint32)
+        dn = np.empty((n, attempts), np.int32)
+        dc = np.empty((n, attempts), np.uint8)
+        rc = lib.ksh_select_node_for_pod(self._h, _addr(pods, first), n, int(attempts), int(seed), int(first),
+                                         idx.ctypes.data, used.ctypes.data, dn.ctypes.data, dc.ctypes.data)
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_select_node_for_pod")
+        return idx, used, dn, dc
 
     def reconcile(self, pods, i, policy=capi.KS_SCORE_LEFTOVER):
         node = C.c_int32(-1)

@@ -112,7 +112,7 @@ class Snapshot:
     def _pods(self, req_cpu, req_mem, sel):
         req_cpu = _c(req_cpu, np.int64)
         req_mem = _c(req_mem, np.int64)
-        sel = _c(sel, np.uint64).reshape(req_cpu.shape[0], -1)
+        sel = _c(sel, np.uint64).reshape(req_cpu.shape[0], -1 if req_cpu.shape[0] else self.label_words)
         if sel.shape[1] != self.label_words:
             raise ValueError(f"sel has {sel.shape[1]} words per pod, snapshot has {self.label_words}")
         pods = ks_pods(req_cpu.shape[0], _ptr(req_cpu), _ptr(req_mem), _ptr(sel), capi.KS_MEM_HOST)
@@ -178,6 +178,20 @@ class Snapshot:
         if rc != capi.KS_OK:
             raise KsError(rc, "ks_stream_bind")
         return idx, score, rounds.value
+
+    def select_sampling(self, req_cpu, req_mem, sel, attempts=capi.KS_REFERENCE_ATTEMPTS, seed=0, first_pod_index=0):
+        """The reference's own policy (src/main.rs:49-71), seeded: (node_idx, attempts_used, draw_node, draw_code)."""
+        pods, keep = self._pods(req_cpu, req_mem, sel)
+        p = int(pods.n)
+        idx = np.empty(p, np.int32)
+        used = np.empty(p, np.uint32)
+        dn = np.empty((p, attempts), np.int32)
+        dc = np.empty((p, attempts), np.uint8)
+        rc = lib.ks_select_sampling(self._h, C.byref(pods), int(attempts), int(seed), int(first_pod_index), _ptr(idx),
+                                    _ptr(used), _ptr(dn), _ptr(dc))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_select_sampling")
+        return idx, used, dn, dc
 
     def last_timings(self):
         ms = (C.c_float * 3)()

@@ -570,6 +570,38 @@ int32_t orc_select_sampling(const orc_cluster* c, const ks_pod_obj* pod, uint32_
     return node;
 }
 
+/* Same policy on the packed form, one generator state per pod (rng_state[p] is advanced in place). */
+int orc_select_sampling_packed(uint32_t n_nodes, uint32_t W, const int64_t* free_cpu, const int64_t* free_mem,
+                               const uint64_t* node_labels, uint64_t n_pods, const int64_t* req_cpu,
+                               const int64_t* req_mem, const uint64_t* pod_sel, uint32_t attempts, uint64_t* rng_state,
+                               int32_t* out_node_idx, uint32_t* out_cells, int32_t* out_draw_node,
+                               uint8_t* out_draw_code) {
+    for (uint64_t p = 0; p < n_pods; p++) {
+        const uint64_t* sel = pod_sel + p * W;
+        int32_t node = -1;
+        uint32_t cells = 0;
+        for (uint32_t a = 0; a < attempts; a++) {
+            if (out_draw_node) out_draw_node[p * attempts + a] = -1;
+            if (out_draw_code) out_draw_code[p * attempts + a] = 0xff;
+        }
+        for (uint32_t a = 0; a < attempts && node < 0; a++) { /* main.rs:53 */
+            if (n_nodes == 0) continue;                         /* :56 */
+            uint32_t n = (uint32_t)(splitmix64(&rng_state[p]) % n_nodes);
+            int fit = req_cpu[p] <= free_cpu[n] && req_mem[p] <= free_mem[n]; /* predicates.rs:42 */
+            uint64_t miss = 0;
+            for (uint32_t w = 0; w < W; w++) miss |= sel[w] & ~node_labels[(uint64_t)n * W + w];
+            int code = !fit ? ORC_CELL_NOT_ENOUGH_RESOURCES : (miss ? ORC_CELL_NODE_SELECTOR_MISMATCH : ORC_CELL_OK);
+            if (out_draw_node) out_draw_node[p * attempts + cells] = (int32_t)n;
+            if (out_draw_code) out_draw_code[p * attempts + cells] = (uint8_t)code;
+            cells++;
+            if (code == ORC_CELL_OK) node = (int32_t)n; /* main.rs:63-65 */
+        }
+        out_node_idx[p] = node;
+        if (out_cells) out_cells[p] = cells;
+    }
+    return ORC_OK;
+}
+
 /* ---- streaming restated (see oracle.h) ---- */
 int orc_commit_claims(uint32_t n_nodes, int64_t* free_cpu, int64_t* free_mem, uint64_t n_claims,
                       const int32_t* claim_node, const int64_t* req_cpu, const int64_t* req_mem, uint8_t* accepted) {

@@ -104,6 +104,12 @@ int orc_run_packed(uint32_t n_nodes, uint32_t label_words, const int64_t* free_c
 int32_t orc_select_sampling(const orc_cluster*, const ks_pod_obj* pod, uint32_t attempts, uint64_t* rng_state,
                             uint32_t* cells_evaluated);
 
+int orc_select_sampling_packed(uint32_t n_nodes, uint32_t label_words, const int64_t* free_cpu, const int64_t* free_mem,
+                               const uint64_t* node_labels, uint64_t n_pods, const int64_t* req_cpu,
+                               const int64_t* req_mem, const uint64_t* pod_sel, uint32_t attempts,
+                               uint64_t* rng_state /* [n_pods], advanced in place */, int32_t* out_node_idx,
+                               uint32_t* out_cells, int32_t* out_draw_node, uint8_t* out_draw_code);
+
 /* Streaming (config C5) restated: what the reference gets from re-LISTing per cell (src/predicates.rs:34-38).
  * orc_commit_claims: claims in arrival (array) order; claim i is accepted iff its request still fits the
  * node's remaining free (predicates.rs:42), then free -= request (util.rs:31-36).  claim_node < 0 = no claim.

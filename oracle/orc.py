@@ -56,6 +56,9 @@ lib.orc_run_packed.argtypes = [C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, 
                                _vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_int]
 lib.orc_select_sampling.restype = C.c_int32
 lib.orc_select_sampling.argtypes = [_vp, _vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+lib.orc_select_sampling_packed.restype = C.c_int
+lib.orc_select_sampling_packed.argtypes = [C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, C.c_uint32, _vp, _vp,
+                                           _vp, _vp, _vp]
 lib.orc_online_cores.restype = C.c_int
 lib.orc_commit_claims.restype = C.c_int
 lib.orc_commit_claims.argtypes = [C.c_uint32, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp]
@@ -164,6 +167,26 @@ def run_packed(free_cpu, free_mem, alloc_cpu, alloc_mem, labels, req_cpu, req_me
     if rc:
         raise RuntimeError(f"orc_run_packed -> {rc}")
     return idx, score, cnt, mask, codes
+
+
+def sampling_packed(free_cpu, free_mem, labels, req_cpu, req_mem, sel, attempts, states):
+    """Reference policy on the packed form; states = uint64[P] generator start states (not modified)."""
+    N = free_cpu.shape[0]
+    P = req_cpu.shape[0]
+    labels = np.ascontiguousarray(labels, np.uint64).reshape(N, -1) if N else np.zeros((0, 1), np.uint64)
+    W = labels.shape[1]
+    sel = np.ascontiguousarray(sel, np.uint64).reshape(P, W)
+    a = [np.ascontiguousarray(x, np.int64) for x in (free_cpu, free_mem, req_cpu, req_mem)]
+    st = np.array(states, np.uint64, copy=True)
+    idx = np.empty(P, np.int32)
+    cells = np.empty(P, np.uint32)
+    dn = np.empty((P, attempts), np.int32)
+    dc = np.empty((P, attempts), np.uint8)
+    rc = lib.orc_select_sampling_packed(N, W, _p(a[0]), _p(a[1]), _p(labels), P, _p(a[2]), _p(a[3]), _p(sel), attempts,
+                                        _p(st), _p(idx), _p(cells), _p(dn), _p(dc))
+    if rc:
+        raise RuntimeError(f"orc_select_sampling_packed -> {rc}")
+    return idx, cells, dn, dc
 
 
 def commit_claims(free_cpu, free_mem, claim_node, req_cpu, req_mem):

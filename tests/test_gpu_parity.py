@@ -399,3 +399,73 @@ def test_adversarial_values(ks, orc, path, seed, P, N, W):
             r1 = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, want_mask=False)
             o1 = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=1, want_mask=False)
             assert np.array_equal(r1.node_idx, o1[0]) and np.array_equal(r1.score, o1[1])
+
+
+def _stream_states(ks, seed, P, first=0):
+    return np.array([ks.capi.sampling_stream(seed, first + p) for p in range(P)], np.uint64)
+
+
+@pytest.mark.parametrize("P,N,keys,attempts", [(500, 40, 8, 5), (4000, 3000, 8, 5), (3000, 777, 32, 3), (1000, 5, 8, 16)])
+def test_reference_sampling_policy_bit_exact(ks, orc, P, N, keys, attempts):
+    """(f)#4: the reference's own <=ATTEMPTS random draws (src/main.rs:49-71), seeded: every draw, every reason
+    code and the outcome equal the oracle's restatement driven by the same generator states."""
+    cl = ks.synth.make(P, N, seed=4242 + N, n_keys=keys, bound_per_node=6)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    seed = 0xB2000005 ^ N
+    o = orc.sampling_packed(fc, fm, lab, rc, rm, sel, attempts, _stream_states(ks, seed, P))
+    _, _, ocnt, omask, ocodes = orc.run_packed(fc, fm, ac, am, lab, rc, rm, sel, want_codes=True)
+    snap, _ = _snapshot(ks, cl)
+    with snap:
+        idx, used, dn, dc = snap.select_sampling(rc, rm, sel, attempts=attempts, seed=seed)
+        # a chunked caller reproduces the single call through first_pod_index
+        half = P // 2
+        idx2, used2, _, _ = snap.select_sampling(rc[half:], rm[half:], sel[half:], attempts=attempts, seed=seed,
+                                                 first_pod_index=half)
+    for got, want, name in zip((idx, used, dn, dc), o, ("node_idx", "attempts", "draw_node", "draw_code")):
+        assert np.array_equal(got, want), name
+    assert np.array_equal(idx2, idx[half:]) and np.array_equal(used2, used[half:])
+    # the policy's contract against the exhaustive answer: a pick is feasible; no feasible node -> None;
+    # None is allowed although feasible nodes exist (the reference gives up after its draws)
+    bits = mask_bits(omask, N)
+    picked = idx >= 0
+    assert bits[np.nonzero(picked)[0], idx[picked]].all()
+    assert (idx[ocnt == 0] == -1).all()
+    made = dn >= 0
+    pp = np.broadcast_to(np.arange(P)[:, None], dn.shape)
+    assert np.array_equal(dc[made], ocodes[pp[made], dn[made]])
+    assert picked.any() and ((~picked) & (ocnt > 0)).any() or N <= 5
+
+
+def test_reference_sampling_policy_faithful_objects(ks, orc):
+    """Same policy on the object path: host layer (strings -> packer -> device) vs the faithful oracle pod by pod."""
+    from test_host_layer import _cluster_objects
+    cl = ks.synth.make(60, 90, seed=99, bound_per_node=3)
+    arena, nodes, bound, pods = _cluster_objects(ks, cl)
+    oc = orc.Cluster(nodes, cl.N, bound, cl.B)
+    seed = 777
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(nodes, cl.N)
+        ctx.set_cluster_pods(bound, cl.B)
+        idx, used, dn, dc = ctx.select_node_for_pod(pods, cl.P, seed=seed)
+    for p in range(cl.P):
+        n, cells = oc.sampling(pods, p, 5, seed=ks.capi.sampling_stream(seed, p))
+        assert (idx[p], used[p]) == (n, cells), p
+
+
+def test_reference_sampling_policy_edge_cases(ks):
+    one = np.zeros((1, 1), np.uint64)
+    with ks.Snapshot(0) as snap:
+        # empty node store: every attempt is wasted (src/main.rs:56,60)
+        idx, used, dn, dc = snap.select_sampling(np.array([1], np.int64), np.array([1], np.int64), one, seed=3)
+        assert idx[0] == -1 and used[0] == 0 and (dn == -1).all() and (dc == 0xff).all()
+        snap.set_nodes(np.array([1000], np.int64), np.array([1 << 30], np.int64), one)
+        idx, used, dn, dc = snap.select_sampling(np.array([1000, 1001], np.int64), np.array([1, 1], np.int64),
+                                                 np.zeros((2, 1), np.uint64), seed=3)
+        assert idx.tolist() == [0, -1] and used.tolist() == [1, 5]
+        assert dc[0].tolist() == [0, 255, 255, 255, 255] and dc[1].tolist() == [1] * 5
+        idx, used, _, _ = snap.select_sampling(np.array([1], np.int64), np.array([1], np.int64), one, attempts=0)
+        assert idx[0] == -1 and used[0] == 0
+        e = np.zeros(0, np.int64)
+        idx, _, _, _ = snap.select_sampling(e, e, np.zeros((0, 1), np.uint64))
+        assert idx.shape == (0,)

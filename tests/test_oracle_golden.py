@@ -152,3 +152,23 @@ def test_sampling_policy_picks_from_feasible_set(ks, orc):
         if cnt[p] == 0:
             assert n == -1
     assert hits > 0
+
+
+def test_sampling_policy_packed_equals_faithful(ks, orc):
+    """The packed restatement of the reference policy draws, checks and stops exactly like the object-model one."""
+    cl = ks.synth.make(80, 60, 11, bound_per_node=4)
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    nodes, bound, pods = arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+    oc = orc.Cluster(nodes, cl.N, bound, cl.B)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    states = np.array([ks.capi.sampling_stream(5, p) for p in range(cl.P)], np.uint64)
+    idx, cells, dn, dc = orc.sampling_packed(fc, fm, lab, rc, rm, sel, 5, states)
+    for p in range(cl.P):
+        n, c = oc.sampling(pods, p, 5, seed=int(states[p]))
+        assert (idx[p], cells[p]) == (n, c)
+        assert (dn[p, c:] == -1).all() and (dc[p, c:] == 0xff).all()
+        if n >= 0:
+            assert dn[p, c - 1] == n and dc[p, c - 1] == 0
+    assert (idx >= 0).any() and (idx < 0).any()

@@ -169,8 +169,7 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// label-pair columns: [bit][tile][32 B] with a 16-byte skew per bit, so that lanes working on the same tile with
-// different required pairs fall into different 16-byte bank groups
+// label-pair columns: [bit][tile][32 B]
 // KS_BP_VARIANT=0 (A/B switch, read once): 16-byte skew per bit and both pods of a phase load the same half first
 static int bp_variant() {
     static const int v = [] {
@@ -272,7 +271,7 @@ __global__ void __launch_bounds__(288)
             running += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
-    // label-pair columns, layout [bit][tile][8 words] (+16-byte skew per bit)
+    // label-pair columns, layout [bit][tile][8 words]
     uint8_t* pairs = B + lay.off_pairs;
     for (uint32_t bit = s; bit < 64u * nt.W; bit += blockDim.x) {
         const uint32_t w_ = bit >> 6, sh = bit & 63;
@@ -412,8 +411,9 @@ __global__ void __launch_bounds__(256)
 // Mask kernel.  Pods arrive bucket-sorted by threshold (k_pod_scatter).  One warp = 8 consecutive sorted pods x
 // 4 tiles, tile index fastest: lanes 4j..4j+3 are one pod's 4 tiles and write 128 contiguous bytes of its mask
 // row with one 256-bit store each.  A shared-memory phase of a 128-bit load (8 lanes) is 2 neighbouring pods x 4
-// tiles: the 4 tiles sit in distinct bank groups (tile tables are skewed by 32 bytes) and the 2 pods read the same
-// or an adjacent row (identical addresses merge; adjacent rows are conflict-free by the chunk swizzle).
+// tiles: the 4 tiles sit in distinct bank groups (quad-interleaved tables) and, with SWAP, the two pods read
+// opposite 16-byte halves of their 32-byte rows, so the 8 lanes always touch 8 different 16-byte bank groups -
+// every row / column load is one wavefront per phase whatever rows the two pods need.
 template <int W, bool SWAP>
 __global__ void __launch_bounds__(BP_THREADS, 1)
     k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,

@@ -266,6 +266,8 @@ int ks_snapshot_set_bound(ks_snapshot* s, uint64_t n_bound, const int32_t* node_
 int ks_snapshot_apply_bind(ks_snapshot* s, int32_t node_idx, int64_t req_cpu, int64_t req_mem) {
     if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
     if (node_idx < 0 || (uint32_t)node_idx >= s->N) return fail(KS_ERR_INVALID, "node index %d out of range", node_idx);
+    if (req_cpu > KS_MAX_CPU_MILLI || req_cpu < -KS_MAX_CPU_MILLI || req_mem > KS_MAX_MEM_BYTES || req_mem < -KS_MAX_MEM_BYTES)
+        return fail(KS_ERR_RANGE, "request out of range");
     std::lock_guard<std::mutex> lk(s->mu);
     CU_TRY(cudaSetDevice(s->device));
     s->derived_dirty = true;
@@ -683,6 +685,7 @@ int ks_select_sampling(ks_snapshot* s, const ks_pods* pods, uint32_t attempts, u
     if (attempts > 64) return fail(KS_ERR_RANGE, "attempts must be <= 64 (the reference uses %u)", KS_REFERENCE_ATTEMPTS);
     if (P == 0) return KS_OK;
     const uint64_t draws = P * (uint64_t)attempts;
+    std::lock_guard<std::mutex> lk(s->mu);
     if (s->N == 0 || attempts == 0) { // choose() on an empty store is None for every attempt (main.rs:56,60)
         for (uint64_t i = 0; i < P; i++) out_node_idx[i] = -1;
         if (out_attempts) memset(out_attempts, 0, P * 4);
@@ -690,7 +693,6 @@ int ks_select_sampling(ks_snapshot* s, const ks_pods* pods, uint32_t attempts, u
         if (out_draw_code) memset(out_draw_code, 0xff, draws);
         return KS_OK;
     }
-    std::lock_guard<std::mutex> lk(s->mu);
     CU_TRY(cudaSetDevice(s->device));
     PodView pv;
     rc = stage_pods(s, pods, s->stream, &pv);

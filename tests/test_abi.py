@@ -46,3 +46,22 @@ def test_no_gpu_means_loud_failure_not_fallback(ks):
     assert b"no CPU fallback" in ks.lib.ks_last_error()
     with pytest.raises(ks.KsError):
         ks.Snapshot(0)
+
+
+def test_headers_are_plain_c_and_the_c_example_links(ks, tmp_path):
+    """include/*.h must be consumable by a C (not C++) host: the example controller loop compiles as strict C99,
+    links against libksched.so alone and, without a GPU, fails loudly instead of computing on the CPU."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "reconcile_loop")
+    libdir = os.path.dirname(ks.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "examples", "reconcile_loop.c"), "-L" + libdir, "-lksched", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if ks.device_count() > 0:
+        assert r.returncode == 0, r.stderr
+        assert "p9: already bound, skipped" in r.stdout
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr

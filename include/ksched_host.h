@@ -45,6 +45,10 @@ int ksh_total_pod_resources(const ks_pod_obj* pod, int64_t* cpu_millicores, int6
 int ksh_is_pod_bound(const ks_pod_obj* pod);
 
 typedef struct ksh_context ksh_context;
+/* device = CUDA ordinal, or KSH_DEVICE_NONE for a packing-only context: objects -> SoA/bitmask arrays
+ * (ksh_context_set_* / upsert / pod events, ksh_pack_pods, ksh_context_export_packed) work on the host; every call
+ * that evaluates a predicate or selects a node returns KS_ERR_NO_DEVICE — nothing is ever computed on the CPU. */
+#define KSH_DEVICE_NONE (-1)
 int ksh_context_create(int device, ksh_context** out);
 void ksh_context_destroy(ksh_context* ctx);
 /* node store contents (what reflector::Store<Node>::state() returns, src/main.rs:56) */
@@ -67,6 +71,13 @@ int ksh_context_pod_deleted(ksh_context* ctx, const ks_pod_obj* pod);
 const char* ksh_context_node_name(const ksh_context* ctx, uint32_t node_idx); /* NULL if out of range */
 uint32_t ksh_context_num_nodes(const ksh_context* ctx);
 uint32_t ksh_context_label_words(const ksh_context* ctx);
+uint64_t ksh_context_num_bound(const ksh_context* ctx);
+/* The packed node side exactly as the next device upload sends it (arguments of ks_snapshot_set_nodes /
+ * ks_snapshot_set_bound in ksched.h): allocatable [N] in millicores / bytes, label words [N * label_words] under the
+ * current dictionary, bound-pod triples [num_bound].  Lets a host feed the packed core itself, and the CPU tests
+ * check the packer against the oracle without a GPU. */
+int ksh_context_export_packed(const ksh_context* ctx, int64_t* alloc_cpu, int64_t* alloc_mem, uint64_t* labels,
+                              int32_t* bound_node, int64_t* bound_cpu, int64_t* bound_mem);
 ks_snapshot* ksh_context_snapshot(ksh_context* ctx); /* borrowed; valid until the next ksh_context_* mutation */
 
 /* Pack P pod objects into caller buffers (req_cpu[P], req_mem[P], sel[P*W]) with the context's current label

@@ -218,14 +218,21 @@ static uint32_t words_for_bits(uint32_t real_bits) {
     return w;
 }
 
-static int upload(ksh_context* c) {
-    if (!c->dirty) return KS_OK;
-    std::vector<uint64_t> lab((size_t)c->N * c->W, 0);
+// node label words [N*W] under the current dictionary
+static void fill_label_words(const ksh_context* c, uint64_t* lab) {
+    std::memset(lab, 0, (size_t)c->N * c->W * sizeof(uint64_t));
     for (uint32_t n = 0; n < c->N; n++)
         for (const std::string& pk : c->node_pairs[n]) {
             auto it = c->dict.find(pk);
             if (it != c->dict.end()) lab[(size_t)n * c->W + (it->second >> 6)] |= 1ull << (it->second & 63);
         }
+}
+
+static int upload(ksh_context* c) {
+    if (!c->snap) return fail(KS_ERR_NO_DEVICE, "packing-only context (KSH_DEVICE_NONE): no device snapshot, nothing is computed on the host");
+    if (!c->dirty) return KS_OK;
+    std::vector<uint64_t> lab((size_t)c->N * c->W, 0);
+    fill_label_words(c, lab.data());
     int rc = ks_snapshot_set_nodes(c->snap, c->N, c->W, c->alloc_cpu.data(), c->alloc_mem.data(), lab.data());
     if (rc) return rc;
     rc = ks_snapshot_set_bound(c->snap, c->bnode.size(), c->bnode.data(), c->bcpu.data(), c->bmem.data());
@@ -309,10 +316,12 @@ int ksh_context_create(int device, ksh_context** out) {
     *out = nullptr;
     ksh_context* c = new (std::nothrow) ksh_context();
     if (!c) return fail(KS_ERR_NOMEM, "out of host memory");
-    int rc = ks_snapshot_create(device, &c->snap);
-    if (rc) {
-        delete c;
-        return rc;
+    if (device != KSH_DEVICE_NONE) { // KSH_DEVICE_NONE: packer only, every call that needs the device fails
+        int rc = ks_snapshot_create(device, &c->snap);
+        if (rc) {
+            delete c;
+            return rc;
+        }
     }
     *out = c;
     return KS_OK;
@@ -326,6 +335,26 @@ void ksh_context_destroy(ksh_context* c) {
 
 uint32_t ksh_context_num_nodes(const ksh_context* c) { return c ? c->N : 0; }
 uint32_t ksh_context_label_words(const ksh_context* c) { return c ? c->W : 0; }
+uint64_t ksh_context_num_bound(const ksh_context* c) { return c ? c->bnode.size() : 0; }
+
+int ksh_context_export_packed(const ksh_context* c, int64_t* alloc_cpu, int64_t* alloc_mem, uint64_t* labels,
+                              int32_t* bound_node, int64_t* bound_cpu, int64_t* bound_mem) {
+    if (!c) return fail(KS_ERR_INVALID, "NULL argument");
+    if (c->N && (!alloc_cpu || !alloc_mem || !labels)) return fail(KS_ERR_INVALID, "NULL node array");
+    if (!c->bnode.empty() && (!bound_node || !bound_cpu || !bound_mem)) return fail(KS_ERR_INVALID, "NULL bound array");
+    if (c->N) {
+        std::memcpy(alloc_cpu, c->alloc_cpu.data(), (size_t)c->N * 8);
+        std::memcpy(alloc_mem, c->alloc_mem.data(), (size_t)c->N * 8);
+        fill_label_words(c, labels);
+    }
+    if (!c->bnode.empty()) {
+        std::memcpy(bound_node, c->bnode.data(), c->bnode.size() * 4);
+        std::memcpy(bound_cpu, c->bcpu.data(), c->bcpu.size() * 8);
+        std::memcpy(bound_mem, c->bmem.data(), c->bmem.size() * 8);
+    }
+    return KS_OK;
+}
+
 ks_snapshot* ksh_context_snapshot(ksh_context* c) {
     if (!c || upload(c)) return nullptr;
     return c->snap;

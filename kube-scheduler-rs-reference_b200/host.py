@@ -25,6 +25,8 @@ for _name, _res, _args in [
     ("ksh_context_node_name", C.c_char_p, [_vp, C.c_uint32]),
     ("ksh_context_num_nodes", C.c_uint32, [_vp]),
     ("ksh_context_label_words", C.c_uint32, [_vp]),
+    ("ksh_context_num_bound", C.c_uint64, [_vp]),
+    ("ksh_context_export_packed", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("ksh_context_snapshot", _vp, [_vp]),
     ("ksh_pack_pods", C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, _vp, C.c_uint32]),
     ("ksh_check_node_validity", C.c_int, [_vp, _vp, C.c_uint32]),
@@ -36,6 +38,7 @@ for _name, _res, _args in [
     _f.restype = _res
     _f.argtypes = _args
 
+KSH_DEVICE_NONE = -1  # packing-only context: objects -> SoA arrays on the host, no predicate is ever evaluated
 KSH_RECONCILE_OK, KSH_RECONCILE_NO_NODE_FOUND, KSH_RECONCILE_BINDING_OBJECT_FAILED = 0, 1, 2
 
 
@@ -144,6 +147,18 @@ class Context:
         if w < 0:
             raise KsError(w, "ksh_pack_pods")
         return rc_, rm_, np.ascontiguousarray(sel[:, :w])
+
+    def export_packed(self):
+        """(alloc_cpu, alloc_mem, labels[N,W], bound_node, bound_cpu, bound_mem): what the next device upload sends."""
+        n, w, b = self.n_nodes, self.label_words, int(lib.ksh_context_num_bound(self._h))
+        ac, am = np.empty(n, np.int64), np.empty(n, np.int64)
+        lab = np.zeros((n, w), np.uint64)
+        bn, bc, bm = np.empty(b, np.int32), np.empty(b, np.int64), np.empty(b, np.int64)
+        rc = lib.ksh_context_export_packed(self._h, ac.ctypes.data, am.ctypes.data, lab.ctypes.data, bn.ctypes.data,
+                                           bc.ctypes.data, bm.ctypes.data)
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_context_export_packed")
+        return ac, am, lab, bn, bc, bm
 
     def check_node_validity(self, pods, i, node_idx):
         rc = lib.ksh_check_node_validity(self._h, _addr(pods, i), int(node_idx))

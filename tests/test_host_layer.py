@@ -63,6 +63,120 @@ def test_malformed_objects_are_status_codes(ks):
     assert b"memory quantity" in ks.lib.ks_last_error()
 
 
+# ------------------------------------------------------------------------------------------------ packer, CPU
+# A packing-only context (KSH_DEVICE_NONE) turns objects into the SoA / bitmask arrays the device consumes and never
+# evaluates a predicate.  The CPU suite checks those arrays by giving them to the oracle's packed flavour and
+# comparing with the oracle's object-model (faithful) flavour on the same objects.
+def _packed_answer(orc, ctx, pods, P, policy=0):
+    rc, rm, sel = ctx.pack_pods(pods, P)           # grows the label dictionary first
+    ac, am, lab, bn, bc, bm = ctx.export_packed()   # ... so the node label words use the final dictionary
+    assert lab.shape[1] == sel.shape[1] == ctx.label_words
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    return orc.run_packed(fc, fm, ac, am, lab, rc, rm, sel, policy=policy, want_codes=True)
+
+
+def _objects(ks, cl):
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    return arena, arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+
+
+@pytest.mark.parametrize("P,N,keys,policy", [(64, 200, 8, 0), (300, 1500, 8, 0), (40, 300, 32, 1), (1, 1, 8, 0)])
+def test_packer_output_equals_faithful_oracle(ks, orc, P, N, keys, policy):
+    cl = ks.synth.make(P, N, seed=900 + P, n_keys=keys, bound_per_node=3)
+    arena, nodes, bound, pods = _objects(ks, cl)
+    oc = orc.Cluster(nodes, cl.N, bound, cl.B)
+    want = oc.run(pods, P, policy=policy, want_codes=True)
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(nodes, cl.N)
+        ctx.set_cluster_pods(bound, cl.B)
+        got = _packed_answer(orc, ctx, pods, P, policy)
+        assert ctx.label_words <= max(1, cl.label_words)  # only pairs that selectors name get a bit
+        ac, am, _, bn, bc, bm = ctx.export_packed()
+    for g, w, name in zip(got, want, ("node_idx", "score", "feasible_cnt", "mask", "codes")):
+        assert np.array_equal(g, w), name
+    # and the numeric columns are the generator's own packed form
+    gac, gam, _, gbn, gbc, gbm, _, _, _ = cl.packed()
+    assert np.array_equal(ac, gac) and np.array_equal(am, gam)
+    assert np.array_equal(bn, gbn) and np.array_equal(bc, gbc) and np.array_equal(bm, gbm)
+
+
+def test_packer_gv1_and_reference_selector_tests(ks, orc):
+    g = load_golden("gv1.json")
+    arena = ks.objects.ObjectArena()
+    nodes, bound, pods = arena.nodes(g["nodes"]), arena.pods(g["bound_pods"]), arena.pods(g["pods"])
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(nodes, len(g["nodes"]))
+        ctx.set_cluster_pods(bound, len(g["bound_pods"]))
+        rc, rm, _ = ctx.pack_pods(pods, len(g["pods"]))
+        assert rc.tolist() == g["expected_req_cpu_milli"] and rm.tolist() == g["expected_req_mem_bytes"]
+        _, _, _, mask, _ = _packed_answer(orc, ctx, pods, len(g["pods"]))
+        ac, am, _, bn, bc, bm = ctx.export_packed()
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    assert fc.tolist() == g["expected_free_cpu_milli"] and fm.tolist() == g["expected_free_mem_bytes"]
+    from helpers import rows_to_str
+    assert rows_to_str(mask_bits(mask, len(g["nodes"]))) == g["expected_feasible_rows"]
+    # the reference's own three nodeSelector tests (src/predicates/test.rs:42-58) through the packer
+    k = load_golden("selector_kats.json")
+    for case in k["cases"]:
+        n_, p_ = arena.nodes([case["node"]]), arena.pods([case["pod"]])
+        with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+            ctx.set_nodes(n_, 1)
+            _, _, sel = ctx.pack_pods(p_, 1)
+            lab = ctx.export_packed()[2]
+        match = not np.any(sel[0] & ~lab[0])
+        assert match == case["expect"], case["id"]
+
+
+def test_packer_incremental_events_equal_a_rebuild(ks, orc):
+    cl = ks.synth.make(120, 40, seed=11, bound_per_node=2)
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    pods = arena.pods(pods_s)
+    first_bound_s = [b for b in bound_s if int(b["node_name"].split("-")[1]) < 30]
+    rest_bound_s = [b for b in bound_s if int(b["node_name"].split("-")[1]) >= 30]
+    changed = dict(nodes_s[5])
+    changed["allocatable"] = {"cpu": "128", "memory": str(1 << 40)}
+    gone = [b for b in first_bound_s if b["node_name"] == "node-3"][:2]
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(arena.nodes(nodes_s[:30]), 30)
+        ctx.set_cluster_pods(arena.pods(first_bound_s), len(first_bound_s))
+        ctx.pack_pods(pods, cl.P)  # dictionary exists before the events: it must survive them
+        rest_nodes = arena.nodes(nodes_s[30:])
+        for i in range(10):
+            assert ctx.upsert_node(rest_nodes, i) == 30 + i
+        rest_bound = arena.pods(rest_bound_s)
+        for i in range(len(rest_bound_s)):
+            ctx.pod_bound(rest_bound, i)
+        assert ctx.upsert_node(arena.nodes([changed])) == 5
+        ctx.remove_node("node-7")
+        gone_objs = arena.pods(gone)
+        for i in range(len(gone)):
+            ctx.pod_deleted(gone_objs, i)
+        ctx.pod_deleted(arena.pods([{"name": "never-seen", "ns": "x", "node_name": "node-1"}]))  # ignored
+        assert ctx.n_nodes == 39 and ctx.node_name(7) == "node-8" and ctx.node_name(39) is None
+        got = _packed_answer(orc, ctx, pods, cl.P)
+    final_nodes_s = [changed if n["name"] == "node-5" else n for n in nodes_s if n["name"] != "node-7"]
+    gone_names = {g_["name"] for g_ in gone}
+    final_bound_s = [b for b in bound_s if b["node_name"] != "node-7" and b["name"] not in gone_names]
+    oc = orc.Cluster(arena.nodes(final_nodes_s), len(final_nodes_s), arena.pods(final_bound_s), len(final_bound_s))
+    want = oc.run(pods, cl.P, want_codes=True)
+    for g_, w, name in zip(got, want, ("node_idx", "score", "feasible_cnt", "mask", "codes")):
+        assert np.array_equal(g_, w), name
+
+
+def test_packing_only_context_never_computes(ks):
+    cl = ks.synth.make(4, 6, seed=1)
+    arena, nodes, bound, pods = _objects(ks, cl)
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(nodes, cl.N)
+        for call in (lambda: ctx.check_node_validity(pods, 0, 0), lambda: ctx.select_nodes(pods, 4),
+                     lambda: ctx.select_node_for_pod(pods, 4), lambda: ctx.reconcile(pods, 0)):
+            with pytest.raises(ks.KsError) as e:
+                call()
+            assert e.value.code == -8  # KS_ERR_NO_DEVICE
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _cluster_objects(ks, cl):
     nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)

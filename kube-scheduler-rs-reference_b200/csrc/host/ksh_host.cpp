@@ -1,12 +1,16 @@
 // ksh_host.cpp — host layer over Pod/Node objects (include/ksched_host.h): quantity parsing, packing into
 // SoA int64 + label bit columns, and the mirror of check_node_validity / select_node_for_pod / reconcile.
 // It only packs and dispatches: every predicate is evaluated by the CUDA core (ks_* in ksched.h).
+// Built for cluster scale: strings are interned once (no per-lookup allocation), label pairs and node names are
+// integers afterwards, node/pod events cost O(labels of the object), and the bulk calls (LIST results, pod
+// batches) are parsed by all host threads with results identical to the single-thread order.
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
-#include <unordered_map>
-#include <unordered_set>
+#include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "../../../include/ksched_host.h"
@@ -32,6 +36,14 @@ int parse_quantity(const char* s, int unit_shift, int64_t* out) {
     u128 mant = 0;
     int int_digits = 0, frac_digits = 0;
     const u128 cap = (u128)1 << 96;
+    { // the first 18 digits fit 64-bit arithmetic: every realistic quantity takes only this loop
+        uint64_t m64 = 0;
+        while (int_digits < 18 && s[i] >= '0' && s[i] <= '9') {
+            m64 = m64 * 10 + (unsigned)(s[i++] - '0');
+            int_digits++;
+        }
+        mant = m64;
+    }
     while (s[i] >= '0' && s[i] <= '9') {
         if (mant >= cap) return KS_ERR_RANGE;
         mant = mant * 10 + (unsigned)(s[i++] - '0');
@@ -102,13 +114,6 @@ const char* kv_find(const ks_kv* kv, uint32_t n, const char* key) {
     return nullptr;
 }
 
-std::string pair_key(const char* k, const char* v) {
-    std::string s(k ? k : "");
-    s.push_back('\0');
-    s.append(v ? v : "");
-    return s;
-}
-
 void json_escape(std::string& out, const char* s) {
     for (; s && *s; s++) {
         const unsigned char c = (unsigned char)*s;
@@ -127,89 +132,129 @@ void json_escape(std::string& out, const char* s) {
 
 } // namespace
 
+// ---- string interning: (a, sep, b) byte strings -> dense ids in insertion order; lookups allocate nothing ----
+static inline uint64_t hash_bytes(uint64_t h, const char* s, size_t n) {
+    for (size_t i = 0; i < n; i++) h = (h ^ (unsigned char)s[i]) * 0x100000001B3ull; // FNV-1a
+    return h;
+}
+static inline uint64_t hash2(const char* a, size_t la, char sep, const char* b, size_t lb) {
+    uint64_t h = hash_bytes(0xCBF29CE484222325ull, a, la);
+    h = (h ^ (unsigned char)sep) * 0x100000001B3ull;
+    h = hash_bytes(h, b, lb);
+    h ^= h >> 32; // the table index uses the low bits
+    return h;
+}
+
+struct Interner {
+    struct Ent {
+        uint64_t h;
+        uint64_t off;
+        uint32_t len;
+    };
+    std::vector<char> arena; // every string stored NUL-terminated
+    std::vector<Ent> ents;
+    std::vector<uint32_t> slots; // open addressing, linear probing; EMPTY = free
+    static constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+
+    void clear() {
+        arena.clear();
+        ents.clear();
+        slots.clear();
+    }
+    size_t size() const { return ents.size(); }
+    const char* str(uint32_t id) const { return arena.data() + ents[id].off; }
+    bool equal(const Ent& e, uint64_t h, const char* a, size_t la, char sep, const char* b, size_t lb) const {
+        if (e.h != h || e.len != la + 1 + lb) return false;
+        const char* s = arena.data() + e.off;
+        return std::memcmp(s, a, la) == 0 && s[la] == sep && std::memcmp(s + la + 1, b, lb) == 0;
+    }
+    int64_t find_h(uint64_t h, const char* a, size_t la, char sep, const char* b, size_t lb) const {
+        if (slots.empty()) return -1;
+        const size_t mask = slots.size() - 1;
+        for (size_t i = h & mask;; i = (i + 1) & mask) {
+            const uint32_t id = slots[i];
+            if (id == EMPTY) return -1;
+            if (equal(ents[id], h, a, la, sep, b, lb)) return id;
+        }
+    }
+    int64_t find(const char* a, char sep, const char* b) const {
+        const size_t la = std::strlen(a), lb = std::strlen(b);
+        return find_h(hash2(a, la, sep, b, lb), a, la, sep, b, lb);
+    }
+    void grow() {
+        const size_t cap = slots.empty() ? 64 : slots.size() * 2;
+        slots.assign(cap, EMPTY);
+        for (uint32_t id = 0; id < ents.size(); id++) {
+            size_t i = ents[id].h & (cap - 1);
+            while (slots[i] != EMPTY) i = (i + 1) & (cap - 1);
+            slots[i] = id;
+        }
+    }
+    uint32_t intern_h(uint64_t h, const char* a, size_t la, char sep, const char* b, size_t lb) {
+        const int64_t f = find_h(h, a, la, sep, b, lb);
+        if (f >= 0) return (uint32_t)f;
+        if ((ents.size() + 1) * 2 > slots.size()) grow();
+        const uint32_t id = (uint32_t)ents.size();
+        ents.push_back({h, (uint64_t)arena.size(), (uint32_t)(la + 1 + lb)});
+        arena.insert(arena.end(), a, a + la);
+        arena.push_back(sep);
+        arena.insert(arena.end(), b, b + lb);
+        arena.push_back('\0');
+        const size_t mask = slots.size() - 1;
+        size_t i = h & mask;
+        while (slots[i] != EMPTY) i = (i + 1) & mask;
+        slots[i] = id;
+        return id;
+    }
+    uint32_t intern(const char* a, char sep, const char* b) {
+        const size_t la = std::strlen(a), lb = std::strlen(b);
+        return intern_h(hash2(a, la, sep, b, lb), a, la, sep, b, lb);
+    }
+};
+
+static inline const char* nz(const char* s) { return s ? s : ""; }
+
+// ---- bound pods keyed by "namespace/name": key hash -> position, with erase (positions move on swap-remove) ----
+struct PosTable {
+    // slot = (high 32 bits of the key hash) << 32 | (position + 2); low word 0 = empty, 1 = tombstone
+    std::vector<uint64_t> slots;
+    size_t used = 0; // live + tombstones
+    void clear() {
+        slots.clear();
+        used = 0;
+    }
+};
+
 struct ksh_context {
     ks_snapshot* snap = nullptr;
     uint32_t N = 0;
-    std::vector<std::string> node_names;
-    std::unordered_map<std::string, uint32_t> name2idx;
-    std::vector<std::vector<std::string>> node_pairs; // per node: pair keys "k\0v"
-    std::unordered_set<std::string> all_pairs;        // pairs carried by at least one node
-    std::unordered_map<std::string, uint32_t> dict;   // pair -> bit id, only pairs some selector has named
-    uint32_t W = 1;
+    // nodes: names are interned once; name id -> current index (-1 = gone), index -> name id
+    Interner names;
+    std::vector<int32_t> nameid2idx;
+    std::vector<uint32_t> idx2nameid;
     std::vector<int64_t> alloc_cpu, alloc_mem;
+    // label pairs "key\0value" interned to pair ids; per pair: how many nodes carry it, and its dictionary bit
+    Interner pairs;
+    std::vector<uint32_t> pair_refcnt;
+    std::vector<int32_t> pair_bit;            // -1 = no selector has named this pair yet
+    std::vector<uint32_t> bit2pair;           // dictionary, in order of assignment
+    std::vector<std::vector<uint32_t>> node_pids; // per node: pair ids of its labels
+    uint32_t W = 1;
+    // bound pods (the LIST results of predicates.rs:21-34), swap-remove on delete
     std::vector<int32_t> bnode;
     std::vector<int64_t> bcpu, bmem;
-    std::vector<std::string> bkey;                    // "namespace/name" of each bound pod ("" = unknown)
-    std::unordered_map<std::string, size_t> bkey2pos; // bound pod -> position in the four lists above
+    std::vector<uint64_t> bhash;  // hash of "ns/name"; 0 with blen 0 = anonymous pod, not tracked
+    std::vector<uint64_t> boff;   // key bytes in bkeys
+    std::vector<uint32_t> blen;
+    std::vector<char> bkeys;
+    PosTable btab;
+    // scratch of the bulk calls, kept between calls (fresh pages are expensive to fault in)
+    std::vector<int32_t> tmp_node;
+    std::vector<int64_t> tmp_cpu, tmp_mem;
+    std::vector<uint64_t> tmp_hash;
+    std::vector<uint32_t> tmp_len;
     bool dirty = true; // device snapshot must be re-uploaded
 };
-
-static std::string pod_key(const ks_pod_obj* pod) {
-    std::string k(pod->ns ? pod->ns : "");
-    k.push_back('/');
-    k.append(pod->name ? pod->name : "");
-    return k;
-}
-
-static void bound_push(ksh_context* c, const std::string& key, int32_t node, int64_t cpu, int64_t mem) {
-    if (!key.empty() && key != "/") c->bkey2pos[key] = c->bnode.size();
-    c->bnode.push_back(node);
-    c->bcpu.push_back(cpu);
-    c->bmem.push_back(mem);
-    c->bkey.push_back(key);
-}
-
-static void bound_erase(ksh_context* c, size_t pos) { // swap-remove
-    const size_t last = c->bnode.size() - 1;
-    c->bkey2pos.erase(c->bkey[pos]);
-    if (pos != last) {
-        c->bnode[pos] = c->bnode[last];
-        c->bcpu[pos] = c->bcpu[last];
-        c->bmem[pos] = c->bmem[last];
-        c->bkey[pos] = c->bkey[last];
-        if (!c->bkey[pos].empty() && c->bkey[pos] != "/") c->bkey2pos[c->bkey[pos]] = pos;
-    }
-    c->bnode.pop_back();
-    c->bcpu.pop_back();
-    c->bmem.pop_back();
-    c->bkey.pop_back();
-}
-
-// parse one node object into (allocatable, label pairs); mirrors src/predicates.rs:27-32
-static int parse_node(const ks_node_obj& nd, std::string* name, int64_t* ac, int64_t* am, std::vector<std::string>* pairs) {
-    *name = nd.name ? nd.name : "";
-    *ac = 0;
-    *am = 0; // status/allocatable None => PodResources::new() = (0,0)   (predicates.rs:27-28)
-    if (nd.has_allocatable) {
-        const char* q = kv_find(nd.allocatable, nd.n_allocatable, "cpu");
-        if (!q) return fail(KS_ERR_MISSING, "node '" + *name + "': allocatable has no cpu (reference panics, predicates.rs:29)");
-        int rc = ksh_parse_cpu_millicores(q, ac);
-        if (rc) return rc;
-        q = kv_find(nd.allocatable, nd.n_allocatable, "memory");
-        if (!q) return fail(KS_ERR_MISSING, "node '" + *name + "': allocatable has no memory (reference panics, predicates.rs:30)");
-        rc = ksh_parse_memory_bytes(q, am);
-        if (rc) return rc;
-        if (*ac > KS_MAX_CPU_MILLI || *ac < -KS_MAX_CPU_MILLI || *am > KS_MAX_MEM_BYTES || *am < -KS_MAX_MEM_BYTES)
-            return fail(KS_ERR_RANGE, "node '" + *name + "': allocatable out of range");
-    }
-    pairs->clear();
-    if (nd.has_labels)
-        for (uint32_t l = 0; l < nd.n_labels; l++) pairs->push_back(pair_key(nd.labels[l].key, nd.labels[l].val));
-    return KS_OK;
-}
-
-// pairs carried by at least one node, and dictionary bits restricted to them
-static void rebuild_pair_universe(ksh_context* c) {
-    c->all_pairs.clear();
-    for (const auto& v : c->node_pairs)
-        for (const auto& p : v) c->all_pairs.insert(p);
-    std::unordered_map<std::string, uint32_t> kept;
-    for (auto& kv : c->dict)
-        if (c->all_pairs.count(kv.first)) kept.emplace(kv.first, (uint32_t)kept.size());
-    c->dict.swap(kept);
-    c->W = 1;
-    while ((uint64_t)c->W * 64 < (uint64_t)c->dict.size() + 1) c->W <<= 1;
-}
 
 static uint32_t words_for_bits(uint32_t real_bits) {
     // +1: the last bit of the last word is the shared "no node carries this pair" bit
@@ -218,14 +263,310 @@ static uint32_t words_for_bits(uint32_t real_bits) {
     return w;
 }
 
+// ---- threads ----
+static unsigned host_threads() {
+    static const unsigned t = [] {
+        if (const char* e = std::getenv("KSH_THREADS")) {
+            const int v = std::atoi(e);
+            if (v > 0) return (unsigned)std::min(v, 256);
+        }
+        const unsigned hc = std::thread::hardware_concurrency();
+        return std::max(1u, std::min(hc ? hc : 1u, 32u));
+    }();
+    return t;
+}
+
+// f(thread, begin, end) over [0,n) in contiguous ascending ranges: concatenating per-thread results in thread order
+// reproduces the serial order
+template <class F>
+static unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F f) {
+    unsigned T = (unsigned)std::min<uint64_t>(host_threads(), std::max<uint64_t>(1, n / std::max<uint64_t>(1, min_per_thread)));
+    if (T <= 1) {
+        f(0u, (uint64_t)0, n);
+        return 1;
+    }
+    std::vector<std::thread> th;
+    th.reserve(T - 1);
+    const uint64_t per = (n + T - 1) / T;
+    for (unsigned t = 1; t < T; t++) th.emplace_back([=, &f] { f(t, std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    f(0u, (uint64_t)0, std::min(n, per));
+    for (auto& x : th) x.join();
+    return T;
+}
+
+struct alignas(128) RangeError { // first failure of a range (ranges stop at their first failure); one cache line pair each
+    int rc = KS_OK;
+    std::string msg;
+};
+static int first_error(const std::vector<RangeError>& errs) {
+    for (const RangeError& e : errs)
+        if (e.rc) return fail(e.rc, e.msg);
+    return KS_OK;
+}
+
+// ---- parsing without touching the caller-visible error string (usable from worker threads) ----
+static int parse_cpu(const char* q, int64_t* out, std::string* err) {
+    const int rc = parse_quantity(q, 3, out);
+    if (rc) *err = std::string("cannot convert cpu quantity '") + (q ? q : "(null)") + "' to integer millicores";
+    return rc;
+}
+static int parse_mem(const char* q, int64_t* out, std::string* err) {
+    const int rc = parse_quantity(q, 0, out);
+    if (rc) *err = std::string("cannot convert memory quantity '") + (q ? q : "(null)") + "' to integer bytes";
+    return rc;
+}
+
+// src/util.rs:54-75: sum of resources.requests over spec.containers only (no initContainers, no limits)
+static int total_pod_resources(const ks_pod_obj* pod, int64_t* cpu, int64_t* mem, std::string* err) {
+    int64_t c = 0, m = 0;
+    if (pod->has_spec) {
+        for (uint32_t i = 0; i < pod->n_containers; i++) {
+            const ks_container_obj& ct = pod->containers[i];
+            if (!ct.has_requests) continue;
+            if (const char* q = kv_find(ct.requests, ct.n_requests, "cpu")) {
+                int64_t v;
+                const int rc = parse_cpu(q, &v, err); // reference: .expect("invalid pod spec: cpu request")
+                if (rc) return rc;
+                if (__builtin_add_overflow(c, v, &c)) return *err = "cpu request sum overflows", KS_ERR_RANGE;
+            }
+            if (const char* q = kv_find(ct.requests, ct.n_requests, "memory")) {
+                int64_t v;
+                const int rc = parse_mem(q, &v, err);
+                if (rc) return rc;
+                if (__builtin_add_overflow(m, v, &m)) return *err = "memory request sum overflows", KS_ERR_RANGE;
+            }
+        }
+    }
+    if (c > KS_MAX_CPU_MILLI || c < -KS_MAX_CPU_MILLI || m > KS_MAX_MEM_BYTES || m < -KS_MAX_MEM_BYTES)
+        return *err = "pod requests outside +-2^36 millicores / +-2^55 bytes", KS_ERR_RANGE;
+    *cpu = c;
+    *mem = m;
+    return KS_OK;
+}
+
+// allocatable of one node; mirrors src/predicates.rs:27-32
+static int parse_node_allocatable(const ks_node_obj& nd, int64_t* ac, int64_t* am, std::string* err) {
+    *ac = 0;
+    *am = 0; // status/allocatable None => PodResources::new() = (0,0)   (predicates.rs:27-28)
+    if (!nd.has_allocatable) return KS_OK;
+    const std::string name = nz(nd.name);
+    const char* q = kv_find(nd.allocatable, nd.n_allocatable, "cpu");
+    if (!q) return *err = "node '" + name + "': allocatable has no cpu (reference panics, predicates.rs:29)", KS_ERR_MISSING;
+    int rc = parse_cpu(q, ac, err);
+    if (rc) return rc;
+    q = kv_find(nd.allocatable, nd.n_allocatable, "memory");
+    if (!q) return *err = "node '" + name + "': allocatable has no memory (reference panics, predicates.rs:30)", KS_ERR_MISSING;
+    rc = parse_mem(q, am, err);
+    if (rc) return rc;
+    if (*ac > KS_MAX_CPU_MILLI || *ac < -KS_MAX_CPU_MILLI || *am > KS_MAX_MEM_BYTES || *am < -KS_MAX_MEM_BYTES)
+        return *err = "node '" + name + "': allocatable out of range", KS_ERR_RANGE;
+    return KS_OK;
+}
+
+// ---- label pairs ----
+static uint32_t intern_pair(ksh_context* c, uint64_t h, const char* k, size_t lk, const char* v, size_t lv) {
+    const uint32_t pid = c->pairs.intern_h(h, k, lk, '\0', v, lv);
+    if (pid == c->pair_refcnt.size()) {
+        c->pair_refcnt.push_back(0);
+        c->pair_bit.push_back(-1);
+    }
+    return pid;
+}
+
+static void node_pairs_release(ksh_context* c, uint32_t idx) {
+    for (uint32_t pid : c->node_pids[idx]) c->pair_refcnt[pid]--;
+    c->node_pids[idx].clear();
+}
+
+static void node_pairs_set(ksh_context* c, uint32_t idx, const ks_node_obj& nd) {
+    std::vector<uint32_t>& v = c->node_pids[idx];
+    if (!nd.has_labels) return;
+    for (uint32_t l = 0; l < nd.n_labels; l++) {
+        const char *k = nz(nd.labels[l].key), *val = nz(nd.labels[l].val);
+        const size_t lk = std::strlen(k), lv = std::strlen(val);
+        const uint32_t pid = intern_pair(c, hash2(k, lk, '\0', val, lv), k, lk, val, lv);
+        if (std::find(v.begin(), v.end(), pid) != v.end()) continue; // a map has each key once; be safe
+        v.push_back(pid);
+        c->pair_refcnt[pid]++;
+    }
+}
+
+// Dictionary bits of pairs that no node carries any more are dead weight (a selector naming such a pair is
+// infeasible everywhere either way); they are dropped, and the rest renumbered in order, when space is needed.
+static void compact_dictionary(ksh_context* c) {
+    std::vector<uint32_t> kept;
+    for (uint32_t pid : c->bit2pair) {
+        if (c->pair_refcnt[pid] > 0) {
+            c->pair_bit[pid] = (int32_t)kept.size();
+            kept.push_back(pid);
+        } else {
+            c->pair_bit[pid] = -1;
+        }
+    }
+    if (kept.size() != c->bit2pair.size()) c->dirty = true;
+    c->bit2pair.swap(kept);
+}
+
+static int assign_bit(ksh_context* c, uint32_t pid) {
+    if (c->pair_bit[pid] >= 0) return KS_OK;
+    if (words_for_bits((uint32_t)c->bit2pair.size() + 1) > KS_MAX_LABEL_WORDS) {
+        compact_dictionary(c);
+        if (words_for_bits((uint32_t)c->bit2pair.size() + 1) > KS_MAX_LABEL_WORDS)
+            return fail(KS_ERR_RANGE, "more than 511 distinct (key,value) pairs referenced by selectors");
+    }
+    c->pair_bit[pid] = (int32_t)c->bit2pair.size();
+    c->bit2pair.push_back(pid);
+    c->dirty = true;
+    return KS_OK;
+}
+
+static void update_words(ksh_context* c) {
+    const uint32_t w = words_for_bits((uint32_t)c->bit2pair.size());
+    if (w != c->W) {
+        c->W = w;
+        c->dirty = true;
+    }
+}
+
 // node label words [N*W] under the current dictionary
 static void fill_label_words(const ksh_context* c, uint64_t* lab) {
     std::memset(lab, 0, (size_t)c->N * c->W * sizeof(uint64_t));
     for (uint32_t n = 0; n < c->N; n++)
-        for (const std::string& pk : c->node_pairs[n]) {
-            auto it = c->dict.find(pk);
-            if (it != c->dict.end()) lab[(size_t)n * c->W + (it->second >> 6)] |= 1ull << (it->second & 63);
+        for (uint32_t pid : c->node_pids[n]) {
+            const int32_t bit = c->pair_bit[pid];
+            if (bit >= 0) lab[(size_t)n * c->W + ((uint32_t)bit >> 6)] |= 1ull << (bit & 63);
         }
+}
+
+// ---- bound pods ----
+static inline uint64_t pod_key_hash(const ks_pod_obj* pod, size_t* lns, size_t* lname) {
+    const char *ns = nz(pod->ns), *name = nz(pod->name);
+    *lns = std::strlen(ns);
+    *lname = std::strlen(name);
+    return hash2(ns, *lns, '/', name, *lname);
+}
+
+static bool bkey_equal(const ksh_context* c, size_t pos, uint64_t h, const ks_pod_obj* pod, size_t lns, size_t lname) {
+    if (c->bhash[pos] != h || c->blen[pos] != lns + 1 + lname) return false;
+    const char* s = c->bkeys.data() + c->boff[pos];
+    return std::memcmp(s, nz(pod->ns), lns) == 0 && s[lns] == '/' && std::memcmp(s + lns + 1, nz(pod->name), lname) == 0;
+}
+
+static inline uint64_t btab_word(uint64_t h, size_t pos) { return (h & 0xFFFFFFFF00000000ull) | (uint32_t)(pos + 2); }
+static inline uint32_t slot_low(uint64_t s) { return (uint32_t)s; }
+
+static void btab_rebuild(ksh_context* c, size_t want_live) {
+    size_t cap = 64;
+    while (cap < want_live * 2 + 2) cap *= 2;
+    c->btab.slots.assign(cap, 0);
+    c->btab.used = 0;
+    for (size_t pos = 0; pos < c->bnode.size(); pos++) {
+        if (c->blen[pos] == 0) continue;
+        size_t i = c->bhash[pos] & (cap - 1);
+        while (c->btab.slots[i] != 0) i = (i + 1) & (cap - 1);
+        c->btab.slots[i] = btab_word(c->bhash[pos], pos);
+        c->btab.used++;
+    }
+}
+
+static int64_t btab_find_slot(const ksh_context* c, uint64_t h, const ks_pod_obj* pod, size_t lns, size_t lname) {
+    if (c->btab.slots.empty()) return -1;
+    const size_t mask = c->btab.slots.size() - 1;
+    for (size_t i = h & mask;; i = (i + 1) & mask) {
+        const uint64_t s = c->btab.slots[i];
+        if (s == 0) return -1;
+        if (slot_low(s) >= 2 && (s >> 32) == (h >> 32) && bkey_equal(c, slot_low(s) - 2, h, pod, lns, lname)) return (int64_t)i;
+    }
+}
+
+static int64_t btab_slot_of_pos(const ksh_context* c, size_t pos) {
+    if (c->btab.slots.empty()) return -1;
+    const size_t mask = c->btab.slots.size() - 1;
+    for (size_t i = c->bhash[pos] & mask;; i = (i + 1) & mask) {
+        const uint64_t s = c->btab.slots[i];
+        if (s == 0) return -1;
+        if (slot_low(s) == pos + 2) return (int64_t)i;
+    }
+}
+
+// append a bound pod; a tracked key that is already present is re-pointed to the new row (last one wins, as a map would)
+static void bound_push(ksh_context* c, const ks_pod_obj* pod, uint64_t h, size_t lns, size_t lname, int32_t node, int64_t cpu,
+                       int64_t mem) {
+    const size_t pos = c->bnode.size();
+    const bool tracked = lns + lname > 0; // a pod without namespace and name cannot be addressed by later events
+    c->bnode.push_back(node);
+    c->bcpu.push_back(cpu);
+    c->bmem.push_back(mem);
+    c->bhash.push_back(tracked ? h : 0);
+    c->boff.push_back(c->bkeys.size());
+    c->blen.push_back(tracked ? (uint32_t)(lns + 1 + lname) : 0);
+    if (!tracked) return;
+    c->bkeys.insert(c->bkeys.end(), nz(pod->ns), nz(pod->ns) + lns);
+    c->bkeys.push_back('/');
+    c->bkeys.insert(c->bkeys.end(), nz(pod->name), nz(pod->name) + lname);
+    if ((c->btab.used + 1) * 2 > c->btab.slots.size()) { // also the first insertion
+        btab_rebuild(c, c->bnode.size());                // places every row, the new one included
+        return;
+    }
+    // one probe walk: an older row with the same key is re-pointed; else the first free slot on the way is taken
+    const size_t mask = c->btab.slots.size() - 1;
+    int64_t free_slot = -1;
+    for (size_t i = h & mask;; i = (i + 1) & mask) {
+        const uint64_t s = c->btab.slots[i];
+        if (s == 0) {
+            if (free_slot < 0) {
+                free_slot = (int64_t)i;
+                c->btab.used++;
+            }
+            break;
+        }
+        if (slot_low(s) == 1) {
+            if (free_slot < 0) free_slot = (int64_t)i;
+        } else if ((s >> 32) == (h >> 32) && bkey_equal(c, slot_low(s) - 2, h, pod, lns, lname)) {
+            c->btab.slots[i] = btab_word(h, pos);
+            return;
+        }
+    }
+    c->btab.slots[(size_t)free_slot] = btab_word(h, pos);
+}
+
+static void bound_erase(ksh_context* c, size_t pos) { // swap-remove
+    const size_t last = c->bnode.size() - 1;
+    if (c->blen[pos]) {
+        const int64_t i = btab_slot_of_pos(c, pos);
+        if (i >= 0) c->btab.slots[(size_t)i] = 1; // tombstone
+    }
+    if (pos != last) {
+        if (c->blen[last]) {
+            const int64_t i = btab_slot_of_pos(c, last);
+            if (i >= 0) c->btab.slots[(size_t)i] = btab_word(c->bhash[last], pos);
+        }
+        c->bnode[pos] = c->bnode[last];
+        c->bcpu[pos] = c->bcpu[last];
+        c->bmem[pos] = c->bmem[last];
+        c->bhash[pos] = c->bhash[last];
+        c->boff[pos] = c->boff[last];
+        c->blen[pos] = c->blen[last];
+    }
+    c->bnode.pop_back();
+    c->bcpu.pop_back();
+    c->bmem.pop_back();
+    c->bhash.pop_back();
+    c->boff.pop_back();
+    c->blen.pop_back();
+    // erased keys stay in bkeys until the next bulk load; bound the garbage
+    if (c->bnode.empty()) c->bkeys.clear();
+}
+
+static void bound_clear(ksh_context* c) {
+    c->bnode.clear();
+    c->bcpu.clear();
+    c->bmem.clear();
+    c->bhash.clear();
+    c->boff.clear();
+    c->blen.clear();
+    c->bkeys.clear();
+    c->btab.clear();
 }
 
 static int upload(ksh_context* c) {
@@ -241,72 +582,83 @@ static int upload(ksh_context* c) {
     return KS_OK;
 }
 
-// register every selector pair of the batch; returns <0 on error, else 0
+static inline int32_t node_index_of(const ksh_context* c, const char* name) {
+    const int64_t id = c->names.find(nz(name), '\0', "");
+    return id < 0 ? -1 : c->nameid2idx[(size_t)id];
+}
+
+// Every selector pair of the batch that some node carries gets a dictionary bit (first occurrence first).
+// The scan runs on all host threads; bits are assigned in pod order afterwards.
 static int grow_dictionary(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
-    for (uint64_t p = 0; p < n; p++) {
-        const ks_pod_obj& pod = pods[p];
-        if (!(pod.has_spec && pod.has_node_selector)) continue;
-        for (uint32_t i = 0; i < pod.n_selector; i++) {
-            std::string pk = pair_key(pod.selector[i].key, pod.selector[i].val);
-            if (c->dict.count(pk) || !c->all_pairs.count(pk)) continue; // known, or absent everywhere
-            const uint32_t bit = (uint32_t)c->dict.size();
-            if (words_for_bits(bit + 1) > KS_MAX_LABEL_WORDS)
-                return fail(KS_ERR_RANGE, "more than 511 distinct (key,value) pairs referenced by selectors");
-            c->dict.emplace(std::move(pk), bit);
-            c->dirty = true;
+    std::vector<std::vector<uint32_t>> need(host_threads());
+    parallel_ranges(n, 4096, [&](unsigned t, uint64_t b, uint64_t e) {
+        std::vector<uint32_t>& out = need[t];
+        for (uint64_t p = b; p < e; p++) {
+            const ks_pod_obj& pod = pods[p];
+            if (!(pod.has_spec && pod.has_node_selector)) continue;
+            for (uint32_t i = 0; i < pod.n_selector; i++) {
+                const int64_t pid = c->pairs.find(nz(pod.selector[i].key), '\0', nz(pod.selector[i].val));
+                if (pid < 0 || c->pair_bit[(size_t)pid] >= 0 || c->pair_refcnt[(size_t)pid] == 0) continue; // unknown pair, known bit, or absent everywhere
+                if (out.empty() || out.back() != (uint32_t)pid) out.push_back((uint32_t)pid);
+            }
         }
-    }
-    const uint32_t w = words_for_bits((uint32_t)c->dict.size());
-    if (w != c->W) {
-        c->W = w;
-        c->dirty = true;
-    }
+    });
+    for (const auto& v : need)
+        for (uint32_t pid : v) {
+            const int rc = assign_bit(c, pid);
+            if (rc) return rc;
+        }
+    update_words(c);
     return KS_OK;
+}
+
+// request totals and selector words of a batch under the current dictionary (grow_dictionary has run)
+static int pack_rows(const ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* req_cpu, int64_t* req_mem,
+                     uint64_t* sel, uint32_t stride) {
+    const uint32_t absent = c->W * 64 - 1;
+    std::vector<RangeError> errs(host_threads());
+    parallel_ranges(n, 2048, [&](unsigned t, uint64_t b, uint64_t e) {
+        for (uint64_t p = b; p < e; p++) {
+            const int rc = total_pod_resources(&pods[p], &req_cpu[p], &req_mem[p], &errs[t].msg);
+            if (rc) {
+                errs[t].rc = rc;
+                return;
+            }
+            uint64_t* row = sel + p * stride;
+            for (uint32_t w = 0; w < stride; w++) row[w] = 0;
+            if (pods[p].has_spec && pods[p].has_node_selector)
+                for (uint32_t i = 0; i < pods[p].n_selector; i++) {
+                    const int64_t pid = c->pairs.find(nz(pods[p].selector[i].key), '\0', nz(pods[p].selector[i].val));
+                    const int32_t b_ = pid < 0 ? -1 : c->pair_bit[(size_t)pid];
+                    const uint32_t bit = b_ < 0 ? absent : (uint32_t)b_; // a pair no node carries: never-set bit
+                    row[bit >> 6] |= 1ull << (bit & 63);
+                }
+        }
+    });
+    return first_error(errs);
 }
 
 extern "C" {
 
 int ksh_parse_cpu_millicores(const char* q, int64_t* out) {
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");
-    int rc = parse_quantity(q, 3, out);
-    if (rc) return fail(rc, std::string("cannot convert cpu quantity '") + (q ? q : "(null)") + "' to integer millicores");
-    return KS_OK;
+    std::string err;
+    const int rc = parse_cpu(q, out, &err);
+    return rc ? fail(rc, err) : KS_OK;
 }
 
 int ksh_parse_memory_bytes(const char* q, int64_t* out) {
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");
-    int rc = parse_quantity(q, 0, out);
-    if (rc) return fail(rc, std::string("cannot convert memory quantity '") + (q ? q : "(null)") + "' to integer bytes");
-    return KS_OK;
+    std::string err;
+    const int rc = parse_mem(q, out, &err);
+    return rc ? fail(rc, err) : KS_OK;
 }
 
-// src/util.rs:54-75: sum of resources.requests over spec.containers only (no initContainers, no limits)
 int ksh_total_pod_resources(const ks_pod_obj* pod, int64_t* cpu, int64_t* mem) {
     if (!pod || !cpu || !mem) return fail(KS_ERR_INVALID, "NULL argument");
-    int64_t c = 0, m = 0;
-    if (pod->has_spec) {
-        for (uint32_t i = 0; i < pod->n_containers; i++) {
-            const ks_container_obj& ct = pod->containers[i];
-            if (!ct.has_requests) continue;
-            if (const char* q = kv_find(ct.requests, ct.n_requests, "cpu")) {
-                int64_t v;
-                int rc = ksh_parse_cpu_millicores(q, &v); // reference: .expect("invalid pod spec: cpu request")
-                if (rc) return rc;
-                if (__builtin_add_overflow(c, v, &c)) return fail(KS_ERR_RANGE, "cpu request sum overflows");
-            }
-            if (const char* q = kv_find(ct.requests, ct.n_requests, "memory")) {
-                int64_t v;
-                int rc = ksh_parse_memory_bytes(q, &v);
-                if (rc) return rc;
-                if (__builtin_add_overflow(m, v, &m)) return fail(KS_ERR_RANGE, "memory request sum overflows");
-            }
-        }
-    }
-    if (c > KS_MAX_CPU_MILLI || c < -KS_MAX_CPU_MILLI || m > KS_MAX_MEM_BYTES || m < -KS_MAX_MEM_BYTES)
-        return fail(KS_ERR_RANGE, "pod requests outside +-2^36 millicores / +-2^55 bytes");
-    *cpu = c;
-    *mem = m;
-    return KS_OK;
+    std::string err;
+    const int rc = total_pod_resources(pod, cpu, mem, &err);
+    return rc ? fail(rc, err) : KS_OK;
 }
 
 int ksh_is_pod_bound(const ks_pod_obj* pod) { return pod && pod->has_spec && pod->node_name != nullptr; } // util.rs:38-45
@@ -362,79 +714,79 @@ ks_snapshot* ksh_context_snapshot(ksh_context* c) {
 
 int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) {
     if (!c || (n && !nodes)) return fail(KS_ERR_INVALID, "NULL argument");
+    // validate first (quantities parsed by all host threads), then replace
     std::vector<int64_t> ac(n), am(n);
-    std::vector<std::vector<std::string>> pairs(n);
-    std::vector<std::string> names(n);
-    std::unordered_set<std::string> all;
-    for (uint32_t i = 0; i < n; i++) {
-        const ks_node_obj& nd = nodes[i];
-        names[i] = nd.name ? nd.name : "";
-        ac[i] = 0;
-        am[i] = 0; // status/allocatable None => PodResources::new() = (0,0)   (predicates.rs:27-28)
-        if (nd.has_allocatable) {
-            const char* q = kv_find(nd.allocatable, nd.n_allocatable, "cpu");
-            if (!q) return fail(KS_ERR_MISSING, "node '" + names[i] + "': allocatable has no cpu (reference panics, predicates.rs:29)");
-            int rc = ksh_parse_cpu_millicores(q, &ac[i]);
-            if (rc) return rc;
-            q = kv_find(nd.allocatable, nd.n_allocatable, "memory");
-            if (!q) return fail(KS_ERR_MISSING, "node '" + names[i] + "': allocatable has no memory (reference panics, predicates.rs:30)");
-            rc = ksh_parse_memory_bytes(q, &am[i]);
-            if (rc) return rc;
-            if (ac[i] > KS_MAX_CPU_MILLI || ac[i] < -KS_MAX_CPU_MILLI || am[i] > KS_MAX_MEM_BYTES || am[i] < -KS_MAX_MEM_BYTES)
-                return fail(KS_ERR_RANGE, "node '" + names[i] + "': allocatable out of range");
-        }
-        if (nd.has_labels)
-            for (uint32_t l = 0; l < nd.n_labels; l++) {
-                pairs[i].push_back(pair_key(nd.labels[l].key, nd.labels[l].val));
-                all.insert(pairs[i].back());
+    std::vector<RangeError> errs(host_threads());
+    parallel_ranges(n, 2048, [&](unsigned t, uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; i++) {
+            const int rc = parse_node_allocatable(nodes[i], &ac[i], &am[i], &errs[t].msg);
+            if (rc) {
+                errs[t].rc = rc;
+                return;
             }
-    }
+        }
+    });
+    int rc = first_error(errs);
+    if (rc) return rc;
+    // selector pairs that already have a bit keep it if some new node still carries the pair
+    std::vector<std::string> named; // "key\0value" of the dictionary, in bit order
+    named.reserve(c->bit2pair.size());
+    for (uint32_t pid : c->bit2pair) named.emplace_back(c->pairs.str(pid), c->pairs.ents[pid].len);
+    c->names.clear();
+    c->nameid2idx.clear();
+    c->idx2nameid.assign(n, 0);
+    c->pairs.clear();
+    c->pair_refcnt.clear();
+    c->pair_bit.clear();
+    c->bit2pair.clear();
+    c->node_pids.assign(n, {});
     c->N = n;
     c->alloc_cpu.swap(ac);
     c->alloc_mem.swap(am);
-    c->node_pairs.swap(pairs);
-    c->node_names.swap(names);
-    c->all_pairs.swap(all);
-    c->name2idx.clear();
-    for (uint32_t i = 0; i < n; i++) c->name2idx.emplace(c->node_names[i], i); // first wins
-    // keep dictionary bits only for pairs that still exist on some node
-    std::unordered_map<std::string, uint32_t> kept;
-    for (auto& kv : c->dict)
-        if (c->all_pairs.count(kv.first)) kept.emplace(kv.first, (uint32_t)kept.size());
-    c->dict.swap(kept);
-    c->W = words_for_bits((uint32_t)c->dict.size());
-    c->bnode.clear();
-    c->bcpu.clear();
-    c->bmem.clear();
-    c->bkey.clear();
-    c->bkey2pos.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t id = c->names.intern(nz(nodes[i].name), '\0', "");
+        if (id == c->nameid2idx.size()) c->nameid2idx.push_back((int32_t)i); // first node of a name wins
+        c->idx2nameid[i] = id;
+        node_pairs_set(c, i, nodes[i]);
+    }
+    for (const std::string& pk : named) {
+        const char* k = pk.c_str();
+        const char* v = k + std::strlen(k) + 1;
+        const int64_t pid = c->pairs.find(k, '\0', v);
+        if (pid >= 0 && c->pair_refcnt[(size_t)pid] > 0) {
+            c->pair_bit[(size_t)pid] = (int32_t)c->bit2pair.size();
+            c->bit2pair.push_back((uint32_t)pid);
+        }
+    }
+    c->W = words_for_bits((uint32_t)c->bit2pair.size());
+    bound_clear(c);
     c->dirty = true;
     return KS_OK;
 }
 
 int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* out_idx) {
     if (!c || !node) return fail(KS_ERR_INVALID, "NULL argument");
-    std::string name;
     int64_t ac, am;
-    std::vector<std::string> pairs;
-    int rc = parse_node(*node, &name, &ac, &am, &pairs);
-    if (rc) return rc;
-    auto it = c->name2idx.find(name);
+    std::string err;
+    const int rc = parse_node_allocatable(*node, &ac, &am, &err);
+    if (rc) return fail(rc, err);
+    const uint32_t id = c->names.intern(nz(node->name), '\0', "");
+    if (id == c->nameid2idx.size()) c->nameid2idx.push_back(-1);
     uint32_t idx;
-    if (it == c->name2idx.end()) {
+    if (c->nameid2idx[id] < 0) { // new node (or one that had been removed): appended
         idx = c->N++;
-        c->node_names.push_back(name);
+        c->nameid2idx[id] = (int32_t)idx;
+        c->idx2nameid.push_back(id);
         c->alloc_cpu.push_back(ac);
         c->alloc_mem.push_back(am);
-        c->node_pairs.push_back(pairs);
-        c->name2idx.emplace(name, idx);
+        c->node_pids.emplace_back();
     } else {
-        idx = it->second;
+        idx = (uint32_t)c->nameid2idx[id];
         c->alloc_cpu[idx] = ac;
         c->alloc_mem[idx] = am;
-        c->node_pairs[idx] = pairs;
+        node_pairs_release(c, idx);
     }
-    rebuild_pair_universe(c);
+    node_pairs_set(c, idx, *node);
     c->dirty = true;
     if (out_idx) *out_idx = idx;
     return KS_OK;
@@ -442,16 +794,20 @@ int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* o
 
 int ksh_context_remove_node(ksh_context* c, const char* name) {
     if (!c || !name) return fail(KS_ERR_INVALID, "NULL argument");
-    auto it = c->name2idx.find(name);
-    if (it == c->name2idx.end()) return KS_OK;
-    const uint32_t idx = it->second;
-    c->node_names.erase(c->node_names.begin() + idx);
+    const int32_t found = node_index_of(c, name);
+    if (found < 0) return KS_OK;
+    const uint32_t idx = (uint32_t)found;
+    node_pairs_release(c, idx);
+    c->nameid2idx[c->idx2nameid[idx]] = -1;
+    c->idx2nameid.erase(c->idx2nameid.begin() + idx);
     c->alloc_cpu.erase(c->alloc_cpu.begin() + idx);
     c->alloc_mem.erase(c->alloc_mem.begin() + idx);
-    c->node_pairs.erase(c->node_pairs.begin() + idx);
+    c->node_pids.erase(c->node_pids.begin() + idx);
     c->N--;
-    c->name2idx.clear();
-    for (uint32_t i = 0; i < c->N; i++) c->name2idx.emplace(c->node_names[i], i);
+    // later nodes move down by one index; a name carried by several rows points to its first remaining row
+    for (uint32_t i = c->N; i-- > idx;) c->nameid2idx[c->idx2nameid[i]] = (int32_t)i;
+    for (uint32_t i = 0; i < idx; i++)
+        if (c->nameid2idx[c->idx2nameid[i]] > (int32_t)i) c->nameid2idx[c->idx2nameid[i]] = (int32_t)i;
     // pods bound to the removed node disappear from every later LIST; indices above it move down
     for (size_t p = 0; p < c->bnode.size();) {
         if ((uint32_t)c->bnode[p] == idx) {
@@ -461,7 +817,6 @@ int ksh_context_remove_node(ksh_context* c, const char* name) {
             p++;
         }
     }
-    rebuild_pair_universe(c);
     c->dirty = true;
     return KS_OK;
 }
@@ -469,52 +824,88 @@ int ksh_context_remove_node(ksh_context* c, const char* name) {
 int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
     if (!ksh_is_pod_bound(pod)) return KS_OK;
-    auto it = c->name2idx.find(pod->node_name);
-    if (it == c->name2idx.end()) return KS_OK;
+    const int32_t node = node_index_of(c, pod->node_name);
+    if (node < 0) return KS_OK;
     int64_t cpu, mem;
-    int rc = ksh_total_pod_resources(pod, &cpu, &mem);
-    if (rc) return rc;
-    const std::string key = pod_key(pod);
-    auto old = c->bkey2pos.find(key);
-    if (old != c->bkey2pos.end()) bound_erase(c, old->second); // update of a pod already known
-    bound_push(c, key, (int32_t)it->second, cpu, mem);
+    std::string err;
+    const int rc = total_pod_resources(pod, &cpu, &mem, &err);
+    if (rc) return fail(rc, err);
+    size_t lns, lname;
+    const uint64_t h = pod_key_hash(pod, &lns, &lname);
+    if (lns + lname > 0) {
+        const int64_t slot = btab_find_slot(c, h, pod, lns, lname);
+        if (slot >= 0) bound_erase(c, slot_low(c->btab.slots[(size_t)slot]) - 2); // update of a pod already known
+    }
+    bound_push(c, pod, h, lns, lname, node, cpu, mem);
     c->dirty = true;
     return KS_OK;
 }
 
 int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
-    auto it = c->bkey2pos.find(pod_key(pod));
-    if (it == c->bkey2pos.end()) return KS_OK;
-    bound_erase(c, it->second);
+    size_t lns, lname;
+    const uint64_t h = pod_key_hash(pod, &lns, &lname);
+    if (lns + lname == 0) return KS_OK;
+    const int64_t slot = btab_find_slot(c, h, pod, lns, lname);
+    if (slot < 0) return KS_OK;
+    bound_erase(c, slot_low(c->btab.slots[(size_t)slot]) - 2);
     c->dirty = true;
     return KS_OK;
 }
 
 const char* ksh_context_node_name(const ksh_context* c, uint32_t idx) {
-    return (c && idx < c->N) ? c->node_names[idx].c_str() : nullptr;
+    return (c && idx < c->N) ? c->names.str(c->idx2nameid[idx]) : nullptr;
 }
 
 int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
-    // validate first, then replace
-    std::vector<int64_t> cpus(n), mems(n);
-    for (uint64_t p = 0; p < n; p++) {
-        if (!ksh_is_pod_bound(&pods[p]) || !c->name2idx.count(pods[p].node_name)) continue;
-        int rc = ksh_total_pod_resources(&pods[p], &cpus[p], &mems[p]); // predicates.rs:37
-        if (rc) return rc;
-    }
-    c->bnode.clear();
-    c->bcpu.clear();
-    c->bmem.clear();
-    c->bkey.clear();
-    c->bkey2pos.clear();
-    for (uint64_t p = 0; p < n; p++) {
-        if (!ksh_is_pod_bound(&pods[p])) continue;
-        auto it = c->name2idx.find(pods[p].node_name); // field selector spec.nodeName=<node> (predicates.rs:22-25)
-        if (it == c->name2idx.end()) continue;
-        bound_push(c, pod_key(&pods[p]), (int32_t)it->second, cpus[p], mems[p]);
-    }
+    if (n > 0xFFFFFFF0ull) return fail(KS_ERR_RANGE, "too many pods");
+    // validate first, then replace.  Per pod (all host threads): spec.nodeName -> node index (the field selector of
+    // predicates.rs:22-25), request totals (predicates.rs:37), key hash.
+    std::vector<int32_t>& node = c->tmp_node;
+    std::vector<int64_t>&cpus = c->tmp_cpu, &mems = c->tmp_mem;
+    std::vector<uint64_t>& hashes = c->tmp_hash;
+    std::vector<uint32_t>& lens = c->tmp_len;
+    node.resize(n);
+    cpus.resize(n);
+    mems.resize(n);
+    hashes.resize(n);
+    lens.resize(2 * n);
+    std::vector<RangeError> errs(host_threads());
+    parallel_ranges(n, 4096, [&](unsigned t, uint64_t b, uint64_t e) {
+        for (uint64_t p = b; p < e; p++) {
+            node[p] = ksh_is_pod_bound(&pods[p]) ? node_index_of(c, pods[p].node_name) : -1;
+            if (node[p] < 0) continue;
+            const int rc = total_pod_resources(&pods[p], &cpus[p], &mems[p], &errs[t].msg);
+            if (rc) {
+                errs[t].rc = rc;
+                return;
+            }
+            size_t lns, lname;
+            hashes[p] = pod_key_hash(&pods[p], &lns, &lname);
+            lens[2 * p] = (uint32_t)lns;
+            lens[2 * p + 1] = (uint32_t)lname;
+        }
+    });
+    const int rc = first_error(errs);
+    if (rc) return rc;
+    bound_clear(c);
+    uint64_t kept = 0, key_bytes = 0;
+    for (uint64_t p = 0; p < n; p++)
+        if (node[p] >= 0) {
+            kept++;
+            key_bytes += (uint64_t)lens[2 * p] + lens[2 * p + 1] + 1;
+        }
+    c->bnode.reserve(kept);
+    c->bcpu.reserve(kept);
+    c->bmem.reserve(kept);
+    c->bhash.reserve(kept);
+    c->boff.reserve(kept);
+    c->blen.reserve(kept);
+    c->bkeys.reserve(key_bytes);
+    btab_rebuild(c, kept); // sized once for the whole list
+    for (uint64_t p = 0; p < n; p++)
+        if (node[p] >= 0) bound_push(c, &pods[p], hashes[p], lens[2 * p], lens[2 * p + 1], node[p], cpus[p], mems[p]);
     c->dirty = true;
     return KS_OK;
 }
@@ -525,19 +916,8 @@ int ksh_pack_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* r
     int rc = grow_dictionary(c, pods, n);
     if (rc) return rc;
     if (stride < c->W) return fail(KS_ERR_INVALID, "sel_stride_words smaller than the dictionary's word count");
-    const uint32_t absent = c->W * 64 - 1;
-    for (uint64_t p = 0; p < n; p++) {
-        rc = ksh_total_pod_resources(&pods[p], &req_cpu[p], &req_mem[p]);
-        if (rc) return rc;
-        uint64_t* row = sel + p * stride;
-        for (uint32_t w = 0; w < stride; w++) row[w] = 0;
-        if (pods[p].has_spec && pods[p].has_node_selector)
-            for (uint32_t i = 0; i < pods[p].n_selector; i++) {
-                auto it = c->dict.find(pair_key(pods[p].selector[i].key, pods[p].selector[i].val));
-                const uint32_t bit = it == c->dict.end() ? absent : it->second;
-                row[bit >> 6] |= 1ull << (bit & 63);
-            }
-    }
+    rc = pack_rows(c, pods, n, req_cpu, req_mem, sel, stride);
+    if (rc) return rc;
     return (int)c->W;
 }
 
@@ -547,9 +927,9 @@ static int pack_and_upload(ksh_context* c, const ks_pod_obj* pods, uint64_t n, s
     if (rc) return rc;
     rc_.resize(n);
     rm_.resize(n);
-    sel.assign((size_t)n * c->W, 0);
-    rc = ksh_pack_pods(c, pods, n, rc_.data(), rm_.data(), sel.data(), c->W);
-    if (rc < 0) return rc;
+    sel.resize((size_t)n * c->W);
+    rc = pack_rows(c, pods, n, rc_.data(), rm_.data(), sel.data(), c->W);
+    if (rc) return rc;
     return upload(c);
 }
 
@@ -609,7 +989,11 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
     // what the next LIST would report once the binding is accepted (src/predicates.rs:34 after src/main.rs:103)
     rc = ks_snapshot_apply_bind(c->snap, idx, cpu, mem);
     if (rc) return rc;
-    bound_push(c, pod_key(pod), idx, cpu, mem);
+    {
+        size_t lns, lname;
+        const uint64_t h = pod_key_hash(pod, &lns, &lname);
+        bound_push(c, pod, h, lns, lname, idx, cpu, mem);
+    }
     *node_idx = idx;
     if (json && cap) { // corev1::Binding{metadata, target: ObjectReference{name}}  (src/main.rs:83-91)
         std::string s = "{\"apiVersion\":\"v1\",\"kind\":\"Binding\",\"metadata\":{\"name\":\"";
@@ -617,7 +1001,7 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
         s += "\",\"namespace\":\"";
         json_escape(s, pod->ns);
         s += "\"},\"target\":{\"name\":\"";
-        json_escape(s, c->node_names[idx].c_str());
+        json_escape(s, ksh_context_node_name(c, (uint32_t)idx));
         s += "\"}}";
         std::snprintf(json, cap, "%s", s.c_str());
     }

@@ -303,3 +303,139 @@ def test_incremental_node_and_pod_events_equal_a_rebuilt_context(ks, orc):
     oidx, oscore, ocnt, _, _ = oc.run(pods, cl.P)
     assert np.array_equal(idx, oidx) and np.array_equal(score, oscore) and np.array_equal(cnt, ocnt)
     assert names == [final_nodes_s[i]["name"] if i >= 0 else None for i in oidx]
+
+
+_THREAD_SNIPPET = r"""
+import hashlib, sys
+sys.path.insert(0, %r)
+import ksched_pkg
+ks = ksched_pkg.load()
+cl = ks.synth.make(30000, 3000, seed=77, n_keys=32, bound_per_node=10)
+nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+arena = ks.objects.ObjectArena()
+nodes, bound, pods = arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+h = hashlib.sha256()
+with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+    ctx.set_nodes(nodes, cl.N)
+    ctx.set_cluster_pods(bound, cl.B)
+    for a in ctx.pack_pods(pods, cl.P) + ctx.export_packed():
+        h.update(a.tobytes())
+    w = ctx.label_words
+    bad = list(pods_s)
+    bad[20000] = dict(bad[20000], containers=[{"cpu": "two"}])
+    bad[5000] = dict(bad[5000], containers=[{"memory": "1.5"}])
+    try:
+        ctx.pack_pods(arena.pods(bad), cl.P)
+        err = "no error"
+    except ks.KsError as e:
+        err = "%%d %%s" %% (e.code, str(e).split(": ", 1)[1])
+print(h.hexdigest(), w, err)
+"""
+
+
+def test_packer_is_identical_for_any_thread_count(ks):
+    """Bulk calls run on all host threads; dictionary bits, packed arrays and the reported error (the first failing
+    object in array order) must not depend on how many there are."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, KSH_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", _THREAD_SNIPPET % root], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] == outs[2], outs
+    assert " -6 " in outs[0] and "1.5" in outs[0]  # pod 5000 (memory '1.5', KS_ERR_INEXACT), not pod 20000
+
+
+def test_packer_event_fuzz_against_a_model(ks, orc):
+    """Random informer events (node upsert / remove, pod bound / re-bound / deleted) on a packing-only context vs a
+    plain Python model of the cluster; the final state is compared through the faithful oracle."""
+    rng = np.random.default_rng(2024)
+    cl = ks.synth.make(150, 60, seed=5, bound_per_node=3)
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    arena = ks.objects.ObjectArena()
+    pods = arena.pods(pods_s)
+    model_nodes = [dict(n) for n in nodes_s[:20]]          # ordered: index = position
+    model_bound = {}                                       # (ns, name) -> spec
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(arena.nodes(model_nodes), len(model_nodes))
+        ctx.set_cluster_pods(arena.pods([]), 0)
+        spare_nodes = [dict(n) for n in nodes_s[20:]]
+        spare_bound = [dict(b) for b in bound_s]
+        for step in range(1500):
+            ev = rng.integers(0, 100)
+            names = [n["name"] for n in model_nodes]
+            if ev < 10 and spare_nodes:                                     # new node
+                n = spare_nodes.pop()
+                assert ctx.upsert_node(arena.nodes([n])) == len(model_nodes)
+                model_nodes.append(n)
+            elif ev < 20 and model_nodes:                                   # node changes (size and a label)
+                i = int(rng.integers(0, len(model_nodes)))
+                n = dict(model_nodes[i])
+                n["allocatable"] = {"cpu": str(int(rng.integers(1, 64))), "memory": str(int(rng.integers(1, 64)) << 30)}
+                lab = dict(n.get("labels") or {})
+                lab["key0"] = f"v{int(rng.integers(0, 8))}"
+                n["labels"] = lab
+                assert ctx.upsert_node(arena.nodes([n])) == i
+                model_nodes[i] = n
+            elif ev < 25 and len(model_nodes) > 5:                          # node goes away, with its pods
+                i = int(rng.integers(0, len(model_nodes)))
+                gone = model_nodes.pop(i)
+                ctx.remove_node(gone["name"])
+                spare_nodes.append(gone)
+                for k in [k for k, b in model_bound.items() if b["node_name"] == gone["name"]]:
+                    del model_bound[k]
+            elif ev < 75 and spare_bound and names:                         # pod bound (new, or an update of a known pod)
+                b = dict(spare_bound[int(rng.integers(0, len(spare_bound)))])
+                b["node_name"] = names[int(rng.integers(0, len(names)))]
+                ctx.pod_bound(arena.pods([b]))
+                model_bound[(b.get("ns"), b["name"])] = b
+            elif model_bound:                                               # pod deleted
+                keys = list(model_bound)
+                k = keys[int(rng.integers(0, len(keys)))]
+                ctx.pod_deleted(arena.pods([model_bound.pop(k)]))
+            if step % 250 == 249:
+                ctx.pack_pods(pods, cl.P)                                   # dictionary grows in between, too
+        assert ctx.n_nodes == len(model_nodes)
+        assert [ctx.node_name(i) for i in range(ctx.n_nodes)] == [n["name"] for n in model_nodes]
+        got = _packed_answer(orc, ctx, pods, cl.P)
+    fb = list(model_bound.values())
+    oc = orc.Cluster(arena.nodes(model_nodes), len(model_nodes), arena.pods(fb), len(fb))
+    want = oc.run(pods, cl.P, want_codes=True)
+    for g_, w, name in zip(got, want, ("node_idx", "score", "feasible_cnt", "mask", "codes")):
+        assert np.array_equal(g_, w), name
+
+
+def test_packer_dictionary_compaction_and_duplicate_names(ks):
+    arena = ks.objects.ObjectArena()
+    alloc = {"cpu": "4", "memory": str(1 << 30)}
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(arena.nodes([{"name": "a", "labels": {"gen": "g0"}, "allocatable": alloc}]), 1)
+        # 700 generations of a label: each gets a dictionary bit when a selector names it, the old ones go stale and
+        # must be reclaimed instead of overflowing the 511-pair dictionary
+        for g in range(700):
+            ctx.upsert_node(arena.nodes([{"name": "a", "labels": {"gen": f"g{g}"}, "allocatable": alloc}]))
+            want = arena.pods([{"name": "p", "ns": "d", "selector": {"gen": f"g{g}"}},
+                               {"name": "q", "ns": "d", "selector": {"gen": f"g{max(g - 1, 0)}"}}])
+            _, _, sel = ctx.pack_pods(want, 2)
+            lab = ctx.export_packed()[2]
+            assert not np.any(sel[0] & ~lab[0])                      # current generation matches
+            assert (g == 0) or np.any(sel[1] & ~lab[0])              # the previous one no longer does
+        assert ctx.label_words <= 8
+        # duplicate names: the first row of a name is the one events and pods address
+        ctx.set_nodes(arena.nodes([{"name": "x", "allocatable": alloc}, {"name": "y", "allocatable": alloc},
+                                   {"name": "x", "allocatable": alloc}]), 3)
+        ctx.pod_bound(arena.pods([{"name": "b", "ns": "d", "node_name": "x", "containers": [{"cpu": "1"}]}]))
+        assert ctx.export_packed()[3].tolist() == [0]
+        ctx.remove_node("x")                                         # removes row 0; the other "x" is now row 1
+        assert [ctx.node_name(i) for i in range(ctx.n_nodes)] == ["y", "x"] and ctx.export_packed()[3].size == 0
+        ctx.pod_bound(arena.pods([{"name": "b", "ns": "d", "node_name": "x", "containers": [{"cpu": "1"}]}]))
+        ctx.pod_bound(arena.pods([{"name": "b", "ns": "d", "node_name": "y", "containers": [{"cpu": "2"}]}]))  # moved
+        bn, bc = ctx.export_packed()[3], ctx.export_packed()[4]
+        assert bn.tolist() == [0] and bc.tolist() == [2000]
+        assert ctx.upsert_node(arena.nodes([{"name": "z", "allocatable": alloc}])) == 2
+        ctx.remove_node("z")
+        assert ctx.upsert_node(arena.nodes([{"name": "z", "allocatable": alloc}])) == 2  # a removed name comes back as new

@@ -248,6 +248,8 @@ struct ksh_context {
     std::vector<uint32_t> blen;
     std::vector<char> bkeys;
     PosTable btab;
+    uint64_t live_pairs = 0;     // pairs carried by at least one node
+    uint64_t live_key_bytes = 0; // bytes of bkeys that belong to current rows
     // scratch of the bulk calls, kept between calls (fresh pages are expensive to fault in)
     std::vector<int32_t> tmp_node;
     std::vector<int64_t> tmp_cpu, tmp_mem;
@@ -374,7 +376,8 @@ static uint32_t intern_pair(ksh_context* c, uint64_t h, const char* k, size_t lk
 }
 
 static void node_pairs_release(ksh_context* c, uint32_t idx) {
-    for (uint32_t pid : c->node_pids[idx]) c->pair_refcnt[pid]--;
+    for (uint32_t pid : c->node_pids[idx])
+        if (--c->pair_refcnt[pid] == 0) c->live_pairs--;
     c->node_pids[idx].clear();
 }
 
@@ -387,8 +390,64 @@ static void node_pairs_set(ksh_context* c, uint32_t idx, const ks_node_obj& nd) 
         const uint32_t pid = intern_pair(c, hash2(k, lk, '\0', val, lv), k, lk, val, lv);
         if (std::find(v.begin(), v.end(), pid) != v.end()) continue; // a map has each key once; be safe
         v.push_back(pid);
-        c->pair_refcnt[pid]++;
+        if (c->pair_refcnt[pid]++ == 0) c->live_pairs++;
     }
+}
+
+// A long-running host sees label values, node names and pods come and go; what the interners and the key arena
+// keep for objects that no longer exist is reclaimed once it outweighs the live part.
+static constexpr size_t GC_SLACK = 1024;
+
+static void gc_pairs(ksh_context* c) {
+    if (c->pairs.size() <= 2 * c->live_pairs + GC_SLACK) return;
+    Interner fresh;
+    std::vector<uint32_t> refcnt;
+    std::vector<int32_t> bit;
+    std::vector<uint32_t> remap(c->pairs.size(), 0xFFFFFFFFu);
+    auto move_pair = [&](uint32_t pid) {
+        if (remap[pid] != 0xFFFFFFFFu) return remap[pid];
+        const Interner::Ent& e = c->pairs.ents[pid];
+        const char* k = c->pairs.str(pid);
+        const size_t lk = std::strlen(k);
+        const uint32_t id = fresh.intern_h(e.h, k, lk, '\0', k + lk + 1, e.len - lk - 1);
+        refcnt.push_back(c->pair_refcnt[pid]);
+        bit.push_back(c->pair_bit[pid]);
+        return remap[pid] = id;
+    };
+    for (uint32_t& pid : c->bit2pair) pid = move_pair(pid); // dictionary entries survive, stale ones included
+    for (auto& v : c->node_pids)
+        for (uint32_t& pid : v) pid = move_pair(pid);
+    c->pairs = std::move(fresh);
+    c->pair_refcnt.swap(refcnt);
+    c->pair_bit.swap(bit);
+}
+
+static void gc_names(ksh_context* c) {
+    if (c->names.size() <= 2 * (size_t)c->N + GC_SLACK) return;
+    Interner fresh;
+    std::vector<int32_t> id2idx;
+    for (uint32_t i = 0; i < c->N; i++) {
+        const uint32_t old = c->idx2nameid[i];
+        const char* name = c->names.str(old);
+        const uint32_t id = fresh.intern_h(c->names.ents[old].h, name, std::strlen(name), '\0', "", 0);
+        if (id == id2idx.size()) id2idx.push_back((int32_t)i); // rows are visited in index order: the first row of a name wins
+        c->idx2nameid[i] = id;
+    }
+    c->names = std::move(fresh);
+    c->nameid2idx.swap(id2idx);
+}
+
+static void gc_bound_keys(ksh_context* c) {
+    if (c->bkeys.size() <= 2 * c->live_key_bytes + 64 * GC_SLACK) return;
+    std::vector<char> fresh;
+    fresh.reserve(c->live_key_bytes);
+    for (size_t pos = 0; pos < c->bnode.size(); pos++) {
+        if (c->blen[pos] == 0) continue;
+        const uint64_t off = fresh.size();
+        fresh.insert(fresh.end(), c->bkeys.begin() + (ptrdiff_t)c->boff[pos], c->bkeys.begin() + (ptrdiff_t)(c->boff[pos] + c->blen[pos]));
+        c->boff[pos] = off;
+    }
+    c->bkeys.swap(fresh);
 }
 
 // Dictionary bits of pairs that no node carries any more are dead weight (a selector naming such a pair is
@@ -501,6 +560,7 @@ static void bound_push(ksh_context* c, const ks_pod_obj* pod, uint64_t h, size_t
     c->boff.push_back(c->bkeys.size());
     c->blen.push_back(tracked ? (uint32_t)(lns + 1 + lname) : 0);
     if (!tracked) return;
+    c->live_key_bytes += lns + 1 + lname;
     c->bkeys.insert(c->bkeys.end(), nz(pod->ns), nz(pod->ns) + lns);
     c->bkeys.push_back('/');
     c->bkeys.insert(c->bkeys.end(), nz(pod->name), nz(pod->name) + lname);
@@ -532,6 +592,7 @@ static void bound_push(ksh_context* c, const ks_pod_obj* pod, uint64_t h, size_t
 
 static void bound_erase(ksh_context* c, size_t pos) { // swap-remove
     const size_t last = c->bnode.size() - 1;
+    c->live_key_bytes -= c->blen[pos];
     if (c->blen[pos]) {
         const int64_t i = btab_slot_of_pos(c, pos);
         if (i >= 0) c->btab.slots[(size_t)i] = 1; // tombstone
@@ -554,8 +615,7 @@ static void bound_erase(ksh_context* c, size_t pos) { // swap-remove
     c->bhash.pop_back();
     c->boff.pop_back();
     c->blen.pop_back();
-    // erased keys stay in bkeys until the next bulk load; bound the garbage
-    if (c->bnode.empty()) c->bkeys.clear();
+    if (c->bnode.empty()) c->bkeys.clear(); // otherwise erased keys wait for gc_bound_keys
 }
 
 static void bound_clear(ksh_context* c) {
@@ -567,6 +627,7 @@ static void bound_clear(ksh_context* c) {
     c->blen.clear();
     c->bkeys.clear();
     c->btab.clear();
+    c->live_key_bytes = 0;
 }
 
 static int upload(ksh_context* c) {
@@ -736,6 +797,7 @@ int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) 
     c->nameid2idx.clear();
     c->idx2nameid.assign(n, 0);
     c->pairs.clear();
+    c->live_pairs = 0;
     c->pair_refcnt.clear();
     c->pair_bit.clear();
     c->bit2pair.clear();
@@ -787,6 +849,7 @@ int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* o
         node_pairs_release(c, idx);
     }
     node_pairs_set(c, idx, *node);
+    gc_pairs(c);
     c->dirty = true;
     if (out_idx) *out_idx = idx;
     return KS_OK;
@@ -817,6 +880,9 @@ int ksh_context_remove_node(ksh_context* c, const char* name) {
             p++;
         }
     }
+    gc_pairs(c);
+    gc_names(c);
+    gc_bound_keys(c);
     c->dirty = true;
     return KS_OK;
 }
@@ -837,6 +903,7 @@ int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
         if (slot >= 0) bound_erase(c, slot_low(c->btab.slots[(size_t)slot]) - 2); // update of a pod already known
     }
     bound_push(c, pod, h, lns, lname, node, cpu, mem);
+    gc_bound_keys(c);
     c->dirty = true;
     return KS_OK;
 }
@@ -849,6 +916,7 @@ int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
     const int64_t slot = btab_find_slot(c, h, pod, lns, lname);
     if (slot < 0) return KS_OK;
     bound_erase(c, slot_low(c->btab.slots[(size_t)slot]) - 2);
+    gc_bound_keys(c);
     c->dirty = true;
     return KS_OK;
 }

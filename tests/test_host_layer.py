@@ -439,3 +439,75 @@ def test_packer_dictionary_compaction_and_duplicate_names(ks):
         assert ctx.upsert_node(arena.nodes([{"name": "z", "allocatable": alloc}])) == 2
         ctx.remove_node("z")
         assert ctx.upsert_node(arena.nodes([{"name": "z", "allocatable": alloc}])) == 2  # a removed name comes back as new
+
+
+def test_packer_survives_long_churn(ks, orc):
+    """Label values, node names and pods that come and go for a long time (the garbage collection of the interned
+    strings runs many times on the way) leave exactly the state of the final objects."""
+    arena = ks.objects.ObjectArena()
+    alloc = {"cpu": "64", "memory": str(256 << 30)}
+    base = [{"name": f"keep-{i}", "labels": {"zone": f"z{i % 3}"}, "allocatable": alloc} for i in range(8)]
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(arena.nodes(base), len(base))
+        live = {}
+        for g in range(6000):
+            a = ks.objects.ObjectArena()  # short-lived objects, like the host's own
+            base[g % 8] = dict(base[g % 8], labels={"zone": f"z{g % 3}", "rev": f"r{g}"})
+            ctx.upsert_node(a.nodes([base[g % 8]]))
+            tmp = {"name": f"tmp-{g}", "labels": {"rev": f"t{g}"}, "allocatable": alloc}
+            assert ctx.upsert_node(a.nodes([tmp])) == 8
+            pod = {"name": f"job-{g}", "ns": "batch", "node_name": f"tmp-{g}" if g % 2 else f"keep-{g % 8}",
+                   "containers": [{"cpu": "100m", "memory": "1048576"}]}
+            ctx.pod_bound(a.pods([pod]))
+            ctx.remove_node(f"tmp-{g}")                    # takes the pods bound to it along
+            if g % 2 == 0:
+                live[pod["name"]] = pod
+            if g % 3 == 0 and live:
+                k = next(iter(live))
+                ctx.pod_deleted(a.pods([live.pop(k)]))
+            if g % 500 == 0:
+                ctx.pack_pods(a.pods([{"name": "s", "ns": "d", "selector": {"rev": f"r{g}"}}]), 1)
+        for g in range(20000):                             # key arena churn: long pod names bound and deleted
+            a = ks.objects.ObjectArena()
+            pod = {"name": f"burst-{g}-" + "x" * 40, "ns": "batch", "node_name": f"keep-{g % 8}", "containers": [{"cpu": "1m"}]}
+            ctx.pod_bound(a.pods([pod]))
+            if g % 1000:
+                ctx.pod_deleted(a.pods([pod]))
+            else:
+                live[pod["name"]] = pod
+        assert ctx.n_nodes == 8
+        pods_s = [{"name": "a", "ns": "d", "selector": {"rev": "r5999"}, "containers": [{"cpu": "1"}]},
+                  {"name": "b", "ns": "d", "selector": {"rev": "r5991"}},           # a label value of the past
+                  {"name": "c", "ns": "d", "selector": {"zone": "z0"}, "containers": [{"cpu": "63950m"}]},
+                  {"name": "d", "ns": "d"}]
+        pods = arena.pods(pods_s)
+        got = _packed_answer(orc, ctx, pods, len(pods_s))
+    fb = list(live.values())
+    oc = orc.Cluster(arena.nodes(base), len(base), arena.pods(fb), len(fb))
+    want = oc.run(pods, len(pods_s), want_codes=True)
+    for g_, w, name in zip(got, want, ("node_idx", "score", "feasible_cnt", "mask", "codes")):
+        assert np.array_equal(g_, w), name
+    assert got[2].tolist()[1] == 0 and got[2].tolist()[0] == 1
+
+
+def test_host_layer_under_sanitizers(tmp_path):
+    """csrc/host/ksh_host.cpp built alone (device calls stubbed) with ASan+UBSan: 300k random events against a model,
+    and the threaded bulk calls (pack_bench) with ThreadSanitizer."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "kube-scheduler-rs-reference_b200", "csrc", "host", "ksh_host.cpp")
+    stub = os.path.join(root, "tests", "native", "ksh_stub_device.cpp")
+    inc = "-I" + os.path.join(root, "include")
+    jobs = [("address,undefined", os.path.join(root, "tests", "native", "ksh_churn.cpp"), [], "churn ok"),
+            ("thread", os.path.join(root, "examples", "pack_bench.cpp"), ["2000", "20000", "20000"], "host_packer_objects_per_sec")]
+    for san, main_src, args, expect in jobs:
+        exe = str(tmp_path / ("t_" + san.split(",")[0]))
+        r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=" + san, inc, src, stub, main_src, "-pthread", "-o", exe],
+                           capture_output=True, text=True)
+        if r.returncode != 0 and "sanitize" in r.stderr:
+            pytest.skip("sanitizer runtime not available: " + r.stderr.splitlines()[0])
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, env=dict(os.environ, KSH_THREADS="4"))
+        assert r.returncode == 0 and expect in r.stdout, (r.stdout, r.stderr)
+        assert "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr

@@ -68,7 +68,8 @@ int ksh_context_upsert_node(ksh_context* ctx, const ks_node_obj* node, uint32_t*
 int ksh_context_remove_node(ksh_context* ctx, const char* name);
 int ksh_context_pod_bound(ksh_context* ctx, const ks_pod_obj* pod);
 int ksh_context_pod_deleted(ksh_context* ctx, const ks_pod_obj* pod);
-const char* ksh_context_node_name(const ksh_context* ctx, uint32_t node_idx); /* NULL if out of range */
+const char* ksh_context_node_name(const ksh_context* ctx, uint32_t node_idx); /* NULL if out of range; borrowed,
+                                                                                 valid until the next ksh_context_* mutation */
 uint32_t ksh_context_num_nodes(const ksh_context* ctx);
 uint32_t ksh_context_label_words(const ksh_context* ctx);
 uint64_t ksh_context_num_bound(const ksh_context* ctx);

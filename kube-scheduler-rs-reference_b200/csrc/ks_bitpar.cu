@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // label-pair columns: [bit][tile][32 B]
-// KS_BP_VARIANT=0 (A/B switch, read once): 16-byte skew per bit and both pods of a phase load the same half first
+// KS_BP_VARIANT (A/B switch, read once): 1 = default; 0 = previous kernel (16-byte skew per bit, both pods of a phase
+// load the same half first); 2 = experimental k_mask_bitpar2
 static int bp_variant() {
     static const int v = [] {
         const char* e = getenv("KS_BP_VARIANT");
@@ -556,6 +557,193 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ variant 2
+// EXPERIMENTAL (KS_BP_VARIANT=2; not the default, not yet run on a GPU): the same mask kernel with the per-pass
+// instruction count cut down.  What changes, guided by the SASS of k_mask_bitpar (profiles/r01_sass_evidence_v23.txt):
+//  * shared memory is addressed through 32-bit shared-window addresses derived once per thread (the compiler
+//    re-derives the cluster-mapped window base - S2R CgaCtaId + 3 ALU - and re-reads layout constants in every pass
+//    because it is register-starved at 64 registers x 1024 threads);
+//  * the label-pair columns a pod needs come as a precomputed list of <= 4 column offsets (k_pod_pair_list, once per
+//    pod) instead of a find-first-set loop over the selector words in every (pod, tile) pass (32 instructions per pair).
+// Layout, lane mapping, half-swap and results are those of k_mask_bitpar<W, true>.
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+constexpr uint32_t PL_END = 0xFFFFu;     // no further column
+constexpr uint32_t PL_GENERIC = 0xFFFEu; // more than 4 required pairs: walk the selector words instead
+
+// Per sorted pod: the label-pair columns its selector requires, as 4 x u16 = (bit index * pstride) / 16.
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_pod_pair_list(const unsigned long long* __restrict__ sel_s, uint32_t P, uint32_t pstride, uint2* __restrict__ plist_s) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P) return;
+    uint32_t e[4] = {PL_END, PL_END, PL_END, PL_END};
+    uint32_t n = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        unsigned long long bits = sel_s[(size_t)q * W + w];
+        while (bits) {
+            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (n < 4) e[n] = (bit * pstride) >> 4; // <= 511 * 1024 / 16 < 0xFFFE
+            n++;
+        }
+    }
+    if (n > 4) e[0] = PL_GENERIC;
+    plist_s[q] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+}
+
+template <int W>
+__global__ void __launch_bounds__(BP_THREADS, 1)
+    k_mask_bitpar2(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
+                   const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s,
+                   const uint2* __restrict__ plist_s, OutView ov, uint32_t ctas_per_cb) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, psub = lane >> 2, tsub = lane & 3;
+    const uint32_t nt = lay.nt;
+    const uint32_t n_groups = (P + 7) / 8;
+    const uint32_t cta_in_cb = blockIdx.x % ctas_per_cb;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    // shared-window addresses, derived once; hsw = byte offset of the half this lane loads first (0 or 16)
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t hsw = (psub & 1u) * 16u;
+    const uint32_t a_baseC = sbase + lay.off_baseC, a_baseM = sbase + lay.off_baseM;
+    const uint32_t a_membC = sbase + lay.off_membC, a_membM = sbase + lay.off_membM;
+    const uint32_t a_tabC = sbase + lay.off_tabC + hsw, a_tabM = sbase + lay.off_tabM + hsw;
+    const uint32_t a_pairs = sbase + lay.off_pairs + hsw;
+    const uint32_t pstride = lay.pstride;
+    const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
+
+    for (uint32_t cb = blockIdx.x / ctas_per_cb; cb < lay.ncb; cb += gridDim.x / ctas_per_cb) {
+        __syncthreads(); // every read of the previous blob is done
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar, lay.blob_bytes);
+            const uint8_t* src = blob + (size_t)cb * lay.blob_bytes;
+            for (uint32_t off = 0; off < lay.blob_bytes; off += 32768u)
+                tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
+        }
+
+        const uint32_t g_step = ctas_per_cb * (BP_THREADS / 32);
+        uint32_t g = cta_in_cb * (BP_THREADS / 32) + warp;
+        uint32_t q = g * 8 + psub;
+        bool act = g < n_groups && q < P;
+        uint2 r = act ? __ldg(rk_s + q) : make_uint2(0, 0); // prefetch while the blob is in flight
+        uint32_t pid = act ? __ldg(pid_s + q) : 0;
+        uint2 pl = act ? __ldg(plist_s + q) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        uint32_t pq = q;
+
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+
+        while (g < n_groups) { // warp-uniform
+            const uint2 cr = r, cpl = pl;
+            const uint32_t cpid = pid, cq = pq;
+            const bool cact = act;
+            g += g_step;
+            q = g * 8 + psub;
+            act = g < n_groups && q < P;
+            if (act) { // software prefetch of the next group's pod data
+                r = __ldg(rk_s + q);
+                pid = __ldg(pid_s + q);
+                pl = __ldg(plist_s + q);
+                pq = q;
+            }
+
+            uint32_t c = 0;
+            const uint32_t hc = (cr.x >> 6) * nt, hm = (cr.y >> 6) * nt;
+            const unsigned long long lowC = (1ull << (cr.x & 63)) - 1ull, lowM = (1ull << (cr.y & 63)) - 1ull;
+            for (uint32_t tb = 0; tb < nt; tb += 4) {
+                const uint32_t ct = tb + tsub;
+                if (cact && ct < nt) {
+                    // tile-local rank of each threshold = tile nodes at global positions < threshold
+                    const uint32_t ic = hc + ct, im = hm + ct;
+                    const uint32_t bc = lds16(a_baseC + ic * 2), bm = lds16(a_baseM + im * 2);
+                    const unsigned long long mc = lds64(a_membC + ic * 8), mm = lds64(a_membM + im * 8);
+                    const uint32_t rankC = bc + __popcll(mc & lowC);
+                    const uint32_t rankM = bm + __popcll(mm & lowM);
+                    const uint32_t tq = (ct >> 2) * (uint32_t)(BP_ROWS * 128) + (ct & 3u) * 32u; // table_row_offset(ct, 0)
+                    const uint32_t aC = a_tabC + tq + rankC * 128u, aM = a_tabM + tq + rankM * 128u;
+                    // first / second half of the 32-byte row: (address) and (address ^ 16); rows are 32-byte aligned
+                    const uint4 c0 = lds128(aC), c1 = lds128(aC ^ 16u);
+                    const uint4 m0 = lds128(aM), m1 = lds128(aM ^ 16u);
+                    uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
+                    uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
+                    const uint32_t a_col = a_pairs + ct * 32u;
+                    if ((cpl.x & 0xFFFFu) != PL_GENERIC) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { // AND the node column of every required pair (predicates.rs:48-53)
+                            const uint32_t e = ((k < 2 ? cpl.x : cpl.y) >> (16 * (k & 1))) & 0xFFFFu;
+                            if (e == PL_END) break;
+                            const uint32_t ap = a_col + (e << 4);
+                            const uint4 q0 = lds128(ap), q1 = lds128(ap ^ 16u);
+                            a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
+                            b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
+                        }
+                    } else { // rare: more than 4 required pairs
+#pragma unroll
+                        for (int w = 0; w < W; w++) {
+                            unsigned long long bits = __ldg(sel_s + (size_t)cq * W + w);
+                            while (bits) {
+                                const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+                                bits &= bits - 1;
+                                const uint32_t ap = a_col + bit * pstride;
+                                const uint4 q0 = lds128(ap), q1 = lds128(ap ^ 16u);
+                                a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
+                                b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
+                            }
+                        }
+                    }
+                    c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
+                         __popc(b.w);
+                    if (want_mask) {
+                        const uint32_t word = (cb * nt + ct) * 8;
+                        if (word < ov.mask_valid_words) {
+                            uint32_t* dst = ov.mask + (size_t)cpid * ov.mask_row_words + word; // 32-byte aligned
+                            // a = the half loaded first (upper 16 bytes for odd pods), b = the other one
+                            asm volatile("{ .reg .pred p; setp.ne.u32 p, %9, 0;\n\t"
+                                         "@p st.global.v8.b32 [%0], {%5,%6,%7,%8,%1,%2,%3,%4};\n\t"
+                                         "@!p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}; }" ::"l"(dst),
+                                         "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(hsw)
+                                         : "memory");
+                        }
+                    }
+                }
+            }
+            if (want_cnt) { // the 4 lanes of a pod are adjacent
+                c += __shfl_xor_sync(0xffffffffu, c, 1);
+                c += __shfl_xor_sync(0xffffffffu, c, 2);
+                if (cact && tsub == 0) {
+                    if (lay.ncb == 1) ov.cnt[cpid] = c; // single writer, no zero-init needed
+                    else if (c) atomicAdd(&ov.cnt[cpid], c);
+                }
+            }
+        }
+    }
+}
+
 // ---- argmax of the separable score = first feasible node in descending priority order ----
 // The priority-ordered index (blobP) is read through L1/L2.  Phase 1 (k_first_fit_head): one thread per pod
 // looks at the two best tiles (512 best nodes) - enough for almost every pod; the rest is appended to a list.
@@ -750,7 +938,7 @@ void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
                     ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
                     ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist,
-                    ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm};
+                    ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.plist_s};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -833,7 +1021,9 @@ template <int W>
 static cudaError_t set_smem_attr() {
     cudaError_t e = cudaFuncSetAttribute(k_mask_bitpar<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_mask_bitpar2<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -860,6 +1050,8 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = regrow(ix.pod_loc, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_s, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.pid_s, cap)) != cudaSuccess) return e;
+        if (bp_variant() == 2)
+            if ((e = regrow(ix.plist_s, cap)) != cudaSuccess) return e;
         ix.cap_pods = cap;
         ix.cap_sel = 0;
     }
@@ -957,7 +1149,15 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
         ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
         const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
-        {
+        if (bp_variant() == 2) { // experimental, see k_mask_bitpar2
+            k_pod_pair_list<W><<<(P + 255) / 256, 256, 0, L.stream>>>(ix.sel_s, P, ix.lay.pstride, ix.plist_s);
+            g_launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (before_mask) // time the mask kernel alone
+                if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
+            k_mask_bitpar2<W><<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(
+                ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, ix.plist_s, L.ov, ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
+        } else {
             auto kern = bp_variant() ? k_mask_bitpar<W, true> : k_mask_bitpar<W, false>;
             kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov,
                                                                     ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);

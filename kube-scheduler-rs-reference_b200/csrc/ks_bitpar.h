@@ -49,6 +49,7 @@ struct BitparIndex {
     uint2* rk_s = nullptr;         // pods in bucket order: thresholds, original pod index, selector words
     uint32_t* pid_s = nullptr;
     unsigned long long* sel_s = nullptr;
+    uint2* plist_s = nullptr;      // experimental variant 2 only: <= 4 label-pair column offsets per sorted pod
     uint32_t* hist = nullptr;      // [65536] bucket histogram -> exclusive scan
     uint32_t* rk_hist = nullptr;   // node sample sort scratch: [3][256] bucket counts, splitters, per-node bucket / slot, lists
     int64_t* rk_spl_v = nullptr;

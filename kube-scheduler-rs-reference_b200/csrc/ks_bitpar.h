@@ -6,8 +6,8 @@
 // prefix table indexed by the tile-local rank of the threshold, and the tile-local rank is
 //   base[bucket][tile] + popc(member[bucket][tile] & lowmask)
 // (bucket = 64 consecutive global positions).  Label selectors are ANDs of per-(key,value) node columns.
-// One thread produces 256 cells (8 mask words) with ~50 instructions; the kernel is bound by the HBM
-// write of the mask.  KS_SCORE_LEFTOVER is separable (node part - pod part), so argmax-score is the first
+// One thread produces 256 cells (8 mask words) with ~100 instructions; the design target is the HBM write of the
+// mask (measured: 53-60 % of it).  KS_SCORE_LEFTOVER is separable (node part - pod part), so argmax-score is the first
 // feasible node in a static priority order: a short early-exit scan per pod (k_first_fit).
 #pragma once
 #include "ks_internal.cuh"

@@ -511,3 +511,39 @@ def test_host_layer_under_sanitizers(tmp_path):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, env=dict(os.environ, KSH_THREADS="4"))
         assert r.returncode == 0 and expect in r.stdout, (r.stdout, r.stderr)
         assert "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr
+
+
+def test_object_level_host_layer_against_a_fake_device(tmp_path):
+    """The -m gpu host-layer tests (objects -> pack -> device calls -> results, reconcile, events, the reference's
+    sampling policy) run here against a scratch libksched.so = the real csrc/host/ksh_host.cpp + a fake device that
+    answers the ks_* calls with the oracle's packed flavour (tests/native/ksh_fake_device.cpp).  Checks the host layer's
+    side of every device call on machines without a GPU; the product library is not involved."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = "kube-scheduler-rs-reference_b200"
+    shadow = tmp_path / "shadow"
+    (shadow / pkg).mkdir(parents=True)
+    for f in os.listdir(os.path.join(root, pkg)):
+        if f.endswith(".py"):
+            shutil.copy(os.path.join(root, pkg, f), shadow / pkg / f)
+    shutil.copy(os.path.join(root, "ksched_pkg.py"), shadow / "ksched_pkg.py")
+    (shadow / "__graft_entry__.py").write_text("def build():\n    pass\n")
+    for d in ("include", "oracle", "tests"):
+        os.symlink(os.path.join(root, d), shadow / d)
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, capture_output=True)
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(root, "include"),
+                        "-I" + os.path.join(root, "oracle"), os.path.join(root, pkg, "csrc", "host", "ksh_host.cpp"),
+                        os.path.join(root, "tests", "native", "ksh_fake_device.cpp"), "-L" + os.path.join(root, "oracle"), "-loracle",
+                        "-Wl,-rpath," + os.path.join(root, "oracle"), "-pthread", "-o", str(shadow / pkg / "libksched.so")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        "tests/test_host_layer.py", "tests/test_gpu_parity.py::test_reference_sampling_policy_faithful_objects",
+                        "tests/test_gpu_parity.py::test_objects_faithful_oracle_vs_gpu", "tests/test_gpu_parity.py::test_gv1_objects_vs_faithful_oracle"],
+                       cwd=str(shadow), capture_output=True, text=True, env=env, timeout=900)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:] + r.stderr[-2000:]

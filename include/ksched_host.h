@@ -10,6 +10,7 @@
  *   ksh_check_node_validity   <- check_node_validity            src/predicates.rs:63-77
  *   ksh_select_nodes          <- select_node_for_pod, batched   src/main.rs:51-71 (argmax score instead of 5 random draws)
  *   ksh_select_node_for_pod   <- select_node_for_pod, seeded    src/main.rs:49-71 (the reference's own 5-draw policy)
+ *   ksh_reconcile_batch       <- reconcile over a drained queue  src/main.rs:73-120 (micro-batch with capacity commit)
  *   ksh_reconcile             <- reconcile                      src/main.rs:73-120 (builds the Binding, does not POST it)
  *   KSH_RECONCILE_*           <- ReconcileError                 src/error.rs:5-15
  * The layer packs objects into the SoA/bitmask form of ksched.h and calls the CUDA core; it never evaluates
@@ -103,6 +104,18 @@ int ksh_select_node_for_pod(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n
  * binding_json may be NULL; otherwise receives a NUL-terminated JSON document (truncated to cap). */
 int ksh_reconcile(ksh_context* ctx, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* binding_json,
                   size_t cap);
+
+/* reconcile() for a drained controller queue, pods in arrival order.  Pods already bound are skipped (KSH_RECONCILE_OK,
+ * node -1; src/main.rs:74-76); pods without namespace/name get KSH_RECONCILE_BINDING_OBJECT_FAILED (reference: unwrap
+ * panic, :80) and are not scheduled; the rest are packed once and bound by the micro-batch loop of ks_stream_bind (ksched.h):
+ * every round selects on the current capacity, claims are accepted per node in arrival order while they still fit, losers
+ * are re-selected against what is left — capacity is never oversubscribed, a pod ends with KSH_RECONCILE_NO_NODE_FOUND
+ * only if no node fits it at its turn.  Accepted binds are committed to the snapshot and to the context's bound-pod list.
+ * out_status[n], out_node_idx[n] (-1 = none).  Binding bodies (see ksh_reconcile) are written back to back, NUL-terminated,
+ * into json (cap bytes); out_json_off[i] = offset of pod i's body or -1 (not bound, or the buffer was full).  json /
+ * out_json_off / out_rounds may be NULL. */
+int ksh_reconcile_batch(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int policy, int32_t* out_status,
+                        int32_t* out_node_idx, char* json, size_t cap, int64_t* out_json_off, uint32_t* out_rounds);
 
 #ifdef __cplusplus
 }

@@ -1038,6 +1038,19 @@ int ksh_select_node_for_pod(ksh_context* c, const ks_pod_obj* pods, uint64_t n, 
                               out_draw_code);
 }
 
+// corev1::Binding{metadata, target: ObjectReference{name}}  (src/main.rs:83-91), the body of
+// POST /api/v1/namespaces/{ns}/pods/{name}/binding
+static std::string binding_body(const ksh_context* c, const ks_pod_obj* pod, uint32_t node_idx) {
+    std::string s = "{\"apiVersion\":\"v1\",\"kind\":\"Binding\",\"metadata\":{\"name\":\"";
+    json_escape(s, pod->name);
+    s += "\",\"namespace\":\"";
+    json_escape(s, pod->ns);
+    s += "\"},\"target\":{\"name\":\"";
+    json_escape(s, ksh_context_node_name(c, node_idx));
+    s += "\"}}";
+    return s;
+}
+
 int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* json, size_t cap) {
     if (!c || !pod || !node_idx) return fail(KS_ERR_INVALID, "NULL argument");
     *node_idx = -1;
@@ -1063,17 +1076,59 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
         bound_push(c, pod, h, lns, lname, idx, cpu, mem);
     }
     *node_idx = idx;
-    if (json && cap) { // corev1::Binding{metadata, target: ObjectReference{name}}  (src/main.rs:83-91)
-        std::string s = "{\"apiVersion\":\"v1\",\"kind\":\"Binding\",\"metadata\":{\"name\":\"";
-        json_escape(s, pod->name);
-        s += "\",\"namespace\":\"";
-        json_escape(s, pod->ns);
-        s += "\"},\"target\":{\"name\":\"";
-        json_escape(s, ksh_context_node_name(c, (uint32_t)idx));
-        s += "\"}}";
-        std::snprintf(json, cap, "%s", s.c_str());
-    }
+    if (json && cap) std::snprintf(json, cap, "%s", binding_body(c, pod, (uint32_t)idx).c_str());
     return KSH_RECONCILE_OK;
+}
+
+// reconcile() for a drained queue: one pack, one micro-batch loop on the device (select -> claims resolved in array order ->
+// losers re-selected against what is left), then the host-side commit of every bind (what the next LIST would show)
+int ksh_reconcile_batch(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int policy, int32_t* out_status, int32_t* out_node_idx,
+                        char* json, size_t cap, int64_t* out_json_off, uint32_t* out_rounds) {
+    if (!c || (n && (!pods || !out_status || !out_node_idx))) return fail(KS_ERR_INVALID, "NULL argument");
+    if (out_rounds) *out_rounds = 0;
+    std::vector<uint64_t> todo;
+    std::vector<ks_pod_obj> sub; // shallow copies: the pods that actually go to the device, in arrival order
+    for (uint64_t i = 0; i < n; i++) {
+        out_node_idx[i] = -1;
+        if (out_json_off) out_json_off[i] = -1;
+        if (ksh_is_pod_bound(&pods[i])) {
+            out_status[i] = KSH_RECONCILE_OK; // src/main.rs:74-76
+        } else if (!pods[i].ns || !pods[i].name) {
+            out_status[i] = KSH_RECONCILE_BINDING_OBJECT_FAILED; // reference: unwrap panic, src/main.rs:80
+        } else {
+            out_status[i] = KSH_RECONCILE_NO_NODE_FOUND; // until bound below (src/main.rs:116-118)
+            todo.push_back(i);
+            sub.push_back(pods[i]);
+        }
+    }
+    if (todo.empty()) return KS_OK;
+    std::vector<int64_t> rc_, rm_;
+    std::vector<uint64_t> sel;
+    int rc = pack_and_upload(c, sub.data(), sub.size(), rc_, rm_, sel);
+    if (rc) return rc;
+    std::vector<int32_t> idx(sub.size(), -1);
+    ks_pods kp{sub.size(), rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
+    rc = ks_stream_bind(c->snap, &kp, policy, idx.data(), nullptr, out_rounds); // commits capacity on the device
+    if (rc) return rc;
+    size_t used = 0;
+    for (size_t k = 0; k < todo.size(); k++) {
+        if (idx[k] < 0) continue;
+        const uint64_t i = todo[k];
+        size_t lns, lname;
+        const uint64_t h = pod_key_hash(&pods[i], &lns, &lname);
+        bound_push(c, &pods[i], h, lns, lname, idx[k], rc_[k], rm_[k]);
+        out_status[i] = KSH_RECONCILE_OK;
+        out_node_idx[i] = idx[k];
+        if (json && out_json_off) {
+            const std::string body = binding_body(c, &pods[i], (uint32_t)idx[k]);
+            if (used + body.size() + 1 <= cap) { // bodies back to back, each NUL-terminated; -1 = did not fit
+                std::memcpy(json + used, body.c_str(), body.size() + 1);
+                out_json_off[i] = (int64_t)used;
+                used += body.size() + 1;
+            }
+        }
+    }
+    return KS_OK;
 }
 
 } // extern "C"

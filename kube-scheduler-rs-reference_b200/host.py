@@ -32,6 +32,7 @@ for _name, _res, _args in [
     ("ksh_check_node_validity", C.c_int, [_vp, _vp, C.c_uint32]),
     ("ksh_select_nodes", C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp]),
     ("ksh_select_node_for_pod", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
+    ("ksh_reconcile_batch", C.c_int, [_vp, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp, C.POINTER(C.c_uint32)]),
     ("ksh_reconcile", C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
 ]:
     _f = getattr(lib, _name)
@@ -195,3 +196,18 @@ class Context:
         if rc < 0:
             raise KsError(rc, "ksh_reconcile")
         return rc, node.value, buf.value.decode()
+
+    def reconcile_batch(self, pods, n, policy=capi.KS_SCORE_LEFTOVER, json_cap=None):
+        """reconcile() over a drained queue: (status[n], node_idx[n], bodies[n] (str | None), rounds)."""
+        status = np.empty(n, np.int32)
+        node = np.empty(n, np.int32)
+        off = np.empty(n, np.int64)
+        cap = int(json_cap if json_cap is not None else 512 * max(n, 1))
+        buf = C.create_string_buffer(cap)
+        rounds = C.c_uint32()
+        rc = lib.ksh_reconcile_batch(self._h, C.addressof(pods), n, int(policy), status.ctypes.data, node.ctypes.data,
+                                     C.addressof(buf), cap, off.ctypes.data, C.byref(rounds))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ksh_reconcile_batch")
+        bodies = [None if o < 0 else C.string_at(C.addressof(buf) + int(o)).decode() for o in off]
+        return status, node, bodies, rounds.value

@@ -51,8 +51,9 @@ class ObjectArena:
         arr = (ks_pod_obj * max(len(specs), 1))()
         for i, s in enumerate(specs):
             o = arr[i]
-            o.ns = _b(s.get("ns", "default"))
-            o.name = _b(s.get("name", f"pod{i}"))
+            ns, name = s.get("ns", "default"), s.get("name", f"pod{i}")
+            o.ns = _b(ns) if ns is not None else None      # None = metadata.namespace / name absent
+            o.name = _b(name) if name is not None else None
             o.has_spec = 1 if s.get("spec", True) else 0
             nn = s.get("node_name")
             o.node_name = _b(nn) if nn is not None else None

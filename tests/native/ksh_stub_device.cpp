@@ -12,5 +12,6 @@ int ks_snapshot_set_bound(ks_snapshot*, uint64_t, const int32_t*, const int64_t*
 int ks_snapshot_apply_bind(ks_snapshot*, int32_t, int64_t, int64_t) { return KS_ERR_NO_DEVICE; }
 int ks_check_cell(ks_snapshot*, int64_t, int64_t, const uint64_t*, uint32_t) { return KS_ERR_NO_DEVICE; }
 int ks_select(ks_snapshot*, const ks_pods*, int, uint32_t, ks_bindings*, void*) { return KS_ERR_NO_DEVICE; }
+int ks_stream_bind(ks_snapshot*, const ks_pods*, int, int32_t*, int64_t*, uint32_t*) { return KS_ERR_NO_DEVICE; }
 int ks_select_sampling(ks_snapshot*, const ks_pods*, uint32_t, uint64_t, uint64_t, int32_t*, uint32_t*, int32_t*, uint8_t*) { return KS_ERR_NO_DEVICE; }
 }

@@ -260,6 +260,67 @@ def test_reconcile_mirror(ks, orc):
 
 
 @pytest.mark.gpu
+def test_reconcile_batch_equals_the_streaming_oracle(ks, orc):
+    """A drained queue through ksh_reconcile_batch: bound pods skipped, nameless pods refused, the rest bound by the
+    micro-batch loop exactly as the oracle's restatement binds the packed batch; every bind is committed (device
+    capacity, bound-pod list, Binding body) and visible to what follows."""
+    cl = ks.synth.make(400, 25, seed=321, bound_per_node=2)        # few nodes: pods compete, several rounds
+    nodes_s, bound_s, pods_s = ks.objects.cluster_specs(cl)
+    pods_s = [dict(p) for p in pods_s]
+    pods_s[7] = dict(pods_s[7], node_name="node-3")                 # already bound -> skipped
+    pods_s[11] = {"name": None, "ns": None, "containers": [{"cpu": "1m"}]}  # no namespace/name -> refused
+    arena = ks.objects.ObjectArena()
+    nodes, bound, pods = arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+    todo = [i for i in range(cl.P) if i not in (7, 11)]
+    # expectation: the packer's arrays (packing-only context) through the oracle's streaming restatement
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as pk:
+        pk.set_nodes(nodes, cl.N)
+        pk.set_cluster_pods(bound, cl.B)
+        rc, rm, sel = pk.pack_pods(arena.pods([pods_s[i] for i in todo]), len(todo))
+        ac, am, lab, bn, bc, bm = pk.export_packed()
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    oidx, _, orounds = orc.stream_bind_packed(fc, fm, ac, am, lab, rc, rm, sel)
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(nodes, cl.N)
+        ctx.set_cluster_pods(bound, cl.B)
+        status, node, bodies, rounds = ctx.reconcile_batch(pods, cl.P)
+        assert rounds == orounds and rounds > 1
+        assert (status[7], node[7], bodies[7]) == (0, -1, None)
+        assert (status[11], node[11]) == (ks.host.KSH_RECONCILE_BINDING_OBJECT_FAILED, -1)
+        assert np.array_equal(node[todo], oidx)
+        assert np.array_equal(status[todo], np.where(oidx >= 0, 0, ks.host.KSH_RECONCILE_NO_NODE_FOUND))
+        assert (oidx >= 0).any() and (oidx < 0).any()
+        for i in todo[:50]:
+            if node[i] >= 0:
+                assert json.loads(bodies[i]) == {"apiVersion": "v1", "kind": "Binding",
+                                                 "metadata": {"name": pods_s[i]["name"], "namespace": pods_s[i].get("ns", "default")},
+                                                 "target": {"name": nodes_s[node[i]]["name"]}}
+            else:
+                assert bodies[i] is None
+        # the binds are in the context's bound-pod list and in the device capacity
+        xn, xc, xm = ctx.export_packed()[3:]
+        assert len(xn) == cl.B + int((oidx >= 0).sum())
+        f2c, f2m = orc.free_reduce(ac, am, xn, xc, xm)
+        assert np.array_equal(f2c, fc) and np.array_equal(f2m, fm)  # fc/fm were advanced in place by the oracle
+        later = arena.pods([{"name": "later", "ns": "d", "containers": [{"cpu": "1m", "memory": "1"}]}])
+        feas = (f2c >= 1) & (f2m >= 1)
+        want = int(np.argmax(np.where(feas, f2c * (1 << 22) + f2m, np.iinfo(np.int64).min))) if feas.any() else -1
+        assert ctx.select_nodes(later, 1)[0][0] == want
+        # a second drain of the same queue: nothing new fits where it did not fit, bound ones would be re-bound ->
+        # only check that it runs on the committed state and never oversubscribes
+        status2, node2, _, _ = ctx.reconcile_batch(pods, cl.P)
+        xn2, xc2, xm2 = ctx.export_packed()[3:]
+        f3c, f3m = orc.free_reduce(ac, am, xn2, xc2, xm2)
+        newly = np.nonzero(node2 >= 0)[0]
+        assert ((f3c >= 0) | (fc < 0)).all() and ((f3m >= 0) | (fm < 0)).all(), "capacity oversubscribed by the second drain"
+        assert len(xn2) == len(xn) + len(newly)
+        # a tiny Binding buffer: binds still happen, bodies that do not fit are reported as missing
+        tiny = arena.pods([{"name": "t1", "ns": "d"}, {"name": "t2", "ns": "d"}])
+        st, nd, bd, _ = ctx.reconcile_batch(tiny, 2, json_cap=120)
+        assert (st == 0).all() and bd[0] is not None and bd[1] is None
+
+
+@pytest.mark.gpu
 def test_incremental_node_and_pod_events_equal_a_rebuilt_context(ks, orc):
     """upsert/remove node and pod bound/deleted events must leave the context in the state a full rebuild from the
     final objects gives (compared through the faithful oracle on that final cluster)."""

@@ -3,7 +3,7 @@
  * INTEGRATION.md.  The cluster is the hand-derived C1 vector of SURVEY.md §8c (5 nodes, 10 pods).
  *
  *   gcc -std=c99 -Iinclude examples/reconcile_loop.c -Lkube-scheduler-rs-reference_b200 -lksched \
- *       -Wl,-rpath,$PWD/kube-scheduler-rs-reference_b200 -o /tmp/reconcile_loop && /tmp/reconcile_loop [--sampling SEED]
+ *       -Wl,-rpath,$PWD/kube-scheduler-rs-reference_b200 -o /tmp/reconcile_loop && /tmp/reconcile_loop [--sampling SEED | --batch]
  *
  * Without a B200 the library refuses to compute (no CPU fallback): the program prints the error and exits 3.
  */
@@ -25,6 +25,7 @@ static int die(const char* what, int rc) {
 
 int main(int argc, char** argv) {
     const int sampling = argc > 1 && strcmp(argv[1], "--sampling") == 0;
+    const int batch = argc > 1 && strcmp(argv[1], "--batch") == 0;
     const uint64_t seed = argc > 2 ? strtoull(argv[2], NULL, 0) : 1;
 
     /* node store: what reflector::Store<Node>::state() holds (main.rs:56) */
@@ -80,6 +81,19 @@ int main(int argc, char** argv) {
     if ((rc = ksh_context_set_nodes(ctx, nodes, N_NODES))) return die("ksh_context_set_nodes", rc);
     if ((rc = ksh_context_set_cluster_pods(ctx, bound, N_BOUND))) return die("ksh_context_set_cluster_pods", rc);
 
+    if (batch) { /* the whole queue in one call: one pack, the device's micro-batch loop, one Binding body per bound pod */
+        int32_t status[N_PODS], node[N_PODS];
+        int64_t off[N_PODS];
+        static char bodies[N_PODS * 512];
+        uint32_t rounds = 0;
+        rc = ksh_reconcile_batch(ctx, pods, N_PODS, KS_SCORE_LEFTOVER, status, node, bodies, sizeof(bodies), off, &rounds);
+        if (rc) return die("ksh_reconcile_batch", rc);
+        for (int i = 0; i < N_PODS; i++)
+            printf("%s: status %d %s\n", pods[i].name, status[i], off[i] >= 0 ? bodies + off[i] : "(no binding)");
+        printf("%u round(s)\n", rounds);
+        ksh_context_destroy(ctx);
+        return 0;
+    }
     for (int i = 0; i < N_PODS; i++) {
         int32_t node = -1;
         char body[512] = "";

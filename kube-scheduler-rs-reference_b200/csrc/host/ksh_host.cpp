@@ -10,6 +10,7 @@
 #include <string>
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -256,6 +257,8 @@ struct ksh_context {
     std::vector<uint64_t> tmp_hash;
     std::vector<uint32_t> tmp_len;
     bool dirty = true; // device snapshot must be re-uploaded
+    // one lock per context: every ksh_* entry that takes a context holds it for the whole call (entries call each other)
+    mutable std::recursive_mutex mu;
 };
 
 static uint32_t words_for_bits(uint32_t real_bits) {
@@ -746,13 +749,26 @@ void ksh_context_destroy(ksh_context* c) {
     delete c;
 }
 
-uint32_t ksh_context_num_nodes(const ksh_context* c) { return c ? c->N : 0; }
-uint32_t ksh_context_label_words(const ksh_context* c) { return c ? c->W : 0; }
-uint64_t ksh_context_num_bound(const ksh_context* c) { return c ? c->bnode.size() : 0; }
+uint32_t ksh_context_num_nodes(const ksh_context* c) {
+    if (!c) return 0;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    return c->N;
+}
+uint32_t ksh_context_label_words(const ksh_context* c) {
+    if (!c) return 0;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    return c->W;
+}
+uint64_t ksh_context_num_bound(const ksh_context* c) {
+    if (!c) return 0;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    return c->bnode.size();
+}
 
 int ksh_context_export_packed(const ksh_context* c, int64_t* alloc_cpu, int64_t* alloc_mem, uint64_t* labels,
                               int32_t* bound_node, int64_t* bound_cpu, int64_t* bound_mem) {
     if (!c) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (c->N && (!alloc_cpu || !alloc_mem || !labels)) return fail(KS_ERR_INVALID, "NULL node array");
     if (!c->bnode.empty() && (!bound_node || !bound_cpu || !bound_mem)) return fail(KS_ERR_INVALID, "NULL bound array");
     if (c->N) {
@@ -769,12 +785,15 @@ int ksh_context_export_packed(const ksh_context* c, int64_t* alloc_cpu, int64_t*
 }
 
 ks_snapshot* ksh_context_snapshot(ksh_context* c) {
-    if (!c || upload(c)) return nullptr;
+    if (!c) return nullptr;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (upload(c)) return nullptr;
     return c->snap;
 }
 
 int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) {
     if (!c || (n && !nodes)) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     // validate first (quantities parsed by all host threads), then replace
     std::vector<int64_t> ac(n), am(n);
     std::vector<RangeError> errs(host_threads());
@@ -828,6 +847,7 @@ int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) 
 
 int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* out_idx) {
     if (!c || !node) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     int64_t ac, am;
     std::string err;
     const int rc = parse_node_allocatable(*node, &ac, &am, &err);
@@ -857,6 +877,7 @@ int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* o
 
 int ksh_context_remove_node(ksh_context* c, const char* name) {
     if (!c || !name) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     const int32_t found = node_index_of(c, name);
     if (found < 0) return KS_OK;
     const uint32_t idx = (uint32_t)found;
@@ -889,6 +910,7 @@ int ksh_context_remove_node(ksh_context* c, const char* name) {
 
 int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!ksh_is_pod_bound(pod)) return KS_OK;
     const int32_t node = node_index_of(c, pod->node_name);
     if (node < 0) return KS_OK;
@@ -910,6 +932,7 @@ int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
 
 int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     size_t lns, lname;
     const uint64_t h = pod_key_hash(pod, &lns, &lname);
     if (lns + lname == 0) return KS_OK;
@@ -922,11 +945,14 @@ int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
 }
 
 const char* ksh_context_node_name(const ksh_context* c, uint32_t idx) {
-    return (c && idx < c->N) ? c->names.str(c->idx2nameid[idx]) : nullptr;
+    if (!c) return nullptr;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    return idx < c->N ? c->names.str(c->idx2nameid[idx]) : nullptr;
 }
 
 int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n > 0xFFFFFFF0ull) return fail(KS_ERR_RANGE, "too many pods");
     // validate first, then replace.  Per pod (all host threads): spec.nodeName -> node index (the field selector of
     // predicates.rs:22-25), request totals (predicates.rs:37), key hash.
@@ -981,6 +1007,7 @@ int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_
 int ksh_pack_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* req_cpu, int64_t* req_mem,
                   uint64_t* sel, uint32_t stride) {
     if (!c || (n && (!pods || !req_cpu || !req_mem || !sel))) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     int rc = grow_dictionary(c, pods, n);
     if (rc) return rc;
     if (stride < c->W) return fail(KS_ERR_INVALID, "sel_stride_words smaller than the dictionary's word count");
@@ -1003,6 +1030,7 @@ static int pack_and_upload(ksh_context* c, const ks_pod_obj* pods, uint64_t n, s
 
 int ksh_check_node_validity(ksh_context* c, const ks_pod_obj* pod, uint32_t node_idx) {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (node_idx >= c->N) return fail(KS_ERR_INVALID, "node index out of range");
     std::vector<int64_t> rc_, rm_;
     std::vector<uint64_t> sel;
@@ -1014,6 +1042,7 @@ int ksh_check_node_validity(ksh_context* c, const ks_pod_obj* pod, uint32_t node
 int ksh_select_nodes(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int policy, int32_t* out_node_idx,
                      int64_t* out_score, uint32_t* out_cnt) {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n == 0) return KS_OK;
     std::vector<int64_t> rc_, rm_;
     std::vector<uint64_t> sel;
@@ -1028,6 +1057,7 @@ int ksh_select_node_for_pod(ksh_context* c, const ks_pod_obj* pods, uint64_t n, 
                             uint64_t first_pod_index, int32_t* out_node_idx, uint32_t* out_attempts,
                             int32_t* out_draw_node, uint8_t* out_draw_code) {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n == 0) return KS_OK;
     std::vector<int64_t> rc_, rm_;
     std::vector<uint64_t> sel;
@@ -1053,6 +1083,7 @@ static std::string binding_body(const ksh_context* c, const ks_pod_obj* pod, uin
 
 int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* json, size_t cap) {
     if (!c || !pod || !node_idx) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     *node_idx = -1;
     if (json && cap) json[0] = '\0';
     if (ksh_is_pod_bound(pod)) return KSH_RECONCILE_OK; // src/main.rs:74-76
@@ -1085,6 +1116,7 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
 int ksh_reconcile_batch(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int policy, int32_t* out_status, int32_t* out_node_idx,
                         char* json, size_t cap, int64_t* out_json_off, uint32_t* out_rounds) {
     if (!c || (n && (!pods || !out_status || !out_node_idx))) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (out_rounds) *out_rounds = 0;
     std::vector<uint64_t> todo;
     std::vector<ks_pod_obj> sub; // shallow copies: the pods that actually go to the device, in arrival order

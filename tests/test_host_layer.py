@@ -553,7 +553,7 @@ def test_packer_survives_long_churn(ks, orc):
 
 def test_host_layer_under_sanitizers(tmp_path):
     """csrc/host/ksh_host.cpp built alone (device calls stubbed) with ASan+UBSan: 300k random events against a model,
-    and the threaded bulk calls (pack_bench) with ThreadSanitizer."""
+    the threaded bulk calls (pack_bench) and four threads sharing one context with ThreadSanitizer."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -561,9 +561,10 @@ def test_host_layer_under_sanitizers(tmp_path):
     stub = os.path.join(root, "tests", "native", "ksh_stub_device.cpp")
     inc = "-I" + os.path.join(root, "include")
     jobs = [("address,undefined", os.path.join(root, "tests", "native", "ksh_churn.cpp"), [], "churn ok"),
-            ("thread", os.path.join(root, "examples", "pack_bench.cpp"), ["2000", "20000", "20000"], "host_packer_objects_per_sec")]
+            ("thread", os.path.join(root, "examples", "pack_bench.cpp"), ["2000", "20000", "20000"], "host_packer_objects_per_sec"),
+            ("thread", os.path.join(root, "tests", "native", "ksh_concurrent.cpp"), [], "concurrent ok")]
     for san, main_src, args, expect in jobs:
-        exe = str(tmp_path / ("t_" + san.split(",")[0]))
+        exe = str(tmp_path / ("t_" + san.split(",")[0] + "_" + os.path.basename(main_src).split(".")[0]))
         r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=" + san, inc, src, stub, main_src, "-pthread", "-o", exe],
                            capture_output=True, text=True)
         if r.returncode != 0 and "sanitize" in r.stderr:

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 SHAPES = {"c2": (10_000, 100_000, 100_000), "c3": (50_000, 1_000_000, 500_000)}  # nodes, pods, bound pods
 
 
-def native(workload):
+def native(workload, device=-1):
     libdir = os.path.join(ROOT, "kube-scheduler-rs-reference_b200")
     build = os.path.join(libdir, "csrc", "build")
     os.makedirs(build, exist_ok=True)
@@ -23,7 +23,7 @@ def native(workload):
     subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "pack_bench.cpp"),
                     "-L" + libdir, "-lksched", "-Wl,-rpath," + libdir, "-pthread", "-o", exe], check=True)
     n, p, b = SHAPES[workload]
-    out = subprocess.run([exe, str(n), str(p), str(b)], check=True, capture_output=True, text=True).stdout
+    out = subprocess.run([exe, str(n), str(p), str(b), str(device)], check=True, capture_output=True, text=True).stdout
     return json.loads(out)
 
 
@@ -50,8 +50,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2", choices=list(SHAPES))
     ap.add_argument("--python-objects", action="store_true")
+    ap.add_argument("--device", type=int, default=-1, help="B200 ordinal: also time the object-level ksh_select_nodes / ksh_reconcile_batch")
     args = ap.parse_args()
-    line = native(args.workload)
+    line = native(args.workload, args.device)
     line["workload"] = args.workload
     if args.python_objects:
         line["python_objects"] = python_objects(args.workload)

@@ -1,7 +1,9 @@
 // pack_bench.cpp — host packer throughput on natively built objects: Pod/Node OBJECTS with
 // quantity strings and label maps -> the SoA int64 / label-bitmask arrays the device consumes, through a
 // packing-only context (KSH_DEVICE_NONE).  No GPU needed.  Shapes follow BASELINE.json configs[1]/[2]:
-//   pack_bench [nodes=10000] [pods=100000] [bound=100000]
+//   pack_bench [nodes=10000] [pods=100000] [bound=100000] [device=-1]
+// With a device ordinal (a B200) it also times the object-level calls end to end: ksh_select_nodes (objects in, bindings out:
+// pack + upload + kernels + copy back) and ksh_reconcile_batch on the first 10000 pods (micro-batch loop + commits + Binding bodies).
 // Prints one JSON line.  KSH_THREADS sets the host thread count (default: all cores, at most 32).
 #include <chrono>
 #include <cstdio>
@@ -22,6 +24,7 @@ static uint64_t splitmix(uint64_t& s) {
 int main(int argc, char** argv) {
     const uint32_t N = argc > 1 ? (uint32_t)atoi(argv[1]) : 10000;
     const uint64_t P = argc > 2 ? (uint64_t)atoll(argv[2]) : 100000, B = argc > 3 ? (uint64_t)atoll(argv[3]) : 100000;
+    const int device = argc > 4 ? atoi(argv[4]) : KSH_DEVICE_NONE;
     uint64_t rng = 0xB2000002;
     std::vector<std::string> strs;
     strs.reserve((P + B) * 10 + (size_t)N * 24);
@@ -64,7 +67,10 @@ int main(int argc, char** argv) {
     for (uint64_t p = 0; p < P; p++) make_pod(pods[p], "pod-", p, nullptr, true);
 
     ksh_context* ctx = nullptr;
-    if (ksh_context_create(KSH_DEVICE_NONE, &ctx)) return 1;
+    if (ksh_context_create(device, &ctx)) {
+        fprintf(stderr, "ksh_context_create failed: %s\n", ks_last_error());
+        return 1;
+    }
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
@@ -89,13 +95,45 @@ int main(int argc, char** argv) {
         const double v[4] = {ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4)};
         for (int k = 0; k < 4; k++) best[k] = v[k] < best[k] ? v[k] : best[k];
     }
+    double select_ms = -1, batch_ms = -1;
+    unsigned batch_rounds = 0;
+    uint64_t batch_bound = 0;
+    if (device != KSH_DEVICE_NONE) {
+        if (ksh_context_set_nodes(ctx, nodes.data(), N) || ksh_context_set_cluster_pods(ctx, bound.data(), B)) return 7;
+        std::vector<int32_t> idx(P);
+        std::vector<int64_t> score(P);
+        std::vector<uint32_t> cnt(P);
+        for (int it = 0; it < 4; it++) { // first call: uploads, index build, module load
+            auto t0 = now();
+            if (ksh_select_nodes(ctx, pods.data(), P, KS_SCORE_LEFTOVER, idx.data(), score.data(), cnt.data())) {
+                fprintf(stderr, "ksh_select_nodes failed: %s\n", ks_last_error());
+                return 8;
+            }
+            const double v = ms(t0, now());
+            if (it > 0 && (select_ms < 0 || v < select_ms)) select_ms = v;
+        }
+        const uint64_t Q = P < 10000 ? P : 10000;
+        std::vector<int32_t> st(Q), nd(Q);
+        std::vector<int64_t> off(Q);
+        std::vector<char> bodies(Q * 256);
+        auto t0 = now();
+        if (ksh_reconcile_batch(ctx, pods.data(), Q, KS_SCORE_LEFTOVER, st.data(), nd.data(), bodies.data(), bodies.size(), off.data(), &batch_rounds)) {
+            fprintf(stderr, "ksh_reconcile_batch failed: %s\n", ks_last_error());
+            return 9;
+        }
+        batch_ms = ms(t0, now());
+        for (uint64_t i = 0; i < Q; i++) batch_bound += nd[i] >= 0;
+    }
     const char* th = getenv("KSH_THREADS");
     printf("{\"metric\": \"host_packer_objects_per_sec\", \"objects\": \"native\", \"threads\": \"%s\", \"hardware_concurrency\": %u, "
            "\"nodes\": %u, \"nodes_per_s\": %.0f, \"bound_pods\": %llu, \"bound_pods_per_s\": %.0f, \"pods\": %llu, "
            "\"pods_per_s\": %.0f, \"label_words\": %d, \"ms\": {\"set_nodes\": %.3f, \"set_cluster_pods\": %.3f, "
-           "\"pack_pods\": %.3f, \"three_events\": %.4f}}\n",
+           "\"pack_pods\": %.3f, \"three_events\": %.4f}, \"device\": %d, \"select_nodes_objects_ms\": %.3f, "
+           "\"select_nodes_objects_cells_per_s\": %.4g, \"reconcile_batch_10k_ms\": %.3f, \"reconcile_batch_rounds\": %u, "
+           "\"reconcile_batch_bound\": %llu}\n",
            th ? th : "default", std::thread::hardware_concurrency(), N, N / best[0] * 1e3, (unsigned long long)B, B / best[1] * 1e3,
-           (unsigned long long)P, P / best[2] * 1e3, W, best[0], best[1], best[2], best[3]);
+           (unsigned long long)P, P / best[2] * 1e3, W, best[0], best[1], best[2], best[3], device, select_ms,
+           select_ms > 0 ? (double)P * N / (select_ms * 1e-3) : 0.0, batch_ms, batch_rounds, (unsigned long long)batch_bound);
     ksh_context_destroy(ctx);
     return 0;
 }

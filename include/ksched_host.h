@@ -52,7 +52,8 @@ typedef struct ksh_context ksh_context;
 #define KSH_DEVICE_NONE (-1)
 int ksh_context_create(int device, ksh_context** out);
 void ksh_context_destroy(ksh_context* ctx);
-/* node store contents (what reflector::Store<Node>::state() returns, src/main.rs:56) */
+/* node store contents (what reflector::Store<Node>::state() returns, src/main.rs:56).  The store is keyed by name, so
+ * names are unique; if a name repeats anyway, pods and events address the first node of that name. */
 int ksh_context_set_nodes(ksh_context* ctx, const ks_node_obj* nodes, uint32_t n_nodes);
 /* every pod object the API server holds; those with spec.nodeName naming a known node are the LIST results
  * of src/predicates.rs:22-34 (any phase) and are charged to that node; the rest are ignored here. */

@@ -220,7 +220,10 @@ orc_cluster* orc_cluster_create(const ks_node_obj* nodes, uint32_t n_nodes, cons
     }
     for (uint32_t i = 0; i < n_nodes; i++) {
         if (!nodes[i].name) continue;
-        if (cluster_find_node(c, nodes[i].name) >= 0) continue; /* first wins */
+        /* Node names are unique in the reference: reflector::Store<Node> is keyed by the object reference
+         * (src/main.rs:133-139), so state() never holds two nodes of one name.  Input that repeats a name is outside
+         * its domain; here (and in the product packer) pods are charged to the first node of the name. */
+        if (cluster_find_node(c, nodes[i].name) >= 0) continue;
         uint64_t h = str_hash(nodes[i].name) & (cap - 1);
         while (c->htab[h]) h = (h + 1) & (cap - 1);
         c->htab[h] = i + 1;

@@ -124,3 +124,43 @@ def test_faithful_and_packed_oracles_agree_on_hypothesis_clusters(ks, orc, clust
     pk = orc.run_packed(fc, fm, ac, am, labels, rc, rm, sel, policy=policy, want_codes=True, nthreads=1)
     for a, b_, what in zip(f, pk, ("node_idx", "score", "cnt", "mask", "codes")):
         assert np.array_equal(a, b_), what
+
+
+@st.composite
+def tricky_cluster(draw):
+    """Like small_cluster, with label keys/values that stress the string handling of the packer: empty strings, shared
+    prefixes, separators, non-ASCII, long values."""
+    nodes_s, bound_s, pods_s = draw(small_cluster())
+    words = ["", "a", "ab", "a/b", "a=b", "zone", "Zone", "zöne", "x" * 70, "a\tb", "k:v", " "]
+    pick = st.sampled_from(words)
+    for n in nodes_s:
+        if draw(st.booleans()):
+            n["labels"] = draw(st.dictionaries(pick, pick, max_size=4))
+    for p in pods_s:
+        if draw(st.booleans()):
+            p["selector"] = draw(st.dictionaries(pick, pick, max_size=3))
+    if draw(st.booleans()) and len(nodes_s) > 1:
+        nodes_s[-1]["name"] = nodes_s[0]["name"]      # outside the reference's domain (its store is keyed by name):
+        #                                                  oracle and product both charge the first node of the name
+    return nodes_s, bound_s, pods_s
+
+
+@settings(max_examples=120, deadline=None)
+@given(tricky_cluster(), st.sampled_from([0, 1]))
+def test_product_packer_equals_faithful_oracle_on_hypothesis_clusters(ks, orc, cluster, policy):
+    """The C++ packer (packing-only context, no device) turns hypothesis-generated objects into arrays whose packed-oracle
+    answer equals the object-model oracle's answer on the same objects."""
+    nodes_s, bound_s, pods_s = cluster
+    arena = ks.objects.ObjectArena()
+    nodes, bound, pods = arena.nodes(nodes_s), arena.pods(bound_s), arena.pods(pods_s)
+    oc = orc.Cluster(nodes, len(nodes_s), bound, len(bound_s))
+    want = oc.run(pods, len(pods_s), policy=policy, want_codes=True, nthreads=1)
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(nodes, len(nodes_s))
+        ctx.set_cluster_pods(bound, len(bound_s))
+        rc, rm, sel = ctx.pack_pods(pods, len(pods_s))
+        ac, am, lab, bn, bc, bm = ctx.export_packed()
+    fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
+    got = orc.run_packed(fc, fm, ac, am, lab, rc, rm, sel, policy=policy, want_codes=True, nthreads=1)
+    for g, w, what in zip(got, want, ("node_idx", "score", "cnt", "mask", "codes")):
+        assert np.array_equal(g, w), what

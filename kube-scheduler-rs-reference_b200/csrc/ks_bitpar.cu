@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256)
 
 // label-pair columns: [bit][tile][32 B]
 // KS_BP_VARIANT (A/B switch, read once): 1 = default; 0 = previous kernel (16-byte skew per bit, both pods of a phase
-// load the same half first); 2 = experimental k_mask_bitpar2
+// load the same half first); 2, 3, 4 = experimental k_mask_bitpar2 with count mode 0, 1, 2
 static int bp_variant() {
     static const int v = [] {
         const char* e = getenv("KS_BP_VARIANT");
@@ -607,7 +607,17 @@ __global__ void __launch_bounds__(256)
     plist_s[q] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
 }
 
-template <int W>
+// carry-save adder on bit columns: (a, b, c) -> sum (weight 1) and carry (weight 2), one LOP3 each
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (a & c) | (b & c);
+}
+
+// CNT: how the feasible count of the 8 mask words of a pass is formed.  POPC runs on the quarter-rate XU pipe, which the
+// v16 capture shows as the busiest execution pipe (53 %), so the variants trade POPCs for LOP3s:
+//   0 = 8 POPC per pass (as k_mask_bitpar);  1 = carry-save tree per pass, 4 POPC;
+//   2 = Harley-Seal accumulators (ones/twos/fours) carried across the passes of a pod group: 1 POPC per pass + 3 per group
+template <int W, int CNT>
 __global__ void __launch_bounds__(BP_THREADS, 1)
     k_mask_bitpar2(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
                    const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s,
@@ -673,6 +683,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
             }
 
             uint32_t c = 0;
+            uint32_t ones = 0, twos = 0, fours = 0; // CNT == 2
             const uint32_t hc = (cr.x >> 6) * nt, hm = (cr.y >> 6) * nt;
             const unsigned long long lowC = (1ull << (cr.x & 63)) - 1ull, lowM = (1ull << (cr.y & 63)) - 1ull;
             for (uint32_t tb = 0; tb < nt; tb += 4) {
@@ -716,8 +727,27 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                             }
                         }
                     }
-                    c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
-                         __popc(b.w);
+                    if (CNT == 0) {
+                        c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
+                             __popc(b.w);
+                    } else if (CNT == 1) { // 8 words -> {s3, b.w} (weight 1), t (weight 2), f (weight 4)
+                        uint32_t s1, c1, s2, c2, s3, c3, t, f;
+                        csa(a.x, a.y, a.z, s1, c1);
+                        csa(a.w, b.x, b.y, s2, c2);
+                        csa(s1, s2, b.z, s3, c3);
+                        csa(c1, c2, c3, t, f);
+                        c += __popc(s3) + __popc(b.w) + 2 * __popc(t) + 4 * __popc(f);
+                    } else { // Harley-Seal step: fold the 8 words into ones/twos/fours, what overflows has weight 8
+                        uint32_t t0, t1, t2, t3, f0, f1, e0;
+                        csa(ones, a.x, a.y, ones, t0);
+                        csa(ones, a.z, a.w, ones, t1);
+                        csa(twos, t0, t1, twos, f0);
+                        csa(ones, b.x, b.y, ones, t2);
+                        csa(ones, b.z, b.w, ones, t3);
+                        csa(twos, t2, t3, twos, f1);
+                        csa(fours, f0, f1, fours, e0);
+                        c += 8 * __popc(e0);
+                    }
                     if (want_mask) {
                         const uint32_t word = (cb * nt + ct) * 8;
                         if (word < ov.mask_valid_words) {
@@ -732,6 +762,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
                     }
                 }
             }
+            if (CNT == 2) c += __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours);
             if (want_cnt) { // the 4 lanes of a pod are adjacent
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
                 c += __shfl_xor_sync(0xffffffffu, c, 2);
@@ -1023,7 +1054,11 @@ static cudaError_t set_smem_attr() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_bitpar2<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_mask_bitpar2<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1050,7 +1085,7 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = regrow(ix.pod_loc, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_s, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.pid_s, cap)) != cudaSuccess) return e;
-        if (bp_variant() == 2)
+        if (bp_variant() >= 2)
             if ((e = regrow(ix.plist_s, cap)) != cudaSuccess) return e;
         ix.cap_pods = cap;
         ix.cap_sel = 0;
@@ -1149,14 +1184,15 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
         ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
         const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
-        if (bp_variant() == 2) { // experimental, see k_mask_bitpar2
+        if (bp_variant() >= 2) { // experimental, see k_mask_bitpar2: 2, 3, 4 = count mode 0, 1, 2
             k_pod_pair_list<W><<<(P + 255) / 256, 256, 0, L.stream>>>(ix.sel_s, P, ix.lay.pstride, ix.plist_s);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (before_mask) // time the mask kernel alone
                 if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-            k_mask_bitpar2<W><<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(
-                ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, ix.plist_s, L.ov, ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
+            auto kern2 = bp_variant() == 2 ? k_mask_bitpar2<W, 0> : (bp_variant() == 3 ? k_mask_bitpar2<W, 1> : k_mask_bitpar2<W, 2>);
+            kern2<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, ix.plist_s, L.ov,
+                                                                     ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
         } else {
             auto kern = bp_variant() ? k_mask_bitpar<W, true> : k_mask_bitpar<W, false>;
             kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov,

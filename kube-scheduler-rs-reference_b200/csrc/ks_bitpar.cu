@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256)
 
 // label-pair columns: [bit][tile][32 B]
 // KS_BP_VARIANT (A/B switch, read once): 1 = default; 0 = previous kernel (16-byte skew per bit, both pods of a phase
-// load the same half first); 2, 3, 4 = experimental k_mask_bitpar2 with count mode 0, 1, 2
+// load the same half first); 2, 3, 4 = experimental k_mask_bitpar2 with count mode 0, 1, 2; 5 = 4 + 32-position sub-buckets
 static int bp_variant() {
     static const int v = [] {
         const char* e = getenv("KS_BP_VARIANT");
@@ -262,6 +262,107 @@ __global__ void __launch_bounds__(288)
         for (uint32_t h0 = 0; h0 < lay.nb; h0 += 32) {
             const uint32_t hi = h0 + lane;
             const uint32_t c = hi < lay.nb ? __popcll(__ldcg(&memb[(size_t)hi * lay.nt + t])) : 0;
+            uint32_t inc = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= (uint32_t)off) inc += o;
+            }
+            if (hi < lay.nb) base[(size_t)hi * lay.nt + t] = (uint16_t)(running + inc - c);
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    // label-pair columns, layout [bit][tile][8 words]
+    uint8_t* pairs = B + lay.off_pairs;
+    for (uint32_t bit = s; bit < 64u * nt.W; bit += blockDim.x) {
+        const uint32_t w_ = bit >> 6, sh = bit & 63;
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t acc = 0;
+            for (int b = 0; b < 32; b++) acc |= (uint32_t)((s_lab[w_][j * 32 + b] >> sh) & 1ull) << b;
+            w[j] = acc;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(pairs + (size_t)bit * lay.pstride + (size_t)t * 32);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// EXPERIMENTAL (KS_BP_VARIANT=5): the same tile index with rank lookups over 32-position sub-buckets - base u16 and
+// membership u32 per 32 global positions - so that a rank costs one 32-bit POPC instead of a 64-bit one (two).
+// One CTA builds the index of one 256-slot tile.  slot_node maps slot -> node (nullptr = identity, i.e. the
+// node-index order used for the mask; ord_idx = priority order used for the argmax).
+__global__ void __launch_bounds__(288)
+    k_build_tile32(NodeTable nt, const uint32_t* __restrict__ gposC, const uint32_t* __restrict__ gposM,
+                 const int32_t* __restrict__ slot_node, uint8_t* __restrict__ blob, BitparLayout lay) {
+    __shared__ uint32_t s_g[2][BP_TILE];
+    __shared__ uint16_t s_lr[2][BP_TILE];
+    __shared__ uint8_t s_valid[BP_TILE];
+    __shared__ uint64_t s_lab[KS_MAX_LABEL_WORDS][BP_TILE];
+    const uint32_t tile_g = blockIdx.x, cb = tile_g / lay.nt, t = tile_g % lay.nt, s = threadIdx.x;
+    uint8_t* B = blob + (size_t)cb * lay.blob_bytes;
+    if (s < BP_TILE) {
+        const uint32_t slot = tile_g * BP_TILE + s;
+        const bool v = slot < nt.N;
+        const uint32_t n = v ? (slot_node ? (uint32_t)slot_node[slot] : slot) : 0;
+        s_valid[s] = v;
+        s_g[0][s] = v ? gposC[n] : 0xFFFFFFFFu;
+        s_g[1][s] = v ? gposM[n] : 0xFFFFFFFFu;
+        for (uint32_t w = 0; w < nt.W; w++) s_lab[w][s] = v ? nt.labels[(size_t)w * nt.Npad + n] : 0ull;
+    }
+    __syncthreads();
+    if (s < BP_TILE) {
+        for (int r = 0; r < 2; r++) {
+            const uint32_t g = s_g[r][s];
+            uint32_t c = 0;
+            for (int k = 0; k < BP_TILE; k++) c += s_g[r][k] < g;
+            s_lr[r][s] = (uint16_t)c;
+        }
+    }
+    __syncthreads();
+    // prefix tables: row r = slots of the tile whose tile-local rank is >= r  (i.e. free >= threshold)
+    if (s < BP_ROWS) {
+        for (int r = 0; r < 2; r++) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t acc = 0;
+                for (int b = 0; b < 32; b++) {
+                    const int k = j * 32 + b;
+                    acc |= (uint32_t)(s_valid[k] && s_lr[r][k] >= s) << b;
+                }
+                w[j] = acc;
+            }
+            uint4* tab = reinterpret_cast<uint4*>(B + (r ? lay.off_tabM : lay.off_tabC) + table_row_offset(t, s));
+            tab[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            tab[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+    // sub-bucket membership + base counts, layout [sub-bucket][tile]; lay.nb = (N >> 5) + 1
+    uint32_t* membC = reinterpret_cast<uint32_t*>(B + lay.off_membC);
+    uint32_t* membM = reinterpret_cast<uint32_t*>(B + lay.off_membM);
+    uint16_t* baseC = reinterpret_cast<uint16_t*>(B + lay.off_baseC);
+    uint16_t* baseM = reinterpret_cast<uint16_t*>(B + lay.off_baseM);
+    for (uint32_t hi = s; hi < lay.nb; hi += blockDim.x) {
+        membC[(size_t)hi * lay.nt + t] = 0u;
+        membM[(size_t)hi * lay.nt + t] = 0u;
+    }
+    __syncthreads();
+    if (s < BP_TILE && s_valid[s]) {
+        atomicOr(&membC[(size_t)(s_g[0][s] >> 5) * lay.nt + t], 1u << (s_g[0][s] & 31));
+        atomicOr(&membM[(size_t)(s_g[1][s] >> 5) * lay.nt + t], 1u << (s_g[1][s] & 31));
+    }
+    __threadfence();
+    __syncthreads();
+    const uint32_t warp = s >> 5, lane = s & 31;
+    if (warp < 2) {
+        const uint32_t* memb = warp ? membM : membC;
+        uint16_t* base = warp ? baseM : baseC;
+        uint32_t running = 0;
+        for (uint32_t h0 = 0; h0 < lay.nb; h0 += 32) {
+            const uint32_t hi = h0 + lane;
+            const uint32_t c = hi < lay.nb ? __popc(__ldcg(&memb[(size_t)hi * lay.nt + t])) : 0;
             uint32_t inc = c;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -576,6 +677,11 @@ __device__ __forceinline__ unsigned long long lds64(uint32_t a) {
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t lds16(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -617,7 +723,8 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
 // v16 capture shows as the busiest execution pipe (53 %), so the variants trade POPCs for LOP3s:
 //   0 = 8 POPC per pass (as k_mask_bitpar);  1 = carry-save tree per pass, 4 POPC;
 //   2 = Harley-Seal accumulators (ones/twos/fours) carried across the passes of a pod group: 1 POPC per pass + 3 per group
-template <int W, int CNT>
+//   FMT 1 = rank lookups in the 32-position sub-bucket format written by k_build_tile32
+template <int W, int CNT, int FMT>
 __global__ void __launch_bounds__(BP_THREADS, 1)
     k_mask_bitpar2(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
                    const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s,
@@ -684,17 +791,26 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
 
             uint32_t c = 0;
             uint32_t ones = 0, twos = 0, fours = 0; // CNT == 2
-            const uint32_t hc = (cr.x >> 6) * nt, hm = (cr.y >> 6) * nt;
-            const unsigned long long lowC = (1ull << (cr.x & 63)) - 1ull, lowM = (1ull << (cr.y & 63)) - 1ull;
+            constexpr uint32_t BSH = FMT ? 5u : 6u; // log2 of the positions per (sub-)bucket
+            const uint32_t hc = (cr.x >> BSH) * nt, hm = (cr.y >> BSH) * nt;
+            const unsigned long long lowC = (1ull << (cr.x & ((1u << BSH) - 1u))) - 1ull,
+                                     lowM = (1ull << (cr.y & ((1u << BSH) - 1u))) - 1ull;
             for (uint32_t tb = 0; tb < nt; tb += 4) {
                 const uint32_t ct = tb + tsub;
                 if (cact && ct < nt) {
                     // tile-local rank of each threshold = tile nodes at global positions < threshold
                     const uint32_t ic = hc + ct, im = hm + ct;
                     const uint32_t bc = lds16(a_baseC + ic * 2), bm = lds16(a_baseM + im * 2);
-                    const unsigned long long mc = lds64(a_membC + ic * 8), mm = lds64(a_membM + im * 8);
-                    const uint32_t rankC = bc + __popcll(mc & lowC);
-                    const uint32_t rankM = bm + __popcll(mm & lowM);
+                    uint32_t rankC, rankM;
+                    if (FMT) {
+                        const uint32_t mc = lds32(a_membC + ic * 4), mm = lds32(a_membM + im * 4);
+                        rankC = bc + __popc(mc & (uint32_t)lowC);
+                        rankM = bm + __popc(mm & (uint32_t)lowM);
+                    } else {
+                        const unsigned long long mc = lds64(a_membC + ic * 8), mm = lds64(a_membM + im * 8);
+                        rankC = bc + __popcll(mc & lowC);
+                        rankM = bm + __popcll(mm & lowM);
+                    }
                     const uint32_t tq = (ct >> 2) * (uint32_t)(BP_ROWS * 128) + (ct & 3u) * 32u; // table_row_offset(ct, 0)
                     const uint32_t aC = a_tabC + tq + rankC * 128u, aM = a_tabM + tq + rankM * 128u;
                     // first / second half of the 32-byte row: (address) and (address ^ 16); rows are 32-byte aligned
@@ -950,6 +1066,40 @@ static bool make_layout_smem(uint32_t N, uint32_t W, BitparLayout* lay) {
     return fill_offsets(lay, W) && lay->blob_bytes <= (uint32_t)BP_SMEM_MAX;
 }
 
+// EXPERIMENTAL (KS_BP_VARIANT=5): the shared-memory blob with 32-position sub-buckets (k_build_tile32 / FMT 1)
+static bool make_layout_smem32(uint32_t N, uint32_t W, BitparLayout* lay) {
+    const uint32_t n_tiles = (N + BP_TILE - 1) / BP_TILE;
+    const uint64_t nb = ((uint64_t)N >> 5) + 1;
+    const uint64_t per_tile = nb * 12 + 2ull * BP_TABLE_BYTES + 64ull * W * 32; // base u16 + membership u32, two resources
+    const uint64_t avail = BP_SMEM_MAX - 1024 - 4096;                           // quad-rounding of the table areas
+    const uint32_t nt_max = (uint32_t)std::min<uint64_t>(32, avail / per_tile);
+    if (n_tiles == 0 || nt_max == 0) return false;
+    uint32_t nt = 1;
+    while (nt * 2 <= nt_max && nt < n_tiles) nt *= 2;
+    lay->nb = (uint32_t)nb;
+    lay->nt = nt;
+    lay->ncb = (n_tiles + nt - 1) / nt;
+    uint32_t off = 0;
+    lay->off_baseC = off;
+    off += round16((uint32_t)(nb * nt * 2));
+    lay->off_baseM = off;
+    off += round16((uint32_t)(nb * nt * 2));
+    lay->off_membC = off;
+    off += round16((uint32_t)(nb * nt * 4));
+    lay->off_membM = off;
+    off += round16((uint32_t)(nb * nt * 4));
+    off = (off + 127u) & ~127u;
+    lay->off_tabC = off;
+    off += table_area_bytes(nt);
+    lay->off_tabM = off;
+    off += table_area_bytes(nt);
+    lay->off_pairs = off;
+    lay->pstride = pair_stride(nt);
+    off += 64u * W * lay->pstride;
+    lay->blob_bytes = (off + 127u) & ~127u;
+    return lay->blob_bytes <= (uint32_t)BP_SMEM_MAX - 1024;
+}
+
 // flat layout for the priority-ordered index (global memory, all tiles in one blob)
 static bool make_layout_flat(uint32_t N, uint32_t W, BitparLayout* lay) {
     lay->nb = (N >> 6) + 1;
@@ -1019,7 +1169,9 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
     g_launches += 4;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     BitparLayout lay{}, layP{};
-    if (!make_layout_smem(nt.N, nt.W, &lay) || !make_layout_flat(nt.N, nt.W, &layP)) return cudaSuccess; // direct path only
+    const bool fmt32 = bp_variant() == 5; // experimental
+    if (!(fmt32 ? make_layout_smem32(nt.N, nt.W, &lay) : make_layout_smem(nt.N, nt.W, &lay)) || !make_layout_flat(nt.N, nt.W, &layP))
+        return cudaSuccess; // direct path only
     const size_t need = (size_t)lay.ncb * lay.blob_bytes;
     if (need > ix.cap_blob) {
         if ((e = regrow(ix.blob, need + need / 8)) != cudaSuccess) return e;
@@ -1030,7 +1182,8 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
         if ((e = regrow(ix.blobP, cap)) != cudaSuccess) return e;
         ix.cap_blobP = cap;
     }
-    k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
+    if (fmt32) k_build_tile32<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
+    else k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ord_idx, ix.blobP, layP);
@@ -1054,11 +1207,13 @@ static cudaError_t set_smem_attr() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_bitpar2<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_mask_bitpar2<W, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1184,13 +1339,16 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
         ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
         const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
-        if (bp_variant() >= 2) { // experimental, see k_mask_bitpar2: 2, 3, 4 = count mode 0, 1, 2
+        if (bp_variant() >= 2) { // experimental, see k_mask_bitpar2: 2, 3, 4 = count mode 0, 1, 2; 5 = mode 2 + 32-position format
             k_pod_pair_list<W><<<(P + 255) / 256, 256, 0, L.stream>>>(ix.sel_s, P, ix.lay.pstride, ix.plist_s);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (before_mask) // time the mask kernel alone
                 if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-            auto kern2 = bp_variant() == 2 ? k_mask_bitpar2<W, 0> : (bp_variant() == 3 ? k_mask_bitpar2<W, 1> : k_mask_bitpar2<W, 2>);
+            auto kern2 = bp_variant() == 2   ? k_mask_bitpar2<W, 0, 0>
+                         : bp_variant() == 3 ? k_mask_bitpar2<W, 1, 0>
+                         : bp_variant() == 4 ? k_mask_bitpar2<W, 2, 0>
+                                             : k_mask_bitpar2<W, 2, 1>;
             kern2<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, ix.plist_s, L.ov,
                                                                      ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
         } else {

@@ -1,7 +1,7 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): both kernel paths, streaming,
 host layer, on shapes that finish quickly under the tool.  Usage on a GPU box:
     compute-sanitizer --tool memcheck python tests/sanitizer_smoke.py
-KS_BP_VARIANT=2|3|4 selects the experimental mask kernels for the bit-parallel path."""
+KS_BP_VARIANT=2|3|4|5 selects the experimental mask kernels for the bit-parallel path."""
 import os
 import sys
 

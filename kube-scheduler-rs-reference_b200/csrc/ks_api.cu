@@ -32,6 +32,11 @@ static int fail(int code, const char* fmt, ...) {
                         __LINE__);                                                                     \
     } while (0)
 
+// Every reallocation of a device buffer bumps this counter; it is part of the CUDA-graph cache key of ks_select, so a
+// cached graph is never replayed after one of the buffers its nodes point to has moved (staging buffers grown by a
+// larger call, ks_check_cells / ks_select_sampling scratch, ...).
+static std::atomic<uint64_t> g_devbuf_epoch{0};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -40,6 +45,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
+        g_devbuf_epoch++;
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
@@ -73,7 +79,7 @@ struct ks_snapshot {
     BitparIndex bp;
     // CUDA-graph replay of the launch sequence of an all-device ks_select (same arguments, same snapshot state)
     cudaGraphExec_t graph_exec = nullptr;
-    uint64_t graph_key[14] = {0};
+    uint64_t graph_key[16] = {0};
     bool graph_valid = false;
     uint64_t graph_launches = 0; // kernels inside the cached graph
     uint64_t version = 1; // bumped whenever device-side snapshot state or buffers change
@@ -410,6 +416,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         if (out->mask_row_bytes % 32 != 0 || out->mask_row_bytes < ks_mask_row_bytes(s->N))
             return fail(KS_ERR_INVALID, "mask_row_bytes must be a multiple of 32 and >= %llu",
                         (unsigned long long)ks_mask_row_bytes(s->N));
+        if (((uintptr_t)out->mask & 31u) != 0) return fail(KS_ERR_INVALID, "mask must be 32-byte aligned");
     }
     if (P == 0) return KS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
@@ -581,12 +588,13 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         };
         // Replay from a cached CUDA graph when the call repeats (same buffers, same snapshot state).  Host buffers
         // qualify only if they are pinned (a captured copy from pageable memory is not allowed).
-        const uint64_t key[14] = {P, (uint64_t)pods->req_cpu, (uint64_t)pods->req_mem, (uint64_t)pods->sel,
+        const uint64_t key[16] = {P, (uint64_t)pods->req_cpu, (uint64_t)pods->req_mem, (uint64_t)pods->sel,
                                   (uint64_t)out->node_idx, (uint64_t)out->score, (uint64_t)out->feasible_cnt,
                                   (uint64_t)out->mask, out->mask_row_bytes,
                                   (uint64_t)policy | ((uint64_t)pods->mem_space << 8) | ((uint64_t)out->mem_space << 9) |
                                       ((uint64_t)out->mask_space << 10),
-                                  (uint64_t)flags ^ ((uint64_t)out->bindings_ready_event << 8), (uint64_t)st, s->version, (uint64_t)use_bitpar};
+                                  (uint64_t)flags ^ ((uint64_t)out->bindings_ready_event << 8), (uint64_t)st, s->version, (uint64_t)use_bitpar,
+                                  g_devbuf_epoch.load(), s->bp.epoch};
         const bool key_hit = s->graph_valid && memcmp(key, s->graph_key, sizeof(key)) == 0;
         bool graph_ok = !timing && !(flags & KS_SELECT_NO_GRAPH);
         if (graph_ok && !key_hit) {

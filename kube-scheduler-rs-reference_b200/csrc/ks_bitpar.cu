@@ -17,6 +17,8 @@
 #include "ks_bitpar.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace ks {
 
@@ -169,17 +171,23 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// label-pair columns: [bit][tile][32 B]
-// KS_BP_VARIANT (A/B switch, read once): 1 = default; 0 = previous kernel (16-byte skew per bit, both pods of a phase
-// load the same half first); 2, 3, 4 = experimental k_mask_bitpar2 with count mode 0, 1, 2; 5 = 4 + 32-position sub-buckets
-static int bp_variant() {
-    static const int v = [] {
-        const char* e = getenv("KS_BP_VARIANT");
-        return e ? atoi(e) : 1;
+// KS_MASK_KERNEL (A/B switch, read once): "rows" (default) = k_mask_rows; "quads" = the round-1 kernel
+// k_mask_bitpar (kept for one A/B session, then removed)
+static bool use_rows_kernel() {
+    static const bool v = [] {
+        const char* e = getenv("KS_MASK_KERNEL");
+        return !(e && strcmp(e, "quads") == 0);
     }();
     return v;
 }
-static uint32_t pair_stride(uint32_t nt) { return bp_variant() ? nt * 32u : nt * 32u + 16u; }
+static int rows_count_mode() { // 0 = 8 POPC per item, 1 = carry-save tree + 4 POPC
+    static const int v = [] {
+        const char* e = getenv("KS_ROWS_COUNT");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+static uint32_t pair_stride(uint32_t nt) { return nt * 32u; }
 
 // Prefix tables are interleaved by QUADS of tiles: row r of tiles 4k..4k+3 forms one 128-byte line
 //   [tile 4k row r | tile 4k+1 row r | tile 4k+2 row r | tile 4k+3 row r]
@@ -289,23 +297,21 @@ __global__ void __launch_bounds__(288)
     }
 }
 
-// EXPERIMENTAL (KS_BP_VARIANT=5): the same tile index with rank lookups over 32-position sub-buckets - base u16 and
-// membership u32 per 32 global positions - so that a rank costs one 32-bit POPC instead of a 64-bit one (two).
-// One CTA builds the index of one 256-slot tile.  slot_node maps slot -> node (nullptr = identity, i.e. the
-// node-index order used for the mask; ord_idx = priority order used for the argmax).
+// ---- "rows" format (ks_bitpar.h): one CTA builds one 256-slot tile of a column block, node-index order ----
+// Also leaves the tile's global positions in ascending order (tile_sorted) for k_build_ranks.
 __global__ void __launch_bounds__(288)
-    k_build_tile32(NodeTable nt, const uint32_t* __restrict__ gposC, const uint32_t* __restrict__ gposM,
-                 const int32_t* __restrict__ slot_node, uint8_t* __restrict__ blob, BitparLayout lay) {
+    k_build_cbtile(NodeTable nt, const uint32_t* __restrict__ gposC, const uint32_t* __restrict__ gposM,
+                   uint8_t* __restrict__ blob, RowsLayout lay, uint32_t* __restrict__ tile_sorted) {
     __shared__ uint32_t s_g[2][BP_TILE];
     __shared__ uint16_t s_lr[2][BP_TILE];
     __shared__ uint8_t s_valid[BP_TILE];
     __shared__ uint64_t s_lab[KS_MAX_LABEL_WORDS][BP_TILE];
-    const uint32_t tile_g = blockIdx.x, cb = tile_g / lay.nt, t = tile_g % lay.nt, s = threadIdx.x;
-    uint8_t* B = blob + (size_t)cb * lay.blob_bytes;
+    const uint32_t tile_g = blockIdx.x, cb = tile_g / RW_TILES, t = tile_g % RW_TILES, s = threadIdx.x;
+    const uint32_t n_tiles_pad = lay.ncb * RW_TILES;
+    uint8_t* B = blob + (size_t)cb * lay.cb_stride;
     if (s < BP_TILE) {
-        const uint32_t slot = tile_g * BP_TILE + s;
-        const bool v = slot < nt.N;
-        const uint32_t n = v ? (slot_node ? (uint32_t)slot_node[slot] : slot) : 0;
+        const uint32_t n = tile_g * BP_TILE + s;
+        const bool v = n < nt.N;
         s_valid[s] = v;
         s_g[0][s] = v ? gposC[n] : 0xFFFFFFFFu;
         s_g[1][s] = v ? gposM[n] : 0xFFFFFFFFu;
@@ -318,6 +324,11 @@ __global__ void __launch_bounds__(288)
             uint32_t c = 0;
             for (int k = 0; k < BP_TILE; k++) c += s_g[r][k] < g;
             s_lr[r][s] = (uint16_t)c;
+            // positions are distinct, so the valid slots fill tile_sorted[0..count) exactly; the rest is +inf
+            uint32_t* ts = tile_sorted + ((size_t)r * n_tiles_pad + tile_g) * BP_TILE;
+            if (s_valid[s]) ts[c] = g;
+            const uint32_t count = nt.N > tile_g * BP_TILE ? min((uint32_t)BP_TILE, nt.N - tile_g * BP_TILE) : 0u;
+            if (s >= count) ts[s] = 0xFFFFFFFFu;
         }
     }
     __syncthreads();
@@ -334,47 +345,12 @@ __global__ void __launch_bounds__(288)
                 }
                 w[j] = acc;
             }
-            uint4* tab = reinterpret_cast<uint4*>(B + (r ? lay.off_tabM : lay.off_tabC) + table_row_offset(t, s));
-            tab[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            tab[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            uint8_t* line = B + (r ? lay.off_tabM : lay.off_tabC) + (size_t)s * RW_LINE + t * 16;
+            *reinterpret_cast<uint4*>(line) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(line + 128) = make_uint4(w[4], w[5], w[6], w[7]);
         }
     }
-    // sub-bucket membership + base counts, layout [sub-bucket][tile]; lay.nb = (N >> 5) + 1
-    uint32_t* membC = reinterpret_cast<uint32_t*>(B + lay.off_membC);
-    uint32_t* membM = reinterpret_cast<uint32_t*>(B + lay.off_membM);
-    uint16_t* baseC = reinterpret_cast<uint16_t*>(B + lay.off_baseC);
-    uint16_t* baseM = reinterpret_cast<uint16_t*>(B + lay.off_baseM);
-    for (uint32_t hi = s; hi < lay.nb; hi += blockDim.x) {
-        membC[(size_t)hi * lay.nt + t] = 0u;
-        membM[(size_t)hi * lay.nt + t] = 0u;
-    }
-    __syncthreads();
-    if (s < BP_TILE && s_valid[s]) {
-        atomicOr(&membC[(size_t)(s_g[0][s] >> 5) * lay.nt + t], 1u << (s_g[0][s] & 31));
-        atomicOr(&membM[(size_t)(s_g[1][s] >> 5) * lay.nt + t], 1u << (s_g[1][s] & 31));
-    }
-    __threadfence();
-    __syncthreads();
-    const uint32_t warp = s >> 5, lane = s & 31;
-    if (warp < 2) {
-        const uint32_t* memb = warp ? membM : membC;
-        uint16_t* base = warp ? baseM : baseC;
-        uint32_t running = 0;
-        for (uint32_t h0 = 0; h0 < lay.nb; h0 += 32) {
-            const uint32_t hi = h0 + lane;
-            const uint32_t c = hi < lay.nb ? __popc(__ldcg(&memb[(size_t)hi * lay.nt + t])) : 0;
-            uint32_t inc = c;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
-                if (lane >= (uint32_t)off) inc += o;
-            }
-            if (hi < lay.nb) base[(size_t)hi * lay.nt + t] = (uint16_t)(running + inc - c);
-            running += __shfl_sync(0xffffffffu, inc, 31);
-        }
-    }
-    // label-pair columns, layout [bit][tile][8 words]
-    uint8_t* pairs = B + lay.off_pairs;
+    // label-pair columns
     for (uint32_t bit = s; bit < 64u * nt.W; bit += blockDim.x) {
         const uint32_t w_ = bit >> 6, sh = bit & 63;
         uint32_t w[8];
@@ -384,9 +360,42 @@ __global__ void __launch_bounds__(288)
             for (int b = 0; b < 32; b++) acc |= (uint32_t)((s_lab[w_][j * 32 + b] >> sh) & 1ull) << b;
             w[j] = acc;
         }
-        uint4* dst = reinterpret_cast<uint4*>(pairs + (size_t)bit * lay.pstride + (size_t)t * 32);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        uint8_t* line = B + lay.off_pairs + (size_t)bit * RW_LINE + t * 16;
+        *reinterpret_cast<uint4*>(line) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(line + 128) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// rank tables: rank[cb][g][resource][t] = number of nodes of tile (cb, t) at sorted positions < g in that
+// resource's order, for every threshold g in [0, N].  One thread = one threshold of one column block: 8 binary searches per resource over the tile's
+// sorted positions (shared memory), one 16-byte store per resource.
+__global__ void __launch_bounds__(256)
+    k_build_ranks(const uint32_t* __restrict__ tile_sorted, RowsLayout lay, uint16_t* __restrict__ rank) {
+    __shared__ uint32_t s_pos[2][RW_TILES][BP_TILE];
+    const uint32_t cb = blockIdx.y, n_tiles_pad = lay.ncb * RW_TILES;
+    for (uint32_t i = threadIdx.x; i < 2 * RW_TILES * BP_TILE; i += blockDim.x) {
+        const uint32_t r = i / (RW_TILES * BP_TILE), tt = (i / BP_TILE) % RW_TILES, k = i % BP_TILE;
+        s_pos[r][tt][k] = tile_sorted[((size_t)r * n_tiles_pad + cb * RW_TILES + tt) * BP_TILE + k];
+    }
+    __syncthreads();
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= lay.n_thr) return;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        uint32_t out[RW_TILES];
+#pragma unroll
+        for (uint32_t tt = 0; tt < RW_TILES; tt++) {
+            const uint32_t* a = s_pos[r][tt];
+            uint32_t lo = 0; // number of elements < g (0..256)
+#pragma unroll
+            for (uint32_t step = BP_TILE / 2; step > 0; step >>= 1)
+                if (a[lo + step - 1] < g) lo += step;
+            if (a[lo] < g) lo++; // lo <= 255 here
+            out[tt] = lo;
+        }
+        uint16_t* dst = rank + (((size_t)cb * lay.n_thr + g) * 2 + r) * RW_TILES; // [cb][g][resource][tile]
+        *reinterpret_cast<uint4*>(dst) = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16),
+                                                   out[4] | (out[5] << 16), out[6] | (out[7] << 16));
     }
 }
 
@@ -486,13 +495,20 @@ __global__ void __launch_bounds__(1024)
     if (threadIdx.x == 1023) chunk_total[blockIdx.x] = s_warp[31];
 }
 
-// counting-sort scatter: pods in bucket order with everything the mask kernel needs, contiguous
+// counting-sort scatter: pods in bucket order with everything the mask kernel needs, contiguous.
+// rows kernel: one 16-byte record per sorted pod {threshold_cpu, threshold_mem, pod index, selector columns};
+// "selector columns" = up to three required label-pair bit indices (10 bits each) + their number in bits 30-31,
+// RW_SEL_GENERIC when the selector names more than three pairs (the kernel then walks sel_s).  The list is padded
+// to a multiple of 8 with inactive records (pod index 0xFFFFFFFF).
+constexpr uint32_t RW_SEL_GENERIC = 0xFFFFFFFFu;
+constexpr uint32_t RW_PID_NONE = 0xFFFFFFFFu;
+
 template <int W>
 __global__ void __launch_bounds__(256)
     k_pod_scatter(PodView pv, const uint2* __restrict__ rk, const uint32_t* __restrict__ start,
                   const uint32_t* __restrict__ chunk_total, uint32_t n_chunks, const uint32_t* __restrict__ pod_bin,
                   const uint32_t* __restrict__ pod_loc, uint2* __restrict__ rk_s, uint32_t* __restrict__ pid_s,
-                  unsigned long long* __restrict__ sel_s) {
+                  unsigned long long* __restrict__ sel_s, uint4* __restrict__ rec_s) {
     __shared__ uint32_t s_chunk[64];
     if (threadIdx.x < 64) { // exclusive prefix over the <=64 chunk totals
         uint32_t acc = 0;
@@ -501,13 +517,30 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pv.P) return;
+    if (p >= pv.P) {
+        if (rec_s && p < ((pv.P + 7u) & ~7u)) rec_s[p] = make_uint4(0, 0, RW_PID_NONE, 0); // padding of the last group
+        return;
+    }
     const uint32_t bin = pod_bin[p];
     const uint32_t q = start[bin] + s_chunk[bin >> 10] + pod_loc[p];
-    rk_s[q] = rk[p];
-    pid_s[q] = p;
+    const uint2 r = rk[p];
+    uint32_t cols = 0, n_req = 0;
 #pragma unroll
-    for (int w = 0; w < W; w++) sel_s[(size_t)q * W + w] = __ldg(pv.sel + (size_t)p * W + w);
+    for (int w = 0; w < W; w++) {
+        unsigned long long bits = __ldg(pv.sel + (size_t)p * W + w);
+        sel_s[(size_t)q * W + w] = bits;
+        while (bits) { // required (key,value) pairs of the selector (predicates.rs:48)
+            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (n_req < 3) cols |= bit << (10 * n_req);
+            n_req++;
+        }
+    }
+    if (rk_s) {
+        rk_s[q] = r;
+        pid_s[q] = p;
+    }
+    if (rec_s) rec_s[q] = make_uint4(r.x, r.y, p, n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30)));
 }
 
 // Mask kernel.  Pods arrive bucket-sorted by threshold (k_pod_scatter).  One warp = 8 consecutive sorted pods x
@@ -658,84 +691,136 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     }
 }
 
-// ------------------------------------------------------------------------------------------------ variant 2
-// EXPERIMENTAL (KS_BP_VARIANT=2; not the default, not yet run on a GPU): the same mask kernel with the per-pass
-// instruction count cut down.  What changes, guided by the SASS of k_mask_bitpar (profiles/r01_sass_evidence_v23.txt):
-//  * shared memory is addressed through 32-bit shared-window addresses derived once per thread (the compiler
-//    re-derives the cluster-mapped window base - S2R CgaCtaId + 3 ALU - and re-reads layout constants in every pass
-//    because it is register-starved at 64 registers x 1024 threads);
-//  * the label-pair columns a pod needs come as a precomputed list of <= 4 column offsets (k_pod_pair_list, once per
-//    pod) instead of a find-first-set loop over the selector words in every (pod, tile) pass (32 instructions per pair).
-// Layout, lane mapping, half-swap and results are those of k_mask_bitpar<W, true>.
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+// ------------------------------------------------------------------------------------------------ rows kernel
+// k_mask_rows: the round-2 mask / count kernel ("rows" format, ks_bitpar.h).
+//   * lane = (pod slot, tile): 8 lanes per pod = the 8 tiles of the column block = 256 contiguous bytes of the
+//     pod's mask row per 256-bit store; a warp iteration covers 8 consecutive sorted pods (two per thread, two
+//     independent dependency chains);
+//   * the tile-local rank of the pod's thresholds comes from the rank tables (one 16-bit load per resource from
+//     L1/L2; the 8 lanes of a pod read 16 contiguous bytes) - no base/membership lookup, no POPC for ranks;
+//   * table rows and label-pair columns are octet-interleaved: the 8 lanes of a shared-memory phase read granule t
+//     of their own 256-byte line -> conflict-free for any ranks, plain (unswapped) stores;
+//   * work = flattened (column block, pod group) space cut into gridDim.x equal contiguous ranges: every SM gets
+//     the same share whatever ncb is, a CTA re-stages the table blob only when its range crosses a column block;
+//     inside a column block the sorted pod list is dealt in RW_STRATA strata so that every CTA sees every
+//     selector-size class;
+//   * pod records are fetched two iterations ahead and ranks one iteration ahead (software pipeline).
+__device__ __forceinline__ uint4 lds128(uint32_t a) { // pure: scheduled freely; ordered after the blob wait by the
+    uint4 v;                                          // address dependence on the post-wait token
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
-    unsigned long long v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+__device__ __forceinline__ uint32_t ldg_u16(const uint16_t* p) { // zero-extended into a 32-bit register
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
+template <class T>
+__device__ __forceinline__ T* opaque_ptr(T* p) { // keeps a per-thread base pointer in one register pair (the compiler
+    asm("" : "+l"(p));                           // would otherwise re-derive its lane part in every iteration)
+    return p;
 }
-
-constexpr uint32_t PL_END = 0xFFFFu;     // no further column
-constexpr uint32_t PL_GENERIC = 0xFFFEu; // more than 4 required pairs: walk the selector words instead
-
-// Per sorted pod: the label-pair columns its selector requires, as 4 x u16 = (bit index * pstride) / 16.
-template <int W>
-__global__ void __launch_bounds__(256)
-    k_pod_pair_list(const unsigned long long* __restrict__ sel_s, uint32_t P, uint32_t pstride, uint2* __restrict__ plist_s) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= P) return;
-    uint32_t e[4] = {PL_END, PL_END, PL_END, PL_END};
-    uint32_t n = 0;
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        unsigned long long bits = sel_s[(size_t)q * W + w];
-        while (bits) {
-            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            if (n < 4) e[n] = (bit * pstride) >> 4; // <= 511 * 1024 / 16 < 0xFFFE
-            n++;
-        }
-    }
-    if (n > 4) e[0] = PL_GENERIC;
-    plist_s[q] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+__device__ __forceinline__ uint4 and4(uint4 a, uint4 b, uint4 c) {
+    return make_uint4(a.x & b.x & c.x, a.y & b.y & c.y, a.z & b.z & c.z, a.w & b.w & c.w);
 }
-
 // carry-save adder on bit columns: (a, b, c) -> sum (weight 1) and carry (weight 2), one LOP3 each
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
     sum = a ^ b ^ c;
     carry = (a & b) | (a & c) | (b & c);
 }
 
-// CNT: how the feasible count of the 8 mask words of a pass is formed.  POPC runs on the quarter-rate XU pipe, which the
-// v16 capture shows as the busiest execution pipe (53 %), so the variants trade POPCs for LOP3s:
-//   0 = 8 POPC per pass (as k_mask_bitpar);  1 = carry-save tree per pass, 4 POPC;
-//   2 = Harley-Seal accumulators (ones/twos/fours) carried across the passes of a pod group: 1 POPC per pass + 3 per group
-//   FMT 1 = rank lookups in the 32-position sub-bucket format written by k_build_tile32
-template <int W, int CNT, int FMT>
-__global__ void __launch_bounds__(BP_THREADS, 1)
-    k_mask_bitpar2(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
-                   const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s,
-                   const uint2* __restrict__ plist_s, OutView ov, uint32_t ctas_per_cb) {
+struct RowsParams { // kernel parameters stay in the constant bank: the loop reads them from there on demand
+    const uint8_t* blob;
+    RowsLayout lay;
+    const uint16_t* rank;            // [cb][threshold g][resource][tile] u16: 32 bytes per (cb, g)
+    const uint4* rec_s;              // sorted pod records, padded to a multiple of 8
+    const unsigned long long* sel_s; // sorted selector words (generic path only)
+    uint32_t n_groups, GS;           // groups of 8 sorted pods; groups per stratum
+    uint32_t* mask;                  // may be nullptr
+    uint32_t row_words;              // mask row pitch in 32-bit words
+    uint32_t* cnt;                   // may be nullptr
+};
+
+// one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
+// a_tab = shared-window address of granule t of line 0 of tabC; tabM and the pair columns sit at constant offsets.
+template <int W, bool PSMEM, int CNT>
+__device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_tab, uint32_t cb, uint32_t t, uint32_t* mask_col,
+                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q) {
+    const uint32_t aC = a_tab + rC * RW_LINE, aM = a_tab + rM * RW_LINE;
+    const uint4 c0 = lds128(aC), c1 = lds128(aC + 128);
+    const uint4 m0 = lds128(aM + RW_TAB_BYTES), m1 = lds128(aM + RW_TAB_BYTES + 128);
+    uint4 a, b;
+    auto column = [&](uint32_t bit, uint4& q0, uint4& q1) { // node column of one required pair (predicates.rs:48-53)
+        if (PSMEM) {
+            const uint32_t ap = a_tab + bit * RW_LINE;
+            q0 = lds128(ap + 2 * RW_TAB_BYTES);
+            q1 = lds128(ap + 2 * RW_TAB_BYTES + 128);
+        } else {
+            const uint4* gp = reinterpret_cast<const uint4*>(prm.blob + (size_t)cb * prm.lay.cb_stride + prm.lay.off_pairs +
+                                                             (size_t)bit * RW_LINE + t * 16u);
+            q0 = __ldg(gp);
+            q1 = __ldg(gp + 8);
+        }
+    };
+    const uint32_t n_req = sel >> 30;
+    if (n_req == 0) {
+        a = and4(c0, m0);
+        b = and4(c1, m1);
+    } else if (sel != RW_SEL_GENERIC) {
+        uint4 q0, q1;
+        column(sel & 0x3FFu, q0, q1);
+        a = and4(c0, m0, q0);
+        b = and4(c1, m1, q1);
+        if (n_req >= 2) {
+            column((sel >> 10) & 0x3FFu, q0, q1);
+            a = and4(a, q0);
+            b = and4(b, q1);
+            if (n_req == 3) {
+                column((sel >> 20) & 0x3FFu, q0, q1);
+                a = and4(a, q0);
+                b = and4(b, q1);
+            }
+        }
+    } else { // rare: more than three required pairs
+        a = and4(c0, m0);
+        b = and4(c1, m1);
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            unsigned long long bits = __ldg(prm.sel_s + (size_t)q * W + w);
+            while (bits) {
+                const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                uint4 q0, q1;
+                column(bit, q0, q1);
+                a = and4(a, q0);
+                b = and4(b, q1);
+            }
+        }
+    }
+    if (mask_col != nullptr && pid != RW_PID_NONE) {
+        uint32_t* dst = mask_col + (size_t)pid * prm.row_words; // 32-byte aligned
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                     "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                     : "memory");
+    }
+    if (CNT == 0) {
+        return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+    } else { // 8 words -> {s3, b.w} (weight 1), t (weight 2), f (weight 4): 4 POPC + 8 LOP3
+        uint32_t s1, c1_, s2, c2_, s3, c3_, tw, fw;
+        csa(a.x, a.y, a.z, s1, c1_);
+        csa(a.w, b.x, b.y, s2, c2_);
+        csa(s1, s2, b.z, s3, c3_);
+        csa(c1_, c2_, c3_, tw, fw);
+        return __popc(s3) + __popc(b.w) + 2 * __popc(tw) + 4 * __popc(fw);
+    }
+}
+
+template <int W, bool PSMEM, int CNT>
+__global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, psub = lane >> 2, tsub = lane & 3;
-    const uint32_t nt = lay.nt;
-    const uint32_t n_groups = (P + 7) / 8;
-    const uint32_t cta_in_cb = blockIdx.x % ctas_per_cb;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid & 7, ps = (tid >> 3) & 3;
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -743,148 +828,75 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
     __syncthreads();
     uint32_t phase = 0;
 
-    // shared-window addresses, derived once; hsw = byte offset of the half this lane loads first (0 or 16)
-    const uint32_t sbase = smem_u32(smem);
-    const uint32_t hsw = (psub & 1u) * 16u;
-    const uint32_t a_baseC = sbase + lay.off_baseC, a_baseM = sbase + lay.off_baseM;
-    const uint32_t a_membC = sbase + lay.off_membC, a_membM = sbase + lay.off_membM;
-    const uint32_t a_tabC = sbase + lay.off_tabC + hsw, a_tabM = sbase + lay.off_tabM + hsw;
-    const uint32_t a_pairs = sbase + lay.off_pairs + hsw;
-    const uint32_t pstride = lay.pstride;
-    const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
+    const uint64_t n_slots = (uint64_t)RW_STRATA * prm.GS; // pod-group slots per column block (>= n_groups)
+    const uint64_t F = n_slots * prm.lay.ncb;
+    uint64_t f = F * blockIdx.x / gridDim.x;
+    const uint64_t f_end = F * (blockIdx.x + 1) / gridDim.x;
 
-    for (uint32_t cb = blockIdx.x / ctas_per_cb; cb < lay.ncb; cb += gridDim.x / ctas_per_cb) {
-        __syncthreads(); // every read of the previous blob is done
+    while (f < f_end) { // one iteration per column block touched by this CTA's range (1 or 2, rarely more)
+        const uint32_t cb = (uint32_t)(f / n_slots);
+        const uint32_t j0 = (uint32_t)(f - (uint64_t)cb * n_slots);
+        const uint32_t j1 = (uint32_t)min(n_slots, (uint64_t)j0 + (f_end - f));
+        f += j1 - j0;
+
+        __syncthreads(); // all reads of the previous blob are done
         if (tid == 0) {
             fence_proxy_async();
-            mbar_arrive_expect_tx(&bar, lay.blob_bytes);
-            const uint8_t* src = blob + (size_t)cb * lay.blob_bytes;
-            for (uint32_t off = 0; off < lay.blob_bytes; off += 32768u)
-                tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
+            mbar_arrive_expect_tx(&bar, prm.lay.smem_bytes);
+            const uint8_t* src = prm.blob + (size_t)cb * prm.lay.cb_stride;
+            for (uint32_t off = 0; off < prm.lay.smem_bytes; off += 32768u)
+                tma_bulk_g2s(smem + off, src + off, min(32768u, prm.lay.smem_bytes - off), &bar);
         }
+        // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
+        const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
+        const uint4* rec_t = opaque_ptr(prm.rec_s + ps);
 
-        const uint32_t g_step = ctas_per_cb * (BP_THREADS / 32);
-        uint32_t g = cta_in_cb * (BP_THREADS / 32) + warp;
-        uint32_t q = g * 8 + psub;
-        bool act = g < n_groups && q < P;
-        uint2 r = act ? __ldg(rk_s + q) : make_uint2(0, 0); // prefetch while the blob is in flight
-        uint32_t pid = act ? __ldg(pid_s + q) : 0;
-        uint2 pl = act ? __ldg(plist_s + q) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-        uint32_t pq = q;
+        // pod records are fetched one iteration ahead; loads are unconditional (slot clamped into the list),
+        // validity only decides whether the item is computed
+        const uint32_t last_grp = prm.n_groups - 1;
+        auto group_of = [&](uint32_t j) { return (j & (RW_STRATA - 1u)) * prm.GS + (j >> 5); };
+        auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
+            const uint4* rp = rec_t + (size_t)min(group_of(j), last_grp) * 8u;
+            ra = __ldg(rp);
+            rb = __ldg(rp + 4);
+        };
+        uint32_t j = j0 + warp;
+        uint4 nA, nB; // records of the next iteration
+        fetch_rec(j, nA, nB);
 
         mbar_wait(&bar, phase);
         phase ^= 1;
+        uint32_t tok; // every shared-memory load below depends on a value produced after the wait
+        asm volatile("mov.u32 %0, 0;" : "=r"(tok)::"memory");
+        const uint32_t a_tab = smem_u32(smem) + t * 16u + tok;
+        const uint32_t tile = cb * RW_TILES + t;
+        uint32_t* mask_col = (prm.mask != nullptr && tile < prm.lay.n_tiles) ? opaque_ptr(prm.mask + (size_t)tile * 8u) : nullptr;
 
-        while (g < n_groups) { // warp-uniform
-            const uint2 cr = r, cpl = pl;
-            const uint32_t cpid = pid, cq = pq;
-            const bool cact = act;
-            g += g_step;
-            q = g * 8 + psub;
-            act = g < n_groups && q < P;
-            if (act) { // software prefetch of the next group's pod data
-                r = __ldg(rk_s + q);
-                pid = __ldg(pid_s + q);
-                pl = __ldg(plist_s + q);
-                pq = q;
-            }
+        for (; j < j1; j += 32) { // warp-uniform
+            const uint4 rA = nA, rB = nB;
+            const uint32_t rCa = ldg_u16(rk_t + (size_t)rA.x * 16u), rMa = ldg_u16(rk_t + (size_t)rA.y * 16u + 8);
+            const uint32_t rCb = ldg_u16(rk_t + (size_t)rB.x * 16u), rMb = ldg_u16(rk_t + (size_t)rB.y * 16u + 8);
+            fetch_rec(j + 32, nA, nB);
+            const uint32_t pidA = rA.z, selA = rA.w, pidB = rB.z, selB = rB.w;
+            const uint32_t grp0 = group_of(j);
+            if (grp0 > last_grp) continue; // slot past the end of its stratum
 
-            uint32_t c = 0;
-            uint32_t ones = 0, twos = 0, fours = 0; // CNT == 2
-            constexpr uint32_t BSH = FMT ? 5u : 6u; // log2 of the positions per (sub-)bucket
-            const uint32_t hc = (cr.x >> BSH) * nt, hm = (cr.y >> BSH) * nt;
-            const unsigned long long lowC = (1ull << (cr.x & ((1u << BSH) - 1u))) - 1ull,
-                                     lowM = (1ull << (cr.y & ((1u << BSH) - 1u))) - 1ull;
-            for (uint32_t tb = 0; tb < nt; tb += 4) {
-                const uint32_t ct = tb + tsub;
-                if (cact && ct < nt) {
-                    // tile-local rank of each threshold = tile nodes at global positions < threshold
-                    const uint32_t ic = hc + ct, im = hm + ct;
-                    const uint32_t bc = lds16(a_baseC + ic * 2), bm = lds16(a_baseM + im * 2);
-                    uint32_t rankC, rankM;
-                    if (FMT) {
-                        const uint32_t mc = lds32(a_membC + ic * 4), mm = lds32(a_membM + im * 4);
-                        rankC = bc + __popc(mc & (uint32_t)lowC);
-                        rankM = bm + __popc(mm & (uint32_t)lowM);
-                    } else {
-                        const unsigned long long mc = lds64(a_membC + ic * 8), mm = lds64(a_membM + im * 8);
-                        rankC = bc + __popcll(mc & lowC);
-                        rankM = bm + __popcll(mm & lowM);
-                    }
-                    const uint32_t tq = (ct >> 2) * (uint32_t)(BP_ROWS * 128) + (ct & 3u) * 32u; // table_row_offset(ct, 0)
-                    const uint32_t aC = a_tabC + tq + rankC * 128u, aM = a_tabM + tq + rankM * 128u;
-                    // first / second half of the 32-byte row: (address) and (address ^ 16); rows are 32-byte aligned
-                    const uint4 c0 = lds128(aC), c1 = lds128(aC ^ 16u);
-                    const uint4 m0 = lds128(aM), m1 = lds128(aM ^ 16u);
-                    uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
-                    uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
-                    const uint32_t a_col = a_pairs + ct * 32u;
-                    if ((cpl.x & 0xFFFFu) != PL_GENERIC) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) { // AND the node column of every required pair (predicates.rs:48-53)
-                            const uint32_t e = ((k < 2 ? cpl.x : cpl.y) >> (16 * (k & 1))) & 0xFFFFu;
-                            if (e == PL_END) break;
-                            const uint32_t ap = a_col + (e << 4);
-                            const uint4 q0 = lds128(ap), q1 = lds128(ap ^ 16u);
-                            a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
-                            b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
-                        }
-                    } else { // rare: more than 4 required pairs
-#pragma unroll
-                        for (int w = 0; w < W; w++) {
-                            unsigned long long bits = __ldg(sel_s + (size_t)cq * W + w);
-                            while (bits) {
-                                const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-                                bits &= bits - 1;
-                                const uint32_t ap = a_col + bit * pstride;
-                                const uint4 q0 = lds128(ap), q1 = lds128(ap ^ 16u);
-                                a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
-                                b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
-                            }
-                        }
-                    }
-                    if (CNT == 0) {
-                        c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
-                             __popc(b.w);
-                    } else if (CNT == 1) { // 8 words -> {s3, b.w} (weight 1), t (weight 2), f (weight 4)
-                        uint32_t s1, c1, s2, c2, s3, c3, t, f;
-                        csa(a.x, a.y, a.z, s1, c1);
-                        csa(a.w, b.x, b.y, s2, c2);
-                        csa(s1, s2, b.z, s3, c3);
-                        csa(c1, c2, c3, t, f);
-                        c += __popc(s3) + __popc(b.w) + 2 * __popc(t) + 4 * __popc(f);
-                    } else { // Harley-Seal step: fold the 8 words into ones/twos/fours, what overflows has weight 8
-                        uint32_t t0, t1, t2, t3, f0, f1, e0;
-                        csa(ones, a.x, a.y, ones, t0);
-                        csa(ones, a.z, a.w, ones, t1);
-                        csa(twos, t0, t1, twos, f0);
-                        csa(ones, b.x, b.y, ones, t2);
-                        csa(ones, b.z, b.w, ones, t3);
-                        csa(twos, t2, t3, twos, f1);
-                        csa(fours, f0, f1, fours, e0);
-                        c += 8 * __popc(e0);
-                    }
-                    if (want_mask) {
-                        const uint32_t word = (cb * nt + ct) * 8;
-                        if (word < ov.mask_valid_words) {
-                            uint32_t* dst = ov.mask + (size_t)cpid * ov.mask_row_words + word; // 32-byte aligned
-                            // a = the half loaded first (upper 16 bytes for odd pods), b = the other one
-                            asm volatile("{ .reg .pred p; setp.ne.u32 p, %9, 0;\n\t"
-                                         "@p st.global.v8.b32 [%0], {%5,%6,%7,%8,%1,%2,%3,%4};\n\t"
-                                         "@!p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}; }" ::"l"(dst),
-                                         "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(hsw)
-                                         : "memory");
-                        }
-                    }
-                }
-            }
-            if (CNT == 2) c += __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours);
-            if (want_cnt) { // the 4 lanes of a pod are adjacent
+            const uint32_t cA = rows_item<W, PSMEM, CNT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + ps);
+            const uint32_t cB = rows_item<W, PSMEM, CNT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 4u + ps);
+            if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
+                uint32_t c = cA | (cB << 16);
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
                 c += __shfl_xor_sync(0xffffffffu, c, 2);
-                if (cact && tsub == 0) {
-                    if (lay.ncb == 1) ov.cnt[cpid] = c; // single writer, no zero-init needed
-                    else if (c) atomicAdd(&ov.cnt[cpid], c);
+                c += __shfl_xor_sync(0xffffffffu, c, 4);
+                if (t == 0) {
+                    const uint32_t ca = c & 0xFFFFu, cb_ = c >> 16;
+                    if (prm.lay.ncb == 1) { // single writer, no zero-init needed
+                        if (pidA != RW_PID_NONE) prm.cnt[pidA] = ca;
+                        if (pidB != RW_PID_NONE) prm.cnt[pidB] = cb_;
+                    } else {
+                        if (pidA != RW_PID_NONE && ca) atomicAdd(&prm.cnt[pidA], ca);
+                        if (pidB != RW_PID_NONE && cb_) atomicAdd(&prm.cnt[pidB], cb_);
+                    }
                 }
             }
         }
@@ -1066,38 +1078,23 @@ static bool make_layout_smem(uint32_t N, uint32_t W, BitparLayout* lay) {
     return fill_offsets(lay, W) && lay->blob_bytes <= (uint32_t)BP_SMEM_MAX;
 }
 
-// EXPERIMENTAL (KS_BP_VARIANT=5): the shared-memory blob with 32-position sub-buckets (k_build_tile32 / FMT 1)
-static bool make_layout_smem32(uint32_t N, uint32_t W, BitparLayout* lay) {
+// "rows" format (ks_bitpar.h): column blocks of RW_TILES tiles; the pair columns are staged with the tables when
+// everything fits in shared memory (W <= 4), else they are read through L1/L2
+static bool make_layout_rows(uint32_t N, uint32_t W, RowsLayout* lay) {
     const uint32_t n_tiles = (N + BP_TILE - 1) / BP_TILE;
-    const uint64_t nb = ((uint64_t)N >> 5) + 1;
-    const uint64_t per_tile = nb * 12 + 2ull * BP_TABLE_BYTES + 64ull * W * 32; // base u16 + membership u32, two resources
-    const uint64_t avail = BP_SMEM_MAX - 1024 - 4096;                           // quad-rounding of the table areas
-    const uint32_t nt_max = (uint32_t)std::min<uint64_t>(32, avail / per_tile);
-    if (n_tiles == 0 || nt_max == 0) return false;
-    uint32_t nt = 1;
-    while (nt * 2 <= nt_max && nt < n_tiles) nt *= 2;
-    lay->nb = (uint32_t)nb;
-    lay->nt = nt;
-    lay->ncb = (n_tiles + nt - 1) / nt;
-    uint32_t off = 0;
-    lay->off_baseC = off;
-    off += round16((uint32_t)(nb * nt * 2));
-    lay->off_baseM = off;
-    off += round16((uint32_t)(nb * nt * 2));
-    lay->off_membC = off;
-    off += round16((uint32_t)(nb * nt * 4));
-    lay->off_membM = off;
-    off += round16((uint32_t)(nb * nt * 4));
-    off = (off + 127u) & ~127u;
-    lay->off_tabC = off;
-    off += table_area_bytes(nt);
-    lay->off_tabM = off;
-    off += table_area_bytes(nt);
-    lay->off_pairs = off;
-    lay->pstride = pair_stride(nt);
-    off += 64u * W * lay->pstride;
-    lay->blob_bytes = (off + 127u) & ~127u;
-    return lay->blob_bytes <= (uint32_t)BP_SMEM_MAX - 1024;
+    if (n_tiles == 0) return false;
+    lay->n_tiles = n_tiles;
+    lay->ncb = (n_tiles + RW_TILES - 1) / RW_TILES;
+    lay->off_tabC = 0;
+    lay->off_tabM = RW_TAB_BYTES;
+    lay->off_pairs = 2 * RW_TAB_BYTES;
+    const uint32_t pairs_bytes = 64u * W * RW_LINE;
+    lay->cb_stride = 2 * RW_TAB_BYTES + pairs_bytes; // multiple of 256
+    lay->pairs_smem = lay->cb_stride <= (uint32_t)BP_SMEM_MAX - 1024u ? 1u : 0u;
+    lay->smem_bytes = lay->pairs_smem ? lay->cb_stride : 2 * RW_TAB_BYTES;
+    lay->n_thr = N + 1;
+    // rank tables: 2 x ncb x (N+1) x 16 B; beyond 4 GB the per-cell kernel serves the snapshot
+    return (uint64_t)lay->ncb * lay->n_thr * RW_TILES * 2ull * 2ull <= (4ull << 30);
 }
 
 // flat layout for the priority-ordered index (global memory, all tiles in one blob)
@@ -1108,10 +1105,12 @@ static bool make_layout_flat(uint32_t N, uint32_t W, BitparLayout* lay) {
     return lay->nt > 0 && fill_offsets(lay, W);
 }
 
+static std::atomic<uint64_t> g_regrow_epoch{0}; // any reallocation invalidates cached CUDA graphs (BitparIndex::epoch)
 template <class T>
 static cudaError_t regrow(T*& p, size_t count) {
     if (p) cudaFree(p);
     p = nullptr;
+    g_regrow_epoch++;
     return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
 }
 
@@ -1119,7 +1118,8 @@ void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
                     ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
                     ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist,
-                    ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.plist_s};
+                    ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.rec_s,
+                    ix.blobR,   ix.rank,   ix.tile_sorted};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -1169,29 +1169,60 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
     g_launches += 4;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     BitparLayout lay{}, layP{};
-    const bool fmt32 = bp_variant() == 5; // experimental
-    if (!(fmt32 ? make_layout_smem32(nt.N, nt.W, &lay) : make_layout_smem(nt.N, nt.W, &lay)) || !make_layout_flat(nt.N, nt.W, &layP))
-        return cudaSuccess; // direct path only
-    const size_t need = (size_t)lay.ncb * lay.blob_bytes;
-    if (need > ix.cap_blob) {
-        if ((e = regrow(ix.blob, need + need / 8)) != cudaSuccess) return e;
-        ix.cap_blob = need + need / 8;
-    }
+    if (!make_layout_flat(nt.N, nt.W, &layP)) return cudaSuccess; // direct path only
     if (layP.blob_bytes > ix.cap_blobP) {
         const size_t cap = (size_t)layP.blob_bytes + layP.blob_bytes / 8;
         if ((e = regrow(ix.blobP, cap)) != cudaSuccess) return e;
         ix.cap_blobP = cap;
     }
-    if (fmt32) k_build_tile32<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
-    else k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
-    g_launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ix.rows_valid = false;
+    if (use_rows_kernel()) {
+        RowsLayout lr{};
+        if (!make_layout_rows(nt.N, nt.W, &lr)) return cudaSuccess; // direct path only
+        const size_t need = (size_t)lr.ncb * lr.cb_stride;
+        if (need > ix.cap_blobR) {
+            if ((e = regrow(ix.blobR, need + need / 8)) != cudaSuccess) return e;
+            ix.cap_blobR = need + need / 8;
+        }
+        const size_t need_rank = (size_t)lr.ncb * lr.n_thr * 2 * RW_TILES;
+        if (need_rank > ix.cap_rank) {
+            const size_t cap = need_rank + need_rank / 8;
+            if ((e = regrow(ix.rank, cap)) != cudaSuccess) return e;
+            ix.cap_rank = cap;
+        }
+        const size_t need_ts = 2ull * lr.ncb * RW_TILES * BP_TILE;
+        if (need_ts > ix.cap_tsorted) {
+            if ((e = regrow(ix.tile_sorted, need_ts + need_ts / 8)) != cudaSuccess) return e;
+            ix.cap_tsorted = need_ts + need_ts / 8;
+        }
+        k_build_cbtile<<<lr.ncb * RW_TILES, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.blobR, lr, ix.tile_sorted);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        k_build_ranks<<<dim3((lr.n_thr + 255) / 256, lr.ncb), 256, 0, st>>>(ix.tile_sorted, lr, ix.rank);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ix.lay_r = lr;
+        ix.rows_valid = true;
+        lay.nt = RW_TILES; // bitpar_profitable: (pod, tile) items
+        lay.ncb = lr.ncb;
+    } else {
+        if (!make_layout_smem(nt.N, nt.W, &lay)) return cudaSuccess; // direct path only
+        const size_t need = (size_t)lay.ncb * lay.blob_bytes;
+        if (need > ix.cap_blob) {
+            if ((e = regrow(ix.blob, need + need / 8)) != cudaSuccess) return e;
+            ix.cap_blob = need + need / 8;
+        }
+        k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ord_idx, ix.blobP, layP);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ix.lay = lay;
     ix.layP = layP;
     ix.valid = true;
+    ix.epoch = g_regrow_epoch.load();
     return cudaSuccess;
 }
 
@@ -1203,17 +1234,11 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
 
 template <int W>
 static cudaError_t set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(k_mask_bitpar<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_bitpar2<W, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_bitpar2<W, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1240,8 +1265,7 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = regrow(ix.pod_loc, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_s, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.pid_s, cap)) != cudaSuccess) return e;
-        if (bp_variant() >= 2)
-            if ((e = regrow(ix.plist_s, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rec_s, cap + 8)) != cudaSuccess) return e;
         ix.cap_pods = cap;
         ix.cap_sel = 0;
     }
@@ -1252,6 +1276,7 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
     }
     if (!ix.hist)
         if ((e = regrow(ix.hist, 65536 + 64)) != cudaSuccess) return e; // bins + chunk totals
+    ix.epoch = g_regrow_epoch.load();
     return cudaSuccess;
 }
 
@@ -1329,32 +1354,38 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, ix.hist + 65536);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        k_pod_scatter<W><<<(P + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.pod_ranks, ix.hist, ix.hist + 65536, n_chunks,
-                                                                ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s);
+        const bool rows = ix.rows_valid;
+        k_pod_scatter<W><<<(((P + 7u) & ~7u) + 255) / 256, 256, 0, L.stream>>>(
+            L.pv, ix.pod_ranks, ix.hist, ix.hist + 65536, n_chunks, ix.pod_bin, ix.pod_loc, rows ? nullptr : ix.rk_s,
+            ix.pid_s, ix.sel_s, rows ? ix.rec_s : nullptr);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
         const uint32_t n_groups = (P + 7) / 8;
-        uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
-        ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
-        const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
-        if (bp_variant() >= 2) { // experimental, see k_mask_bitpar2: 2, 3, 4 = count mode 0, 1, 2; 5 = mode 2 + 32-position format
-            k_pod_pair_list<W><<<(P + 255) / 256, 256, 0, L.stream>>>(ix.sel_s, P, ix.lay.pstride, ix.plist_s);
-            g_launches++;
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if (before_mask) // time the mask kernel alone
-                if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-            auto kern2 = bp_variant() == 2   ? k_mask_bitpar2<W, 0, 0>
-                         : bp_variant() == 3 ? k_mask_bitpar2<W, 1, 0>
-                         : bp_variant() == 4 ? k_mask_bitpar2<W, 2, 0>
-                                             : k_mask_bitpar2<W, 2, 1>;
-            kern2<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, ix.plist_s, L.ov,
-                                                                     ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
+        if (rows) {
+            const uint32_t GS = (n_groups + RW_STRATA - 1) / RW_STRATA;
+            const uint64_t F = (uint64_t)RW_STRATA * GS * ix.lay_r.ncb;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + 31) / 32);
+            auto kern = rows_count_mode() ? k_mask_rows<W, W <= 4, 1> : k_mask_rows<W, W <= 4, 0>;
+            RowsParams prm;
+            prm.blob = ix.blobR;
+            prm.lay = ix.lay_r;
+            prm.rank = ix.rank;
+            prm.rec_s = ix.rec_s;
+            prm.sel_s = ix.sel_s;
+            prm.n_groups = n_groups;
+            prm.GS = GS;
+            prm.mask = L.ov.mask;
+            prm.row_words = (uint32_t)L.ov.mask_row_words;
+            prm.cnt = L.ov.cnt;
+            kern<<<grid, BP_THREADS, ix.lay_r.smem_bytes, L.stream>>>(prm);
         } else {
-            auto kern = bp_variant() ? k_mask_bitpar<W, true> : k_mask_bitpar<W, false>;
-            kern<<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov,
-                                                                    ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
+            uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
+            ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
+            const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
+            k_mask_bitpar<W, true><<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(
+                ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov, ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
         }
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

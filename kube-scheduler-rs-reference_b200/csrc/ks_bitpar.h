@@ -6,8 +6,11 @@
 // prefix table indexed by the tile-local rank of the threshold, and the tile-local rank is
 //   base[bucket][tile] + popc(member[bucket][tile] & lowmask)
 // (bucket = 64 consecutive global positions).  Label selectors are ANDs of per-(key,value) node columns.
-// One thread produces 256 cells (8 mask words) with ~100 instructions; the design target is the HBM write of the
-// mask (measured: 53-60 % of it).  KS_SCORE_LEFTOVER is separable (node part - pod part), so argmax-score is the first
+// Round 2 ("rows" kernel, the default): the tile-local rank of every possible threshold is tabulated once per
+// snapshot ([column block][threshold][tile] u16, read through L1/L2), the prefix tables are octet-interleaved
+// (row r of the 8 tiles of a column block = one 256-byte line, conflict-free whatever the ranks are), and one pod
+// takes 8 lanes = 8 tiles = 256 contiguous bytes of its mask row: ~50 instructions per 256 cells.
+// KS_SCORE_LEFTOVER is separable (node part - pod part), so argmax-score is the first
 // feasible node in a static priority order: a short early-exit scan per pod (k_first_fit).
 #pragma once
 #include "ks_internal.cuh"
@@ -27,6 +30,25 @@ struct BitparLayout { // byte offsets inside one column-block blob
     uint32_t off_baseC, off_membC, off_baseM, off_membM, off_tabC, off_tabM, off_pairs;
     uint32_t pstride;  // bytes between two label-pair columns
     uint32_t blob_bytes;
+};
+
+// "rows" format: column block = 8 tiles (2048 nodes).  One blob per column block:
+//   tabC [257 rows][256 B], tabM [257 rows][256 B], pairs [64*W bits][256 B]
+// and every 256-byte line is [half 0 of tiles 0..7 | half 1 of tiles 0..7] (16 B each): lane t of an 8-lane
+// shared-memory phase reads granule t of its own row -> 8 distinct bank groups for any ranks.
+constexpr uint32_t RW_TILES = 8;                            // tiles per column block
+constexpr uint32_t RW_LINE = 256;                           // bytes per table row / pair column of a column block
+constexpr uint32_t RW_TAB_BYTES = (uint32_t)BP_ROWS * RW_LINE; // 65792
+constexpr uint32_t RW_STRATA = 32;                          // the sorted pod list is dealt to the warps in 32 strata
+
+struct RowsLayout {
+    uint32_t ncb;        // column blocks
+    uint32_t n_tiles;    // ceil(N / 256)
+    uint32_t off_tabC, off_tabM, off_pairs; // byte offsets inside a column-block blob
+    uint32_t smem_bytes; // bytes staged in shared memory (tables, + pair columns when they fit)
+    uint32_t cb_stride;  // bytes between two column-block blobs in global memory
+    uint32_t pairs_smem; // 1 = the pair columns are staged with the tables, 0 = read through L1/L2 (W = 8)
+    uint32_t n_thr;      // thresholds per column block in the rank tables: N + 1
 };
 
 struct BitparIndex {
@@ -49,7 +71,14 @@ struct BitparIndex {
     uint2* rk_s = nullptr;         // pods in bucket order: thresholds, original pod index, selector words
     uint32_t* pid_s = nullptr;
     unsigned long long* sel_s = nullptr;
-    uint2* plist_s = nullptr;      // experimental variant 2 only: <= 4 label-pair column offsets per sorted pod
+    uint4* rec_s = nullptr;        // rows kernel: {threshold_cpu, threshold_mem, pod index, selector columns} per sorted pod
+    uint8_t* blobR = nullptr;      // rows kernel: lay_r.ncb column-block blobs
+    uint16_t* rank = nullptr;      // rows kernel: [cb][threshold g][resource][tile] = nodes of the tile at sorted positions < g
+    uint32_t* tile_sorted = nullptr; // build scratch: per tile, its nodes' global positions in ascending order
+    size_t cap_blobR = 0, cap_rank = 0, cap_tsorted = 0;
+    RowsLayout lay_r{};
+    bool rows_valid = false;
+    uint64_t epoch = 0;            // bumped whenever a device buffer of the index is reallocated (CUDA-graph cache key)
     uint32_t* hist = nullptr;      // [65536] bucket histogram -> exclusive scan
     uint32_t* rk_hist = nullptr;   // node sample sort scratch: [3][256] bucket counts, splitters, per-node bucket / slot, lists
     int64_t* rk_spl_v = nullptr;

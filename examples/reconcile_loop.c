@@ -49,9 +49,9 @@ int main(int argc, char** argv) {
     const ks_container_obj c_b1[] = {{1, 2, r_b1}}, c_b2[] = {{1, 2, r_b2}}, c_b3[] = {{1, 2, r_b3}, {1, 2, r_b3}},
                            c_b4[] = {{1, 2, r_b4}}, c_b5[] = {{1, 2, r_b5}};
     const ks_pod_obj bound[N_BOUND] = {
-        {"default", "b1", 1, "n1", 1, c_b1, 0, 0, NULL}, {"default", "b2", 1, "n2", 1, c_b2, 0, 0, NULL},
-        {"default", "b3", 1, "n2", 2, c_b3, 0, 0, NULL}, {"default", "b4", 1, "n3", 1, c_b4, 0, 0, NULL},
-        {"default", "b5", 1, "n4", 1, c_b5, 0, 0, NULL},
+        {"default", "b1", 1, "n1", 1, c_b1, 0, 0, NULL, NULL}, {"default", "b2", 1, "n2", 1, c_b2, 0, 0, NULL, NULL},
+        {"default", "b3", 1, "n2", 2, c_b3, 0, 0, NULL, NULL}, {"default", "b4", 1, "n3", 1, c_b4, 0, 0, NULL, NULL},
+        {"default", "b5", 1, "n4", 1, c_b5, 0, 0, NULL, NULL},
     };
 
     /* pending pods (the Controller's queue) */
@@ -68,11 +68,12 @@ int main(int argc, char** argv) {
                            c5[] = {{1, 2, r5}}, c6[] = {{1, 2, r6}}, c7[] = {{1, 2, r7a}, {1, 2, r7b}},
                            c8[] = {{1, 2, r8}}, c9[] = {{0, 0, NULL}}; /* limits only: no requests */
     const ks_pod_obj pods[N_PODS] = {
-        {"default", "p0", 1, NULL, 0, NULL, 0, 0, NULL},     {"default", "p1", 1, NULL, 1, c1, 1, 1, zone_a},
-        {"default", "p2", 1, NULL, 1, c2, 0, 0, NULL},       {"default", "p3", 1, NULL, 1, c3, 0, 0, NULL},
-        {"default", "p4", 1, NULL, 1, c4, 1, 1, zone_b},     {"default", "p5", 1, NULL, 1, c5, 0, 0, NULL},
-        {"default", "p6", 1, NULL, 1, c6, 0, 0, NULL},       {"default", "p7", 1, NULL, 2, c7, 0, 0, NULL},
-        {"default", "p8", 1, NULL, 1, c8, 0, 0, NULL},       {"default", "p9", 1, "n0", 1, c9, 0, 0, NULL}, /* already bound */
+        {"default", "p0", 1, NULL, 0, NULL, 0, 0, NULL, NULL},     {"default", "p1", 1, NULL, 1, c1, 1, 1, zone_a, NULL},
+        {"default", "p2", 1, NULL, 1, c2, 0, 0, NULL,
+         "{\"name\":\"p2\",\"namespace\":\"default\",\"uid\":\"0b5e\",\"labels\":{\"app\":\"web\"}}"},       {"default", "p3", 1, NULL, 1, c3, 0, 0, NULL, NULL},
+        {"default", "p4", 1, NULL, 1, c4, 1, 1, zone_b, NULL},     {"default", "p5", 1, NULL, 1, c5, 0, 0, NULL, NULL},
+        {"default", "p6", 1, NULL, 1, c6, 0, 0, NULL, NULL},       {"default", "p7", 1, NULL, 2, c7, 0, 0, NULL, NULL},
+        {"default", "p8", 1, NULL, 1, c8, 0, 0, NULL, NULL},       {"default", "p9", 1, "n0", 1, c9, 0, 0, NULL, NULL}, /* already bound */
     };
 
     ksh_context* ctx = NULL;

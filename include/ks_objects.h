@@ -46,6 +46,9 @@ typedef struct ks_pod_obj {
     int32_t has_node_selector;
     uint32_t n_selector;
     const ks_kv* selector;
+    const char* metadata_json; /* optional: the pod's whole ObjectMeta, pre-serialised by the caller as one JSON object
+                                  ("{...}").  The reference sends `metadata: pod.metadata.clone()` in the Binding
+                                  (src/main.rs:88-91); when set, ksh_reconcile emits it verbatim, else {name, namespace}. */
 } ks_pod_obj;
 
 typedef struct ks_node_obj {

@@ -74,6 +74,24 @@ typedef struct ks_pods { /* SoA view of P pending pods (what total_pod_resources
     int32_t mem_space;       /* KS_MEM_HOST or KS_MEM_DEVICE for the three arrays above */
 } ks_pods;
 
+/* ---- multi-GPU exchange of the bindings (one process per GPU, pods sharded) ----
+ * The reference has no multi-process story; north_star asks for ONE all-gather of the per-pod bindings.  Here the
+ * all-gather is fused into the argmax kernels: every binding is stored into the local output AND into every peer's
+ * gather buffer through peer-mapped (CUDA IPC) pointers over NVLink, then one flag per (source, destination) pair is
+ * released; ks_select ends with a wait on this rank's flags, so when the call's stream work is done the gather
+ * buffer holds the bindings of every rank.  No collective library call is on the data path.
+ * All pointers are DEVICE pointers valid in the calling process (peer_* ones were opened with ks_ipc_open). */
+#define KS_MAX_PEERS 15u
+typedef struct ks_exchange {
+    uint32_t world, rank;                 /* ranks taking part, this rank */
+    uint32_t n_peers;                     /* = world - 1 */
+    int32_t* peer_node_idx[KS_MAX_PEERS]; /* where THIS rank's node_idx[0..n) goes in peer k's gather buffer */
+    int64_t* peer_score[KS_MAX_PEERS];    /* same for score */
+    uint32_t* peer_flag[KS_MAX_PEERS];    /* peer k's arrival flag for THIS rank */
+    uint32_t* local_flags;                /* this rank's flags [world]; entry r is written by rank r */
+    uint32_t* local_state;                /* this rank's private words [2]: step sequence number, CTA counter (zeroed) */
+} ks_exchange;
+
 typedef struct ks_bindings { /* outputs; any pointer may be NULL to skip that output */
     int32_t* node_idx;       /* [n] argmax-score feasible node, ties -> lowest index, -1 = NoNodeFound */
     int64_t* score;          /* [n] score of node_idx (0 when -1) */
@@ -85,6 +103,7 @@ typedef struct ks_bindings { /* outputs; any pointer may be NULL to skip that ou
     void* bindings_ready_event; /* optional cudaEvent_t (NULL = none), device-space outputs only: recorded as soon as
                                    node_idx and score are final - on the bit-parallel path that is well before the
                                    mask/count pass ends, so a collective over the bindings can overlap it */
+    const ks_exchange* exchange; /* optional (NULL = none), device-space outputs only: fused all-gather, see above */
 } ks_bindings;
 
 const char* ks_last_error(void);
@@ -107,6 +126,19 @@ int ks_snapshot_apply_bind(ks_snapshot* s, int32_t node_idx, int64_t req_cpu, in
 int ks_snapshot_get_free(ks_snapshot* s, int64_t* free_cpu, int64_t* free_mem); /* D2H, [n_nodes] each */
 uint32_t ks_snapshot_num_nodes(const ks_snapshot* s);
 uint32_t ks_snapshot_label_words(const ks_snapshot* s);
+
+/* ---- device memory that other processes of the node can map (CUDA IPC), for ks_exchange ----
+ * ks_ipc_alloc: cudaMalloc + zero fill on `device`; out_handle receives the 64-byte cudaIpcMemHandle_t to send to the
+ * peers (any byte transport: torch.distributed, MPI, a file).  ks_ipc_open maps a peer's allocation into this process
+ * (peer access between the two GPUs is enabled by the runtime).  ks_ipc_close / ks_ipc_free undo them. */
+/* after a run of ks_select calls with an exchange: synchronises the device and reports whether any wait timed out */
+int ks_exchange_check(ks_snapshot* s);
+int ks_ipc_alloc(int device, uint64_t bytes, void** out_ptr, uint8_t out_handle[64]);
+int ks_ipc_open(int device, const uint8_t handle[64], void** out_ptr);
+int ks_ipc_close(int device, void* ptr);
+int ks_ipc_free(int device, void* ptr);
+/* synchronising device-to-host copy of `bytes` bytes (reading a gather buffer allocated with ks_ipc_alloc) */
+int ks_device_read(int device, const void* dev_ptr, void* host_ptr, uint64_t bytes);
 
 /* ---- per-cell entry = check_node_validity (src/predicates.rs:63-77) ---- */
 int ks_check_cell(ks_snapshot* s, int64_t req_cpu, int64_t req_mem, const uint64_t* sel, uint32_t node_idx);

@@ -34,10 +34,19 @@ class ks_pods(C.Structure):
                 ("mem_space", C.c_int32)]
 
 
+KS_MAX_PEERS = 15
+
+
+class ks_exchange(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("n_peers", C.c_uint32),
+                ("peer_node_idx", C.c_void_p * KS_MAX_PEERS), ("peer_score", C.c_void_p * KS_MAX_PEERS),
+                ("peer_flag", C.c_void_p * KS_MAX_PEERS), ("local_flags", C.c_void_p), ("local_state", C.c_void_p)]
+
+
 class ks_bindings(C.Structure):
     _fields_ = [("node_idx", C.c_void_p), ("score", C.c_void_p), ("feasible_cnt", C.c_void_p),
                 ("mem_space", C.c_int32), ("mask", C.c_void_p), ("mask_row_bytes", C.c_uint64),
-                ("mask_space", C.c_int32), ("bindings_ready_event", C.c_void_p)]
+                ("mask_space", C.c_int32), ("bindings_ready_event", C.c_void_p), ("exchange", C.POINTER(ks_exchange))]
 
 
 def _proto(name, restype, *argtypes):
@@ -69,6 +78,12 @@ _proto("ks_snapshot_commit_claims", C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
 _proto("ks_stream_bind", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_int, C.c_void_p, C.c_void_p,
        C.POINTER(C.c_uint32))
 
+_proto("ks_exchange_check", C.c_int, C.c_void_p)
+_proto("ks_ipc_alloc", C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p)
+_proto("ks_ipc_open", C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p))
+_proto("ks_ipc_close", C.c_int, C.c_int, C.c_void_p)
+_proto("ks_ipc_free", C.c_int, C.c_int, C.c_void_p)
+_proto("ks_device_read", C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
 _proto("ks_select_sampling", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p,
        C.c_void_p, C.c_void_p, C.c_void_p)
 KS_REFERENCE_ATTEMPTS = 5

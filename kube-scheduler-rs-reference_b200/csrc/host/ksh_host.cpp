@@ -9,6 +9,7 @@
 #include <new>
 #include <string>
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <thread>
@@ -24,6 +25,11 @@ int fail(int code, const std::string& msg) {
     ks__set_error(msg.c_str());
     return code;
 }
+
+// Nothing may throw across the C ABI (ksched_host.h): every extern "C" entry point is a function-try-block ending here
+#define KSH_CATCH                                                                                   \
+    catch (const std::bad_alloc&) { return fail(KS_ERR_NOMEM, "out of host memory in the host layer"); } \
+    catch (...) { return fail(KS_ERR_INVALID, "unexpected C++ exception in the host layer"); }
 
 typedef unsigned __int128 u128;
 
@@ -293,9 +299,22 @@ static unsigned parallel_ranges(uint64_t n, uint64_t min_per_thread, F f) {
     std::vector<std::thread> th;
     th.reserve(T - 1);
     const uint64_t per = (n + T - 1) / T;
-    for (unsigned t = 1; t < T; t++) th.emplace_back([=, &f] { f(t, std::min(n, t * per), std::min(n, (t + 1) * per)); });
-    f(0u, (uint64_t)0, std::min(n, per));
+    std::atomic<bool> oom{false}; // an exception must not leave a worker thread: it is re-raised after the join
+    for (unsigned t = 1; t < T; t++)
+        th.emplace_back([=, &f, &oom] {
+            try {
+                f(t, std::min(n, t * per), std::min(n, (t + 1) * per));
+            } catch (...) {
+                oom = true;
+            }
+        });
+    try {
+        f(0u, (uint64_t)0, std::min(n, per));
+    } catch (...) {
+        oom = true;
+    }
     for (auto& x : th) x.join();
+    if (oom) throw std::bad_alloc();
     return T;
 }
 
@@ -551,11 +570,21 @@ static int64_t btab_slot_of_pos(const ksh_context* c, size_t pos) {
     }
 }
 
-// append a bound pod; a tracked key that is already present is re-pointed to the new row (last one wins, as a map would)
+static void bound_erase(ksh_context* c, size_t pos);
+
+// append a bound pod; a tracked key that is already present REPLACES its row (last one wins, as a map would): the old
+// row is removed so its requests are no longer charged, and the device copy is re-uploaded from the host truth
 static void bound_push(ksh_context* c, const ks_pod_obj* pod, uint64_t h, size_t lns, size_t lname, int32_t node, int64_t cpu,
                        int64_t mem) {
-    const size_t pos = c->bnode.size();
     const bool tracked = lns + lname > 0; // a pod without namespace and name cannot be addressed by later events
+    if (tracked) {
+        const int64_t old = btab_find_slot(c, h, pod, lns, lname);
+        if (old >= 0) {
+            bound_erase(c, slot_low(c->btab.slots[(size_t)old]) - 2);
+            c->dirty = true;
+        }
+    }
+    const size_t pos = c->bnode.size();
     c->bnode.push_back(node);
     c->bcpu.push_back(cpu);
     c->bmem.push_back(mem);
@@ -667,6 +696,43 @@ static int grow_dictionary(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
             }
         }
     });
+    // Room check first.  The dictionary only has to cover the pairs THIS batch names (node columns are re-uploaded
+    // whenever it changes), so when the pairs accumulated over the context's lifetime leave no room - e.g. hostname
+    // selectors across more than 511 nodes over time - it is rebuilt from the current batch instead of failing.
+    {
+        std::vector<uint32_t> fresh;
+        std::vector<uint8_t> seen(c->pairs.size(), 0);
+        for (const auto& v : need)
+            for (uint32_t pid : v)
+                if (!seen[pid]) {
+                    seen[pid] = 1;
+                    fresh.push_back(pid);
+                }
+        if (words_for_bits((uint32_t)(c->bit2pair.size() + fresh.size())) > KS_MAX_LABEL_WORDS) {
+            compact_dictionary(c);
+            if (words_for_bits((uint32_t)(c->bit2pair.size() + fresh.size())) > KS_MAX_LABEL_WORDS) {
+                for (uint32_t pid : c->bit2pair) c->pair_bit[pid] = -1;
+                c->bit2pair.clear();
+                c->dirty = true;
+                std::fill(seen.begin(), seen.end(), 0);
+                for (uint64_t p = 0; p < n; p++) { // rare path: serial re-scan, every live pair of the batch
+                    const ks_pod_obj& pod = pods[p];
+                    if (!(pod.has_spec && pod.has_node_selector)) continue;
+                    for (uint32_t i = 0; i < pod.n_selector; i++) {
+                        const int64_t pid = c->pairs.find(nz(pod.selector[i].key), '\0', nz(pod.selector[i].val));
+                        if (pid < 0 || c->pair_refcnt[(size_t)pid] == 0 || seen[(size_t)pid]) continue;
+                        seen[(size_t)pid] = 1;
+                        if (words_for_bits((uint32_t)c->bit2pair.size() + 1) > KS_MAX_LABEL_WORDS)
+                            return fail(KS_ERR_RANGE, "one batch names more than 511 distinct (key,value) pairs that nodes carry: split the batch");
+                        c->pair_bit[(size_t)pid] = (int32_t)c->bit2pair.size();
+                        c->bit2pair.push_back((uint32_t)pid);
+                    }
+                }
+                update_words(c);
+                return KS_OK;
+            }
+        }
+    }
     for (const auto& v : need)
         for (uint32_t pid : v) {
             const int rc = assign_bit(c, pid);
@@ -704,30 +770,33 @@ static int pack_rows(const ksh_context* c, const ks_pod_obj* pods, uint64_t n, i
 
 extern "C" {
 
-int ksh_parse_cpu_millicores(const char* q, int64_t* out) {
+int ksh_parse_cpu_millicores(const char* q, int64_t* out) try {
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");
     std::string err;
     const int rc = parse_cpu(q, out, &err);
     return rc ? fail(rc, err) : KS_OK;
 }
+KSH_CATCH
 
-int ksh_parse_memory_bytes(const char* q, int64_t* out) {
+int ksh_parse_memory_bytes(const char* q, int64_t* out) try {
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");
     std::string err;
     const int rc = parse_mem(q, out, &err);
     return rc ? fail(rc, err) : KS_OK;
 }
+KSH_CATCH
 
-int ksh_total_pod_resources(const ks_pod_obj* pod, int64_t* cpu, int64_t* mem) {
+int ksh_total_pod_resources(const ks_pod_obj* pod, int64_t* cpu, int64_t* mem) try {
     if (!pod || !cpu || !mem) return fail(KS_ERR_INVALID, "NULL argument");
     std::string err;
     const int rc = total_pod_resources(pod, cpu, mem, &err);
     return rc ? fail(rc, err) : KS_OK;
 }
+KSH_CATCH
 
 int ksh_is_pod_bound(const ks_pod_obj* pod) { return pod && pod->has_spec && pod->node_name != nullptr; } // util.rs:38-45
 
-int ksh_context_create(int device, ksh_context** out) {
+int ksh_context_create(int device, ksh_context** out) try {
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");
     *out = nullptr;
     ksh_context* c = new (std::nothrow) ksh_context();
@@ -742,6 +811,7 @@ int ksh_context_create(int device, ksh_context** out) {
     *out = c;
     return KS_OK;
 }
+KSH_CATCH
 
 void ksh_context_destroy(ksh_context* c) {
     if (!c) return;
@@ -766,7 +836,7 @@ uint64_t ksh_context_num_bound(const ksh_context* c) {
 }
 
 int ksh_context_export_packed(const ksh_context* c, int64_t* alloc_cpu, int64_t* alloc_mem, uint64_t* labels,
-                              int32_t* bound_node, int64_t* bound_cpu, int64_t* bound_mem) {
+                              int32_t* bound_node, int64_t* bound_cpu, int64_t* bound_mem) try {
     if (!c) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (c->N && (!alloc_cpu || !alloc_mem || !labels)) return fail(KS_ERR_INVALID, "NULL node array");
@@ -783,6 +853,7 @@ int ksh_context_export_packed(const ksh_context* c, int64_t* alloc_cpu, int64_t*
     }
     return KS_OK;
 }
+KSH_CATCH
 
 ks_snapshot* ksh_context_snapshot(ksh_context* c) {
     if (!c) return nullptr;
@@ -791,7 +862,7 @@ ks_snapshot* ksh_context_snapshot(ksh_context* c) {
     return c->snap;
 }
 
-int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) {
+int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) try {
     if (!c || (n && !nodes)) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     // validate first (quantities parsed by all host threads), then replace
@@ -844,8 +915,9 @@ int ksh_context_set_nodes(ksh_context* c, const ks_node_obj* nodes, uint32_t n) 
     c->dirty = true;
     return KS_OK;
 }
+KSH_CATCH
 
-int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* out_idx) {
+int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* out_idx) try {
     if (!c || !node) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     int64_t ac, am;
@@ -874,8 +946,9 @@ int ksh_context_upsert_node(ksh_context* c, const ks_node_obj* node, uint32_t* o
     if (out_idx) *out_idx = idx;
     return KS_OK;
 }
+KSH_CATCH
 
-int ksh_context_remove_node(ksh_context* c, const char* name) {
+int ksh_context_remove_node(ksh_context* c, const char* name) try {
     if (!c || !name) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     const int32_t found = node_index_of(c, name);
@@ -907,8 +980,9 @@ int ksh_context_remove_node(ksh_context* c, const char* name) {
     c->dirty = true;
     return KS_OK;
 }
+KSH_CATCH
 
-int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
+int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) try {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (!ksh_is_pod_bound(pod)) return KS_OK;
@@ -929,8 +1003,9 @@ int ksh_context_pod_bound(ksh_context* c, const ks_pod_obj* pod) {
     c->dirty = true;
     return KS_OK;
 }
+KSH_CATCH
 
-int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
+int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) try {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     size_t lns, lname;
@@ -943,6 +1018,7 @@ int ksh_context_pod_deleted(ksh_context* c, const ks_pod_obj* pod) {
     c->dirty = true;
     return KS_OK;
 }
+KSH_CATCH
 
 const char* ksh_context_node_name(const ksh_context* c, uint32_t idx) {
     if (!c) return nullptr;
@@ -950,7 +1026,7 @@ const char* ksh_context_node_name(const ksh_context* c, uint32_t idx) {
     return idx < c->N ? c->names.str(c->idx2nameid[idx]) : nullptr;
 }
 
-int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
+int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n) try {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n > 0xFFFFFFF0ull) return fail(KS_ERR_RANGE, "too many pods");
@@ -1003,9 +1079,10 @@ int ksh_context_set_cluster_pods(ksh_context* c, const ks_pod_obj* pods, uint64_
     c->dirty = true;
     return KS_OK;
 }
+KSH_CATCH
 
 int ksh_pack_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* req_cpu, int64_t* req_mem,
-                  uint64_t* sel, uint32_t stride) {
+                  uint64_t* sel, uint32_t stride) try {
     if (!c || (n && (!pods || !req_cpu || !req_mem || !sel))) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     int rc = grow_dictionary(c, pods, n);
@@ -1015,6 +1092,7 @@ int ksh_pack_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* r
     if (rc) return rc;
     return (int)c->W;
 }
+KSH_CATCH
 
 static int pack_and_upload(ksh_context* c, const ks_pod_obj* pods, uint64_t n, std::vector<int64_t>& rc_, std::vector<int64_t>& rm_,
                            std::vector<uint64_t>& sel) {
@@ -1028,7 +1106,7 @@ static int pack_and_upload(ksh_context* c, const ks_pod_obj* pods, uint64_t n, s
     return upload(c);
 }
 
-int ksh_check_node_validity(ksh_context* c, const ks_pod_obj* pod, uint32_t node_idx) {
+int ksh_check_node_validity(ksh_context* c, const ks_pod_obj* pod, uint32_t node_idx) try {
     if (!c || !pod) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (node_idx >= c->N) return fail(KS_ERR_INVALID, "node index out of range");
@@ -1038,9 +1116,10 @@ int ksh_check_node_validity(ksh_context* c, const ks_pod_obj* pod, uint32_t node
     if (rc) return rc;
     return ks_check_cell(c->snap, rc_[0], rm_[0], sel.data(), node_idx);
 }
+KSH_CATCH
 
 int ksh_select_nodes(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int policy, int32_t* out_node_idx,
-                     int64_t* out_score, uint32_t* out_cnt) {
+                     int64_t* out_score, uint32_t* out_cnt) try {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n == 0) return KS_OK;
@@ -1049,13 +1128,14 @@ int ksh_select_nodes(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int pol
     int rc = pack_and_upload(c, pods, n, rc_, rm_, sel);
     if (rc) return rc;
     ks_pods kp{n, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
-    ks_bindings kb{out_node_idx, out_score, out_cnt, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr};
+    ks_bindings kb{out_node_idx, out_score, out_cnt, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr, nullptr};
     return ks_select(c->snap, &kp, policy, KS_SELECT_AUTO, &kb, nullptr);
 }
+KSH_CATCH
 
 int ksh_select_node_for_pod(ksh_context* c, const ks_pod_obj* pods, uint64_t n, uint32_t attempts, uint64_t seed,
                             uint64_t first_pod_index, int32_t* out_node_idx, uint32_t* out_attempts,
-                            int32_t* out_draw_node, uint8_t* out_draw_code) {
+                            int32_t* out_draw_node, uint8_t* out_draw_code) try {
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n == 0) return KS_OK;
@@ -1067,26 +1147,48 @@ int ksh_select_node_for_pod(ksh_context* c, const ks_pod_obj* pods, uint64_t n, 
     return ks_select_sampling(c->snap, &kp, attempts, seed, first_pod_index, out_node_idx, out_attempts, out_draw_node,
                               out_draw_code);
 }
+KSH_CATCH
+
+// A pod that comes back to reconcile() unbound although this context bound it earlier (the caller's POST failed or
+// raced, error_policy requeued it - src/main.rs:105-108,122-125): the reference's next LIST would not show it, so
+// the earlier charge is dropped before the new selection.  Returns true if a row was released.
+static bool release_earlier_binding(ksh_context* c, const ks_pod_obj* pod) {
+    size_t lns, lname;
+    const uint64_t h = pod_key_hash(pod, &lns, &lname);
+    if (lns + lname == 0) return false;
+    const int64_t slot = btab_find_slot(c, h, pod, lns, lname);
+    if (slot < 0) return false;
+    bound_erase(c, slot_low(c->btab.slots[(size_t)slot]) - 2);
+    c->dirty = true; // the device's free[] still carries the old charge: re-upload before the next evaluation
+    return true;
+}
 
 // corev1::Binding{metadata, target: ObjectReference{name}}  (src/main.rs:83-91), the body of
 // POST /api/v1/namespaces/{ns}/pods/{name}/binding
 static std::string binding_body(const ksh_context* c, const ks_pod_obj* pod, uint32_t node_idx) {
-    std::string s = "{\"apiVersion\":\"v1\",\"kind\":\"Binding\",\"metadata\":{\"name\":\"";
-    json_escape(s, pod->name);
-    s += "\",\"namespace\":\"";
-    json_escape(s, pod->ns);
-    s += "\"},\"target\":{\"name\":\"";
+    std::string s = "{\"apiVersion\":\"v1\",\"kind\":\"Binding\",\"metadata\":";
+    if (pod->metadata_json && pod->metadata_json[0]) { // src/main.rs:88: metadata: pod.metadata.clone()
+        s += pod->metadata_json;
+    } else {
+        s += "{\"name\":\"";
+        json_escape(s, pod->name);
+        s += "\",\"namespace\":\"";
+        json_escape(s, pod->ns);
+        s += "\"}";
+    }
+    s += ",\"target\":{\"name\":\"";
     json_escape(s, ksh_context_node_name(c, node_idx));
     s += "\"}}";
     return s;
 }
 
-int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* json, size_t cap) {
+int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* node_idx, char* json, size_t cap) try {
     if (!c || !pod || !node_idx) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     *node_idx = -1;
     if (json && cap) json[0] = '\0';
     if (ksh_is_pod_bound(pod)) return KSH_RECONCILE_OK; // src/main.rs:74-76
+    release_earlier_binding(c, pod);
     int32_t idx = -1;
     int rc = ksh_select_nodes(c, pod, 1, policy, &idx, nullptr, nullptr); // src/main.rs:78
     if (rc) return rc;
@@ -1100,7 +1202,10 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
     if (rc) return rc;
     // what the next LIST would report once the binding is accepted (src/predicates.rs:34 after src/main.rs:103)
     rc = ks_snapshot_apply_bind(c->snap, idx, cpu, mem);
-    if (rc) return rc;
+    if (rc) {
+        c->dirty = true; // the device may or may not carry the bind: re-upload from the host truth next time
+        return rc;
+    }
     {
         size_t lns, lname;
         const uint64_t h = pod_key_hash(pod, &lns, &lname);
@@ -1110,11 +1215,12 @@ int ksh_reconcile(ksh_context* c, const ks_pod_obj* pod, int policy, int32_t* no
     if (json && cap) std::snprintf(json, cap, "%s", binding_body(c, pod, (uint32_t)idx).c_str());
     return KSH_RECONCILE_OK;
 }
+KSH_CATCH
 
 // reconcile() for a drained queue: one pack, one micro-batch loop on the device (select -> claims resolved in array order ->
 // losers re-selected against what is left), then the host-side commit of every bind (what the next LIST would show)
 int ksh_reconcile_batch(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int policy, int32_t* out_status, int32_t* out_node_idx,
-                        char* json, size_t cap, int64_t* out_json_off, uint32_t* out_rounds) {
+                        char* json, size_t cap, int64_t* out_json_off, uint32_t* out_rounds) try {
     if (!c || (n && (!pods || !out_status || !out_node_idx))) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (out_rounds) *out_rounds = 0;
@@ -1129,6 +1235,7 @@ int ksh_reconcile_batch(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int 
             out_status[i] = KSH_RECONCILE_BINDING_OBJECT_FAILED; // reference: unwrap panic, src/main.rs:80
         } else {
             out_status[i] = KSH_RECONCILE_NO_NODE_FOUND; // until bound below (src/main.rs:116-118)
+            release_earlier_binding(c, &pods[i]);
             todo.push_back(i);
             sub.push_back(pods[i]);
         }
@@ -1141,7 +1248,10 @@ int ksh_reconcile_batch(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int 
     std::vector<int32_t> idx(sub.size(), -1);
     ks_pods kp{sub.size(), rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
     rc = ks_stream_bind(c->snap, &kp, policy, idx.data(), nullptr, out_rounds); // commits capacity on the device
-    if (rc) return rc;
+    if (rc) {
+        c->dirty = true; // some rounds may have committed claims on the device: the host list is the truth
+        return rc;
+    }
     size_t used = 0;
     for (size_t k = 0; k < todo.size(); k++) {
         if (idx[k] < 0) continue;
@@ -1162,5 +1272,6 @@ int ksh_reconcile_batch(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int 
     }
     return KS_OK;
 }
+KSH_CATCH
 
 } // extern "C"

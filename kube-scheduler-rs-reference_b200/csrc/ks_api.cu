@@ -68,7 +68,7 @@ struct ks_snapshot {
     uint32_t N = 0, Npad = 0, W = 1;
     DevBuf alloc_cpu, alloc_mem, free_cpu, free_mem, prio, labels, flag;
     DevBuf st_rc, st_rm, st_sel, st_idx, st_score, st_cnt, st_mask, st_codes, st_bnode, st_bcpu, st_bmem;
-    DevBuf part_key, part_idx, part_cnt, st_samp;
+    DevBuf part_key, part_idx, part_cnt, st_samp, xflag;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host-space calls are pipelined in pod chunks: chunk c+1 is copied in on copy_stream while chunk c computes
     cudaStream_t copy_stream = nullptr;
@@ -151,6 +151,8 @@ int ks_snapshot_create(int device, ks_snapshot** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_cfork, cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = s->flag.ensure(sizeof(int));
+    if (e == cudaSuccess) e = s->xflag.ensure(sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(s->xflag.p, 0, sizeof(int));
     if (e != cudaSuccess) {
         ks_snapshot_destroy(s);
         return fail(KS_ERR_CUDA, "snapshot init failed: %s", cudaGetErrorString(e));
@@ -166,7 +168,7 @@ void ks_snapshot_destroy(ks_snapshot* s) {
     DevBuf* bufs[] = {&s->alloc_cpu, &s->alloc_mem, &s->free_cpu, &s->free_mem, &s->prio,     &s->labels,
                       &s->flag,      &s->st_rc,     &s->st_rm,    &s->st_sel,   &s->st_idx,   &s->st_score,
                       &s->st_cnt,    &s->st_mask,   &s->st_codes, &s->st_bnode, &s->st_bcpu,  &s->st_bmem,
-                      &s->part_key,  &s->part_idx,  &s->part_cnt, &s->st_samp};
+                      &s->part_key,  &s->part_idx,  &s->part_cnt, &s->st_samp,  &s->xflag};
     for (DevBuf* b : bufs) b->release();
     bitpar_release(s->bp);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -418,11 +420,40 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                         (unsigned long long)ks_mask_row_bytes(s->N));
         if (((uintptr_t)out->mask & 31u) != 0) return fail(KS_ERR_INVALID, "mask must be 32-byte aligned");
     }
-    if (P == 0) return KS_OK;
+    const ks_exchange* xc = out->exchange;
+    if (xc) {
+        if (out->mem_space != KS_MEM_DEVICE || !out->node_idx || !out->score)
+            return fail(KS_ERR_INVALID, "exchange needs device-space node_idx and score outputs");
+        if (xc->world < 2 || xc->world > KS_MAX_PEERS + 1 || xc->rank >= xc->world || xc->n_peers != xc->world - 1)
+            return fail(KS_ERR_INVALID, "bad exchange world/rank/n_peers");
+        if (!xc->local_flags || !xc->local_state) return fail(KS_ERR_INVALID, "exchange: NULL local_flags / local_state");
+        for (uint32_t k = 0; k < xc->n_peers; k++)
+            if (!xc->peer_node_idx[k] || !xc->peer_score[k] || !xc->peer_flag[k])
+                return fail(KS_ERR_INVALID, "exchange: NULL peer pointer %u", k);
+    }
+    if (P == 0 && !xc) return KS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU_TRY(cudaSetDevice(s->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
     const bool timing = (flags & KS_SELECT_TIMING) != 0;
+    PeerOut po;
+    if (xc) {
+        po.n = xc->n_peers;
+        po.world = xc->world;
+        po.rank = xc->rank;
+        for (uint32_t k = 0; k < xc->n_peers; k++) {
+            po.idx[k] = xc->peer_node_idx[k];
+            po.score[k] = xc->peer_score[k];
+            po.flag[k] = xc->peer_flag[k];
+        }
+        po.local_flags = xc->local_flags;
+        po.state = xc->local_state;
+    }
+    if (P == 0) { // an empty shard still takes part in the exchange: publish the sequence number, wait for the others
+        CU_TRY(launch_exchange_push(po, nullptr, nullptr, 0, st));
+        CU_TRY(launch_exchange_wait(po, s->xflag.as<int>(), st));
+        return KS_OK;
+    }
     s->timing_valid = false;
     if (timing) CU_TRY(cudaEventRecord(s->ev[0], st));
 
@@ -467,6 +498,10 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         if (ov.node_idx) CU_TRY(cudaMemsetAsync(ov.node_idx, 0xff, P * 4, st));
         if (ov.score) CU_TRY(cudaMemsetAsync(ov.score, 0, P * 8, st));
         if (ov.cnt) CU_TRY(cudaMemsetAsync(ov.cnt, 0, P * 4, st));
+        if (xc) {
+            CU_TRY(launch_exchange_push(po, ov.node_idx, ov.score, (uint32_t)P, st));
+            CU_TRY(launch_exchange_wait(po, s->xflag.as<int>(), st));
+        }
         if (out_host) {
             if (out->node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
             if (out->score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
@@ -481,6 +516,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         L.ov = ov;
         L.policy = policy;
         L.stream = st;
+        L.po = po;
         bool use_bitpar = false;
         if (flags & KS_SELECT_FORCE_BITPAR) use_bitpar = true;
         else if (!(flags & KS_SELECT_FORCE_DIRECT))
@@ -569,7 +605,11 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                 cudaError_t e = launch_select_direct(L, part, n_chunks, tiles_per_chunk);
                 if (e != cudaSuccess) return fail(KS_ERR_CUDA, "direct select failed: %s", cudaGetErrorString(e));
                 if (timing) CU_TRY(cudaEventRecord(s->ev[2], st));
+                if (xc) CU_TRY(launch_exchange_push(po, ov.node_idx, ov.score, (uint32_t)P, st));
             }
+            // fused all-gather: this rank's bindings went out from the argmax kernels (bit-parallel path) or the push
+            // kernel; the call's stream work ends when every other rank's bindings have arrived here
+            if (xc) CU_TRY(launch_exchange_wait(po, s->xflag.as<int>(), st));
             if (out_host) {
                 if (L.host_node_idx) CU_TRY(cudaMemcpyAsync(out->node_idx, ov.node_idx, P * 4, cudaMemcpyDeviceToHost, st));
                 if (L.host_score) CU_TRY(cudaMemcpyAsync(out->score, ov.score, P * 8, cudaMemcpyDeviceToHost, st));
@@ -593,7 +633,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
                                   (uint64_t)out->mask, out->mask_row_bytes,
                                   (uint64_t)policy | ((uint64_t)pods->mem_space << 8) | ((uint64_t)out->mem_space << 9) |
                                       ((uint64_t)out->mask_space << 10),
-                                  (uint64_t)flags ^ ((uint64_t)out->bindings_ready_event << 8), (uint64_t)st, s->version, (uint64_t)use_bitpar,
+                                  (uint64_t)flags ^ ((uint64_t)out->bindings_ready_event << 8) ^ ((uint64_t)(xc ? xc->local_state : nullptr) << 20), (uint64_t)st, s->version, (uint64_t)use_bitpar,
                                   g_devbuf_epoch.load(), s->bp.epoch};
         const bool key_hit = s->graph_valid && memcmp(key, s->graph_key, sizeof(key)) == 0;
         bool graph_ok = !timing && !(flags & KS_SELECT_NO_GRAPH);
@@ -654,6 +694,70 @@ int ks_last_timings(ks_snapshot* s, float ms[3]) {
 }
 
 const char* ks_last_path(const ks_snapshot* s) { return s ? s->last_path : "none"; }
+
+int ks_exchange_check(ks_snapshot* s) {
+    if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaDeviceSynchronize());
+    int flag = 0;
+    CU_TRY(cudaMemcpy(&flag, s->xflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        CU_TRY(cudaMemset(s->xflag.p, 0, sizeof(int)));
+        return fail(KS_ERR_CUDA, "exchange: a peer's bindings did not arrive within the timeout");
+    }
+    return KS_OK;
+}
+
+int ks_ipc_alloc(int device, uint64_t bytes, void** out_ptr, uint8_t out_handle[64]) {
+    if (!out_ptr || !out_handle || bytes == 0) return fail(KS_ERR_INVALID, "bad ks_ipc_alloc argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU_TRY(cudaSetDevice(device));
+    void* p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(KS_ERR_CUDA, "ks_ipc_alloc failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(out_handle, &h, 64);
+    *out_ptr = p;
+    return KS_OK;
+}
+
+int ks_ipc_open(int device, const uint8_t handle[64], void** out_ptr) {
+    if (!out_ptr || !handle) return fail(KS_ERR_INVALID, "bad ks_ipc_open argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU_TRY(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KS_OK;
+}
+
+int ks_ipc_close(int device, void* ptr) {
+    if (!ptr) return KS_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaIpcCloseMemHandle(ptr));
+    return KS_OK;
+}
+
+int ks_device_read(int device, const void* dev_ptr, void* host_ptr, uint64_t bytes) {
+    if (!dev_ptr || !host_ptr) return fail(KS_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(host_ptr, dev_ptr, bytes, cudaMemcpyDeviceToHost));
+    return KS_OK;
+}
+
+int ks_ipc_free(int device, void* ptr) {
+    if (!ptr) return KS_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFree(ptr));
+    return KS_OK;
+}
 
 int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n, const int32_t* claim_node, const int64_t* req_cpu,
                               const int64_t* req_mem, uint8_t* out_accepted) {
@@ -755,7 +859,7 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
             for (uint32_t w = 0; w < W; w++) sel[k * W + w] = pods->sel[p * W + w];
         }
         ks_pods kp{m, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
-        ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr};
+        ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr, nullptr};
         rc = ks_select(s, &kp, policy, KS_SELECT_FORCE_DIRECT, &kb, nullptr); // claims against the current free[]
         if (rc) return rc;
         rc = ks_snapshot_commit_claims(s, m, idx.data(), rc_.data(), rm_.data(), acc.data());

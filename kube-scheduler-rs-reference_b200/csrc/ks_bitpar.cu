@@ -961,7 +961,7 @@ __device__ __forceinline__ int first_bit_256(const uint32_t (&m)[8]) {
     return first;
 }
 
-__device__ __forceinline__ void write_binding(const OutView& ov, const PodView& pv, uint32_t p, int slot,
+__device__ __forceinline__ void write_binding(const OutView& ov, const PodView& pv, const PeerOut& po, uint32_t p, int slot,
                                               const int32_t* __restrict__ ord_idx, const int64_t* __restrict__ ord_prio) {
     int32_t best = -1;
     int64_t score = 0;
@@ -971,6 +971,10 @@ __device__ __forceinline__ void write_binding(const OutView& ov, const PodView& 
     }
     if (ov.node_idx) ov.node_idx[p] = best;
     if (ov.score) ov.score[p] = score;
+    for (uint32_t k = 0; k < po.n; k++) { // fused all-gather: the same binding goes to every peer over NVLink
+        po.idx[k][p] = best;
+        po.score[k][p] = score;
+    }
 }
 
 constexpr uint32_t FF_HEAD_TILES = 2;
@@ -979,30 +983,32 @@ template <int W>
 __global__ void __launch_bounds__(256)
     k_first_fit_head(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
                      const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov,
-                     uint32_t* __restrict__ tail_list, uint32_t* __restrict__ tail_count) {
+                     uint32_t* __restrict__ tail_list, uint32_t* __restrict__ tail_count, PeerOut po, bool last_kernel) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pv.P) return;
-    const PodThreshold t = pod_threshold(blobP, lay, __ldg(rk + p));
-    unsigned long long sel[W];
+    if (p < pv.P) {
+        const PodThreshold t = pod_threshold(blobP, lay, __ldg(rk + p));
+        unsigned long long sel[W];
 #pragma unroll
-    for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
-    uint32_t m0[8], m1[8];
-    ptile_mask<W>(blobP, lay, t, sel, 0, m0);
-    ptile_mask<W>(blobP, lay, t, sel, min(1u, lay.nt - 1), m1);
-    int slot = first_bit_256(m0);
-    if (slot < 0 && lay.nt > 1) {
-        const int s1 = first_bit_256(m1);
-        if (s1 >= 0) slot = BP_TILE + s1;
+        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+        uint32_t m0[8], m1[8];
+        ptile_mask<W>(blobP, lay, t, sel, 0, m0);
+        ptile_mask<W>(blobP, lay, t, sel, min(1u, lay.nt - 1), m1);
+        int slot = first_bit_256(m0);
+        if (slot < 0 && lay.nt > 1) {
+            const int s1 = first_bit_256(m1);
+            if (s1 >= 0) slot = BP_TILE + s1;
+        }
+        if (slot >= 0 || lay.nt <= FF_HEAD_TILES) write_binding(ov, pv, po, p, slot, ord_idx, ord_prio);
+        else tail_list[atomicAdd(tail_count, 1u)] = p; // order of the list does not affect any result
     }
-    if (slot >= 0 || lay.nt <= FF_HEAD_TILES) write_binding(ov, pv, p, slot, ord_idx, ord_prio);
-    else tail_list[atomicAdd(tail_count, 1u)] = p; // order of the list does not affect any result
+    if (last_kernel) exchange_signal(po); // no tail kernel follows: this rank's bindings are complete
 }
 
 template <int W>
 __global__ void __launch_bounds__(256)
     k_first_fit_tail(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
                      const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov,
-                     const uint32_t* __restrict__ tail_list, const uint32_t* __restrict__ tail_count) {
+                     const uint32_t* __restrict__ tail_list, const uint32_t* __restrict__ tail_count, PeerOut po) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t n = *tail_count;
@@ -1028,8 +1034,9 @@ __global__ void __launch_bounds__(256)
                 break;
             }
         }
-        if (lane == 0) write_binding(ov, pv, p, slot, ord_idx, ord_prio);
+        if (lane == 0) write_binding(ov, pv, po, p, slot, ord_idx, ord_prio);
     }
+    exchange_signal(po); // the head kernel's stores completed before this kernel started
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1318,13 +1325,14 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
         uint32_t* tail_count = ix.tail_list + ix.cap_pods;
         if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), ix.aux)) != cudaSuccess) return e;
+        const bool has_tail = ix.layP.nt > FF_HEAD_TILES;
         k_first_fit_head<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
-                                                                 ix.pod_ranks, L.ov, ix.tail_list, tail_count);
+                                                                 ix.pod_ranks, L.ov, ix.tail_list, tail_count, L.po, !has_tail);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (ix.layP.nt > FF_HEAD_TILES) {
+        if (has_tail) {
             k_first_fit_tail<W><<<sms * 2, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
-                                                             ix.pod_ranks, L.ov, ix.tail_list, tail_count);
+                                                             ix.pod_ranks, L.ov, ix.tail_list, tail_count, L.po);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         }

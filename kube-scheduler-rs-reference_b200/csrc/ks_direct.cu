@@ -9,6 +9,8 @@
 #include "ks_internal.cuh"
 #include "ks_launch.h"
 
+#include <algorithm>
+
 namespace ks {
 
 std::atomic<uint64_t> g_launches{0};
@@ -32,7 +34,7 @@ cudaError_t launch_free_reduce(int64_t* free_cpu, int64_t* free_mem, const int32
     if (B == 0) return cudaSuccess;
     int threads = 256;
     uint64_t blocks = (B + threads - 1) / threads;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 4096) blocks = 4096; // grid-stride beyond that
     k_node_free_reduce<<<(unsigned)blocks, threads, 0, st>>>(free_cpu, free_mem, bnode, bcpu, bmem, B);
     g_launches++;
     return cudaGetLastError();
@@ -60,6 +62,59 @@ __global__ void k_node_prio(const int64_t* __restrict__ free_cpu, const int64_t*
 cudaError_t launch_node_prio(const int64_t* free_cpu, const int64_t* free_mem, int64_t* prio, uint32_t N,
                              uint32_t Npad, int* range_flag, cudaStream_t st) {
     k_node_prio<<<(Npad + 255) / 256, 256, 0, st>>>(free_cpu, free_mem, prio, N, Npad, range_flag);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ exchange
+// ks_exchange (include/ksched.h).  The bit-parallel path stores the bindings into the peers' gather buffers from
+// inside its argmax kernels (ks_bitpar.cu); the per-cell path pushes its finished arrays with this kernel.
+__global__ void __launch_bounds__(256)
+    k_exchange_push(PeerOut po, const int32_t* __restrict__ node_idx, const int64_t* __restrict__ score, uint32_t P) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const int32_t ix = node_idx[p];
+        const int64_t sc = score[p];
+        for (uint32_t k = 0; k < po.n; k++) {
+            po.idx[k][p] = ix;
+            po.score[k][p] = sc;
+        }
+    }
+    exchange_signal(po);
+}
+
+// One warp; lane r waits until rank r's flag carries this rank's current sequence number (all ranks step in
+// lockstep).  A peer that never arrives raises *error_flag after ~4 s instead of hanging the GPU.
+__global__ void __launch_bounds__(32) k_exchange_wait(PeerOut po, int* __restrict__ error_flag) {
+    const uint32_t r = threadIdx.x;
+    if (r >= po.world || r == po.rank) return;
+    const uint32_t target = *reinterpret_cast<volatile uint32_t*>(po.state);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(po.local_flags + r) : "memory");
+        if ((int32_t)(v - target) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) {
+            if (error_flag) atomicExch(error_flag, 2);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+cudaError_t launch_exchange_push(const PeerOut& po, const int32_t* node_idx, const int64_t* score, uint32_t P, cudaStream_t st) {
+    if (po.n == 0) return cudaSuccess;
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(256u, (P + 255u) / 256u));
+    k_exchange_push<<<grid, 256, 0, st>>>(po, node_idx, score, P);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_wait(const PeerOut& po, int* error_flag, cudaStream_t st) {
+    if (po.n == 0) return cudaSuccess;
+    k_exchange_wait<<<1, 32, 0, st>>>(po, error_flag);
     g_launches++;
     return cudaGetLastError();
 }

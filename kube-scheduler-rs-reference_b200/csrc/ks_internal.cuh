@@ -43,6 +43,37 @@ struct OutView {
     uint32_t mask_valid_words; // words per row that may be written: 8*ceil(N/256)
 };
 
+// Fused all-gather of the bindings (ks_exchange, include/ksched.h): peer-mapped destinations of this rank's shard
+struct PeerOut {
+    uint32_t n = 0; // peers; 0 = no exchange
+    uint32_t world = 1, rank = 0;
+    int32_t* idx[KS_MAX_PEERS];
+    int64_t* score[KS_MAX_PEERS];
+    uint32_t* flag[KS_MAX_PEERS];
+    uint32_t* local_flags = nullptr;
+    uint32_t* state = nullptr; // [0] = step sequence number, [1] = CTA completion counter
+};
+
+// Last CTA of the kernel that completes this rank's bindings: publish a new sequence number to every peer.
+// Call at the very end of the kernel, by all threads of the CTA.
+__device__ __forceinline__ void exchange_signal(const PeerOut& po) {
+    if (po.n == 0) return;
+    __syncthreads(); // every store of this CTA has been issued
+    if (threadIdx.x == 0) {
+        __threadfence_system(); // ... and is visible system-wide before the counter moves
+        const uint32_t ctas = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(po.state + 1, 1u) == ctas - 1) {
+            po.state[1] = 0; // every CTA has arrived: ready for the next launch
+            const uint32_t seq = po.state[0] + 1;
+            po.state[0] = seq;
+            __threadfence_system();
+            for (uint32_t k = 0; k < po.n; k++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(po.flag[k]), "r"(seq) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(po.local_flags + po.rank), "r"(seq) : "memory");
+        }
+    }
+}
+
 // Per-(chunk,pod) partial results when the node dimension is split across CTAs (small P).
 struct PartialView {
     int64_t* key;  // best policy key (LEFTOVER: node priority; LEAST_ALLOCATED: score)
@@ -105,6 +136,7 @@ struct SelectLaunch {
     int32_t* host_node_idx = nullptr;
     int64_t* host_score = nullptr;
     cudaEvent_t ready_event = nullptr; // caller's "bindings are final" event (ks_bindings.bindings_ready_event)
+    PeerOut po;                        // fused all-gather of the bindings (po.n == 0: none)
 };
 
 } // namespace ks

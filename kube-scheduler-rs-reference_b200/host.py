@@ -114,6 +114,10 @@ class Context:
     def n_nodes(self):
         return int(lib.ksh_context_num_nodes(self._h))
 
+    @property
+    def num_bound(self):
+        return int(lib.ksh_context_num_bound(self._h))
+
     def upsert_node(self, nodes, i=0):
         idx = C.c_uint32()
         rc = lib.ksh_context_upsert_node(self._h, _addr(nodes, i), C.byref(idx))

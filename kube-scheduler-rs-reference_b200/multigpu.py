@@ -59,6 +59,80 @@ def all_gather_bindings(local_buf, out_buf=None):
     return out_buf
 
 
+class PeerExchange:
+    """Gather buffers for the fused all-gather of the bindings (include/ksched.h, ks_exchange).
+
+    Every rank owns one CUDA-IPC allocation  [score i64: world x cap | node_idx i32: world x cap | flags | state];
+    rank r's argmax kernels store its shard's bindings into slot r of EVERY rank's buffer over NVLink and release one
+    flag per destination; ks_select returns (stream-wise) once this rank's buffer holds every shard.
+    torch.distributed only carries the 64-byte IPC handles at set-up time."""
+
+    def __init__(self, device, world, rank, capacity, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _capi as capi
+        self.device, self.world, self.rank, self.cap = int(device), int(world), int(rank), int(capacity)
+        self._capi, self._C = capi, C
+        self.off_score = 0
+        self.off_idx = self.world * self.cap * 8
+        self.off_flags = (self.world * self.cap * 12 + 255) // 256 * 256
+        self.off_state = self.off_flags + 256
+        self.bytes = self.off_state + 256
+        base = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        rc = capi.lib.ks_ipc_alloc(self.device, self.bytes, C.byref(base), handle)
+        if rc != capi.KS_OK:
+            raise capi.KsError(rc, "ks_ipc_alloc")
+        self.base = base.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.peer_base = {}
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            p = C.c_void_p()
+            rc = capi.lib.ks_ipc_open(self.device, handles[r], C.byref(p))
+            if rc != capi.KS_OK:
+                raise capi.KsError(rc, f"ks_ipc_open(rank {r})")
+            self.peer_base[r] = p.value
+        d = capi.ks_exchange()
+        d.world, d.rank, d.n_peers = self.world, self.rank, self.world - 1
+        for k, r in enumerate(sorted(self.peer_base)):
+            d.peer_node_idx[k] = self.peer_base[r] + self.off_idx + self.rank * self.cap * 4
+            d.peer_score[k] = self.peer_base[r] + self.off_score + self.rank * self.cap * 8
+            d.peer_flag[k] = self.peer_base[r] + self.off_flags + self.rank * 4
+        d.local_flags = self.base + self.off_flags
+        d.local_state = self.base + self.off_state
+        self.desc = d
+
+    @property
+    def node_idx_ptr(self):  # this rank's own slot: pass as ks_bindings.node_idx
+        return self.base + self.off_idx + self.rank * self.cap * 4
+
+    @property
+    def score_ptr(self):
+        return self.base + self.off_score + self.rank * self.cap * 8
+
+    def read(self):
+        """(node_idx [world, cap] int32, score [world, cap] int64) of everything gathered so far (synchronises)."""
+        buf = np.empty(self.world * self.cap * 12, np.uint8)
+        rc = self._capi.lib.ks_device_read(self.device, self.base, buf.ctypes.data, buf.nbytes)
+        if rc != self._capi.KS_OK:
+            raise self._capi.KsError(rc, "ks_device_read")
+        score = buf[:self.off_idx].view(np.int64).reshape(self.world, self.cap)
+        idx = buf[self.off_idx:self.off_idx + self.world * self.cap * 4].view(np.int32).reshape(self.world, self.cap)
+        return idx, score
+
+    def close(self):
+        lib = self._capi.lib
+        for p in self.peer_base.values():
+            lib.ks_ipc_close(self.device, p)
+        self.peer_base = {}
+        if self.base:
+            lib.ks_ipc_free(self.device, self.base)
+            self.base = None
+
+
 def stream_bind_distributed(snap, req_cpu, req_mem, sel, arrival, policy=0, max_rounds=64, done=True):
     """Streaming micro-batch on `world` replicas (config C5 on several GPUs).  Every rank holds a full replica of
     the snapshot and its own arrivals (`arrival` = globally unique, ordered ids).  Per round: local select (claims

@@ -15,7 +15,8 @@ class ks_container_obj(C.Structure):
 class ks_pod_obj(C.Structure):
     _fields_ = [("ns", C.c_char_p), ("name", C.c_char_p), ("has_spec", C.c_int32), ("node_name", C.c_char_p),
                 ("n_containers", C.c_uint32), ("containers", C.POINTER(ks_container_obj)),
-                ("has_node_selector", C.c_int32), ("n_selector", C.c_uint32), ("selector", C.POINTER(ks_kv))]
+                ("has_node_selector", C.c_int32), ("n_selector", C.c_uint32), ("selector", C.POINTER(ks_kv)),
+                ("metadata_json", C.c_char_p)]
 
 
 class ks_node_obj(C.Structure):
@@ -47,7 +48,8 @@ class ObjectArena:
         """specs: list of dicts with keys
              name, ns (default 'default'), spec (default True), node_name (None = unbound),
              containers: list of (None | dict of requests)   [None = container without resources.requests]
-             selector: None | dict"""
+             selector: None | dict
+             metadata_json: None | str  (the pod's ObjectMeta as one JSON object, emitted verbatim in the Binding)"""
         arr = (ks_pod_obj * max(len(specs), 1))()
         for i, s in enumerate(specs):
             o = arr[i]
@@ -72,6 +74,8 @@ class ObjectArena:
             self._keep.append(carr)
             o.n_containers = len(conts)
             o.containers = carr
+            mj = s.get("metadata_json")
+            o.metadata_json = _b(mj) if mj is not None else None
             sel = s.get("selector")
             if sel is None:
                 o.has_node_selector = 0

@@ -137,7 +137,7 @@ class Snapshot:
         row = capi.mask_row_bytes(self.n_nodes)
         if want_mask:
             mask = np.zeros((p, row), np.uint8)
-        out = ks_bindings(_ptr(idx), _ptr(score), _ptr(cnt), capi.KS_MEM_HOST, _ptr(mask), row, capi.KS_MEM_HOST, None)
+        out = ks_bindings(_ptr(idx), _ptr(score), _ptr(cnt), capi.KS_MEM_HOST, _ptr(mask), row, capi.KS_MEM_HOST, None, None)
         rc = lib.ks_select(self._h, C.byref(pods), int(policy), int(flags), C.byref(out), None)
         if rc != capi.KS_OK:
             raise KsError(rc, "ks_select")
@@ -145,11 +145,13 @@ class Snapshot:
 
     def select_raw(self, n_pods, req_cpu, req_mem, sel, pods_space, node_idx, score, cnt, out_space, mask=None,
                    mask_row_bytes=0, mask_space=capi.KS_MEM_DEVICE, policy=capi.KS_SCORE_LEFTOVER,
-                   flags=capi.KS_SELECT_AUTO, stream=None, ready_event=None):
-        """Pointer-level call (torch tensors / raw addresses); the caller keeps the buffers alive."""
+                   flags=capi.KS_SELECT_AUTO, stream=None, ready_event=None, exchange=None):
+        """Pointer-level call (torch tensors / raw addresses); the caller keeps the buffers alive.
+        exchange: a multigpu.PeerExchange (fused all-gather of node_idx / score into every rank's gather buffer)."""
         pods = ks_pods(int(n_pods), _ptr(req_cpu), _ptr(req_mem), _ptr(sel), int(pods_space))
         out = ks_bindings(_ptr(node_idx), _ptr(score), _ptr(cnt), int(out_space), _ptr(mask), int(mask_row_bytes),
-                          int(mask_space), C.c_void_p(ready_event) if ready_event else None)
+                          int(mask_space), C.c_void_p(ready_event) if ready_event else None,
+                          C.pointer(exchange.desc) if exchange is not None else None)
         rc = lib.ks_select(self._h, C.byref(pods), int(policy), int(flags), C.byref(out),
                            C.c_void_p(stream) if stream else None)
         if rc != capi.KS_OK:
@@ -202,3 +204,9 @@ class Snapshot:
 
     def last_path(self):
         return lib.ks_last_path(self._h).decode()
+
+    def exchange_check(self):
+        """Synchronise and raise if a fused all-gather (ks_exchange) timed out waiting for a peer."""
+        rc = lib.ks_exchange_check(self._h)
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_exchange_check")

@@ -137,4 +137,11 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* idx
     return orc_stream_bind_packed(s->N, s->W, s->free_cpu.data(), s->free_mem.data(), s->alloc_cpu.data(), s->alloc_mem.data(),
                                   s->labels.data(), pods->n, pods->req_cpu, pods->req_mem, pods->sel, policy, idx, score, rounds);
 }
+// multi-GPU exchange / IPC entry points: nothing to fake on a CPU box (the ctypes binding only needs the symbols)
+int ks_exchange_check(ks_snapshot*) { return KS_OK; }
+int ks_ipc_alloc(int, uint64_t, void**, uint8_t*) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
+int ks_ipc_open(int, const uint8_t*, void**) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
+int ks_ipc_close(int, void*) { return KS_OK; }
+int ks_ipc_free(int, void*) { return KS_OK; }
+int ks_device_read(int, const void*, void*, uint64_t) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
 }

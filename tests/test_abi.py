@@ -48,9 +48,7 @@ def test_no_gpu_means_loud_failure_not_fallback(ks):
         ks.Snapshot(0)
 
 
-def test_headers_are_plain_c_and_the_c_example_links(ks, tmp_path):
-    """include/*.h must be consumable by a C (not C++) host: the example controller loop compiles as strict C99,
-    links against libksched.so alone and, without a GPU, fails loudly instead of computing on the CPU."""
+def _build_c_example(ks, tmp_path):
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "reconcile_loop")
@@ -59,9 +57,27 @@ def test_headers_are_plain_c_and_the_c_example_links(ks, tmp_path):
            os.path.join(root, "examples", "reconcile_loop.c"), "-L" + libdir, "-lksched", "-Wl,-rpath," + libdir, "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_headers_are_plain_c_and_the_c_example_links(ks, tmp_path):
+    """include/*.h must be consumable by a C (not C++) host: the example controller loop compiles as strict C99,
+    links against libksched.so alone and, without a GPU, fails loudly instead of computing on the CPU."""
+    exe = _build_c_example(ks, tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     if ks.device_count() > 0:
         assert r.returncode == 0, r.stderr
         assert "p9: already bound, skipped" in r.stdout
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [[], ["--batch"]])
+def test_c_example_drives_the_abi_on_a_gpu(ks, tmp_path, mode):
+    """examples/reconcile_loop.c (strict C99, links libksched.so only) run on the B200: the reference's reconcile loop
+    through the C ABI, pod by pod and as a drained batch."""
+    exe = _build_c_example(ks, tmp_path)
+    r = subprocess.run([exe] + mode, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ("round(s)" if mode else "already bound, skipped") in r.stdout

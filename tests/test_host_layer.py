@@ -260,6 +260,40 @@ def test_reconcile_mirror(ks, orc):
 
 
 @pytest.mark.gpu
+def test_reconcile_retry_does_not_leak_capacity(ks, orc):
+    """A pod that comes back unbound (the caller's POST failed or raced, error_policy requeued it; src/main.rs:105-108,
+    :122-125) must not be charged twice: the reference's LIST would never show the failed binding."""
+    arena = ks.objects.ObjectArena()
+    nodes = arena.nodes([{"name": "n0", "allocatable": {"cpu": "2", "memory": "4000"}},
+                         {"name": "n1", "allocatable": {"cpu": "1", "memory": "4000"}}])
+    pods = arena.pods([{"name": "a", "ns": "d", "containers": [{"cpu": "1500m", "memory": "1000"}],
+                        "metadata_json": '{"name":"a","namespace":"d","uid":"u-1","labels":{"app":"x"}}'},
+                       {"name": "b", "ns": "d", "containers": [{"cpu": "1500m", "memory": "1000"}]}])
+    with ks.host.Context(0) as ctx:
+        ctx.set_nodes(nodes, 2)
+        ctx.set_cluster_pods(arena.pods([]), 0)
+        for _ in range(3):  # the same pod reconciled three times: one row, one charge, always the same answer
+            rc, node, js = ctx.reconcile(pods, 0)
+            assert (rc, node) == (0, 0) and ctx.num_bound == 1
+        # metadata passthrough: the Binding carries the pod's whole ObjectMeta (src/main.rs:88 metadata: pod.metadata.clone())
+        assert json.loads(js) == {"apiVersion": "v1", "kind": "Binding", "target": {"name": "n0"},
+                                  "metadata": {"name": "a", "namespace": "d", "uid": "u-1", "labels": {"app": "x"}}}
+        assert ctx.reconcile(pods, 1)[:2] == (ks.host.KSH_RECONCILE_NO_NODE_FOUND, -1)  # n0 has 500m left, n1 1000m
+        ctx.pod_deleted(pods, 0)
+        assert ctx.num_bound == 0
+        assert ctx.reconcile(pods, 1)[:2] == (0, 0)  # the whole of n0 is back
+        # the batch form: a pod of the batch that this context bound earlier is released first, too
+        st, nd, _, _ = ctx.reconcile_batch(pods, 2)
+        assert ctx.num_bound == 1 and sorted(nd.tolist()) == [-1, 0]
+        # duplicate keys in a LIST result: the last row wins, nothing is charged twice
+        dup = arena.pods([{"name": "x", "ns": "d", "node_name": "n0", "containers": [{"cpu": "1"}]},
+                          {"name": "x", "ns": "d", "node_name": "n0", "containers": [{"cpu": "1"}]}])
+        ctx.set_cluster_pods(dup, 2)
+        assert ctx.num_bound == 1
+        assert ctx.reconcile(pods, 1)[:2] == (ks.host.KSH_RECONCILE_NO_NODE_FOUND, -1)  # n0: 1000m left < 1500m
+
+
+@pytest.mark.gpu
 def test_reconcile_batch_equals_the_streaming_oracle(ks, orc):
     """A drained queue through ksh_reconcile_batch: bound pods skipped, nameless pods refused, the rest bound by the
     micro-batch loop exactly as the oracle's restatement binds the packed batch; every bind is committed (device
@@ -306,14 +340,14 @@ def test_reconcile_batch_equals_the_streaming_oracle(ks, orc):
         feas = (f2c >= 1) & (f2m >= 1)
         want = int(np.argmax(np.where(feas, f2c * (1 << 22) + f2m, np.iinfo(np.int64).min))) if feas.any() else -1
         assert ctx.select_nodes(later, 1)[0][0] == want
-        # a second drain of the same queue: nothing new fits where it did not fit, bound ones would be re-bound ->
-        # only check that it runs on the committed state and never oversubscribes
+        # a second drain of the same queue (the caller's POSTs failed and every pod was requeued): the earlier bindings of
+        # these pods are released first, so each pod is charged once, and capacity is never oversubscribed
         status2, node2, _, _ = ctx.reconcile_batch(pods, cl.P)
         xn2, xc2, xm2 = ctx.export_packed()[3:]
         f3c, f3m = orc.free_reduce(ac, am, xn2, xc2, xm2)
         newly = np.nonzero(node2 >= 0)[0]
         assert ((f3c >= 0) | (fc < 0)).all() and ((f3m >= 0) | (fm < 0)).all(), "capacity oversubscribed by the second drain"
-        assert len(xn2) == len(xn) + len(newly)
+        assert len(xn2) == cl.B + len(newly)
         # a tiny Binding buffer: binds still happen, bodies that do not fit are reported as missing
         tiny = arena.pods([{"name": "t1", "ns": "d"}, {"name": "t2", "ns": "d"}])
         st, nd, bd, _ = ctx.reconcile_batch(tiny, 2, json_cap=120)
@@ -500,6 +534,31 @@ def test_packer_dictionary_compaction_and_duplicate_names(ks):
         assert ctx.upsert_node(arena.nodes([{"name": "z", "allocatable": alloc}])) == 2
         ctx.remove_node("z")
         assert ctx.upsert_node(arena.nodes([{"name": "z", "allocatable": alloc}])) == 2  # a removed name comes back as new
+
+
+def test_packer_dictionary_is_rebuilt_from_the_batch_when_full(ks):
+    """More than 511 distinct (key,value) pairs named by selectors over a context's lifetime while every pair stays
+    live on some node (hostname selectors): later batches must still pack - the dictionary only has to cover the
+    pairs of the current batch."""
+    arena = ks.objects.ObjectArena()
+    alloc = {"cpu": "4", "memory": str(1 << 30)}
+    n = 700
+    with ks.host.Context(ks.host.KSH_DEVICE_NONE) as ctx:
+        ctx.set_nodes(arena.nodes([{"name": f"n{i}", "labels": {"kubernetes.io/hostname": f"n{i}", "zone": f"z{i % 3}"},
+                                    "allocatable": alloc} for i in range(n)]), n)
+        for lo in range(0, n, 100):  # 7 batches x 100 hostname selectors: 700 live pairs over time
+            want = arena.pods([{"name": f"p{i}", "ns": "d", "selector": {"kubernetes.io/hostname": f"n{i}", "zone": f"z{i % 3}"}}
+                               for i in range(lo, lo + 100)] + [{"name": "plain", "ns": "d"}])
+            _, _, sel = ctx.pack_pods(want, 101)
+            lab = ctx.export_packed()[2]
+            assert ctx.label_words <= 8 and not sel[100].any()
+            for k in range(100):  # pod k matches exactly node lo+k
+                match = ~np.any(sel[k][None, :] & ~lab, axis=1)
+                assert np.nonzero(match)[0].tolist() == [lo + k]
+        # one batch that names more live pairs than the dictionary can hold is refused with a clear status
+        big = arena.pods([{"name": f"p{i}", "ns": "d", "selector": {"kubernetes.io/hostname": f"n{i}"}} for i in range(600)])
+        with pytest.raises(ks.KsError, match="split the batch"):
+            ctx.pack_pods(big, 600)
 
 
 def test_packer_survives_long_churn(ks, orc):

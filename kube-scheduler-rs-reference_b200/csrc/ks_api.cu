@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <algorithm>
 #include <vector>
@@ -69,6 +70,9 @@ struct ks_snapshot {
     DevBuf alloc_cpu, alloc_mem, free_cpu, free_mem, prio, labels, flag;
     DevBuf st_rc, st_rm, st_sel, st_idx, st_score, st_cnt, st_mask, st_codes, st_bnode, st_bcpu, st_bmem;
     DevBuf part_key, part_idx, part_cnt, st_samp, xflag;
+    DevBuf sb_pkey, sb_pidx, sb_pend, sb_ctl; // device-side streaming loop (k_stream_batch)
+    void* h_stream = nullptr;                 // pinned staging of one streaming micro-batch (inputs and results)
+    int sms = 0, coop = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host-space calls are pipelined in pod chunks: chunk c+1 is copied in on copy_stream while chunk c computes
     cudaStream_t copy_stream = nullptr;
@@ -145,6 +149,8 @@ int ks_snapshot_create(int device, ks_snapshot** out) {
     ks_snapshot* s = new (std::nothrow) ks_snapshot();
     if (!s) return fail(KS_ERR_NOMEM, "out of host memory");
     s->device = device;
+    s->sms = prop.multiProcessorCount;
+    s->coop = prop.cooperativeLaunch;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
@@ -168,7 +174,9 @@ void ks_snapshot_destroy(ks_snapshot* s) {
     DevBuf* bufs[] = {&s->alloc_cpu, &s->alloc_mem, &s->free_cpu, &s->free_mem, &s->prio,     &s->labels,
                       &s->flag,      &s->st_rc,     &s->st_rm,    &s->st_sel,   &s->st_idx,   &s->st_score,
                       &s->st_cnt,    &s->st_mask,   &s->st_codes, &s->st_bnode, &s->st_bcpu,  &s->st_bmem,
-                      &s->part_key,  &s->part_idx,  &s->part_cnt, &s->st_samp,  &s->xflag};
+                      &s->part_key,  &s->part_idx,  &s->part_cnt, &s->st_samp,  &s->xflag,
+                      &s->sb_pkey,   &s->sb_pidx,   &s->sb_pend,  &s->sb_ctl};
+    if (s->h_stream) cudaFreeHost(s->h_stream);
     for (DevBuf* b : bufs) b->release();
     bitpar_release(s->bp);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -530,7 +538,8 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         } else {
             const uint32_t n_tiles = s->Npad / TILE_N;
             const uint32_t pod_ctas = (L.pv.P + direct_pods_per_cta(s->W) - 1) / direct_pods_per_cta(s->W);
-            if (pod_ctas < 2 * 148) n_chunks = std::min<uint32_t>(n_tiles, (2 * 148 + pod_ctas - 1) / pod_ctas);
+            const uint32_t want_ctas = 2u * (uint32_t)s->sms; // at least two CTAs per SM
+            if (pod_ctas < want_ctas) n_chunks = std::min<uint32_t>(n_tiles, (want_ctas + pod_ctas - 1) / pod_ctas);
             tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
             n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
             if (n_chunks > 1) {
@@ -833,6 +842,69 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
     if (pods->n && !out_node_idx) return fail(KS_ERR_INVALID, "out_node_idx is NULL");
     const uint64_t n = pods->n;
     const uint32_t W = s->W;
+    if (policy != KS_SCORE_LEFTOVER && policy != KS_SCORE_LEAST_ALLOCATED) return fail(KS_ERR_INVALID, "bad policy");
+    static const bool host_loop = getenv("KS_STREAM_HOST_LOOP") != nullptr; // A/B switch: the round-1 host-driven loop
+    if (n > 0 && n <= STREAM_BATCH_MAX && s->N > 0 && s->coop && !host_loop) {
+        // device-side loop: one H2D, ONE cooperative launch that runs every round, one D2H
+        std::lock_guard<std::mutex> lk(s->mu);
+        CU_TRY(cudaSetDevice(s->device));
+        const size_t o_rc = 0, o_rm = o_rc + STREAM_BATCH_MAX * 8, o_sel = o_rm + STREAM_BATCH_MAX * 8,
+                     o_idx = o_sel + (size_t)STREAM_BATCH_MAX * 8 * KS_MAX_LABEL_WORDS, o_score = o_idx + STREAM_BATCH_MAX * 4,
+                     o_ctl = o_score + STREAM_BATCH_MAX * 8, h_bytes = o_ctl + 16;
+        if (!s->h_stream) CU_TRY(cudaHostAlloc(&s->h_stream, h_bytes, cudaHostAllocDefault));
+        uint8_t* h = static_cast<uint8_t*>(s->h_stream);
+        memcpy(h + o_rc, pods->req_cpu, n * 8);
+        memcpy(h + o_rm, pods->req_mem, n * 8);
+        memcpy(h + o_sel, pods->sel, n * 8 * W);
+        const uint32_t grid = std::max(1u, std::min<uint32_t>((uint32_t)s->sms, (s->N + 127u) / 128u));
+        CU_TRY(s->st_rc.ensure(STREAM_BATCH_MAX * 8));
+        CU_TRY(s->st_rm.ensure(STREAM_BATCH_MAX * 8));
+        CU_TRY(s->st_sel.ensure((size_t)STREAM_BATCH_MAX * 8 * KS_MAX_LABEL_WORDS));
+        CU_TRY(s->st_idx.ensure(STREAM_BATCH_MAX * 4));
+        CU_TRY(s->st_score.ensure(STREAM_BATCH_MAX * 8));
+        CU_TRY(s->sb_pkey.ensure((size_t)STREAM_BATCH_MAX * s->sms * 8));
+        CU_TRY(s->sb_pidx.ensure((size_t)STREAM_BATCH_MAX * s->sms * 4));
+        CU_TRY(s->sb_pend.ensure(2 * STREAM_BATCH_MAX * 4));
+        CU_TRY(s->sb_ctl.ensure(16));
+        cudaStream_t st = s->stream;
+        CU_TRY(cudaMemcpyAsync(s->st_rc.p, h + o_rc, n * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(s->st_rm.p, h + o_rm, n * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(s->st_sel.p, h + o_sel, n * 8 * W, cudaMemcpyHostToDevice, st));
+        StreamBatchArgs a;
+        a.N = s->N;
+        a.Npad = s->Npad;
+        a.alloc_cpu = s->alloc_cpu.as<int64_t>();
+        a.alloc_mem = s->alloc_mem.as<int64_t>();
+        a.labels = s->labels.as<uint64_t>();
+        a.free_cpu = s->free_cpu.as<int64_t>();
+        a.free_mem = s->free_mem.as<int64_t>();
+        a.policy = policy;
+        a.m = (uint32_t)n;
+        a.req_cpu = s->st_rc.as<int64_t>();
+        a.req_mem = s->st_rm.as<int64_t>();
+        a.sel = s->st_sel.as<uint64_t>();
+        a.pkey = s->sb_pkey.as<int64_t>();
+        a.pidx = s->sb_pidx.as<int32_t>();
+        a.pend = s->sb_pend.as<uint32_t>();
+        a.ctl = s->sb_ctl.as<uint32_t>();
+        a.out_idx = s->st_idx.as<int32_t>();
+        a.out_score = s->st_score.as<int64_t>();
+        a.max_rounds = (uint32_t)n + 1;
+        a.grid = grid;
+        s->derived_dirty = true; // free[] changes: the bit-parallel index is stale
+        s->version++;
+        cudaError_t e = launch_stream_batch(a, W, st);
+        if (e != cudaSuccess) return fail(KS_ERR_CUDA, "k_stream_batch launch failed: %s", cudaGetErrorString(e));
+        CU_TRY(cudaMemcpyAsync(h + o_idx, s->st_idx.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(h + o_score, s->st_score.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(h + o_ctl, s->sb_ctl.p, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        memcpy(out_node_idx, h + o_idx, n * 4);
+        if (out_score) memcpy(out_score, h + o_score, n * 8);
+        if (out_rounds) *out_rounds = reinterpret_cast<const uint32_t*>(h + o_ctl)[1];
+        s->last_path = "stream_batch";
+        return KS_OK;
+    }
     std::vector<uint64_t> pending(n);
     for (uint64_t i = 0; i < n; i++) {
         pending[i] = i;

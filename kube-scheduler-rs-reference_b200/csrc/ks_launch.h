@@ -27,4 +27,26 @@ namespace ks {
 cudaError_t launch_stream_resolve(int64_t* free_cpu, int64_t* free_mem, const int32_t* claim_node, const int64_t* req_cpu,
                                   const int64_t* req_mem, uint32_t n, uint32_t N, uint8_t* accepted, cudaStream_t st);
 uint32_t stream_max_claims();
+
+// device-side micro-batch loop (k_stream_batch, ks_stream.cu)
+constexpr uint32_t STREAM_BATCH_MAX = 1024; // pods per cooperative launch
+struct StreamBatchArgs {
+    uint32_t N, Npad;
+    const int64_t *alloc_cpu, *alloc_mem;
+    const uint64_t* labels;
+    int64_t *free_cpu, *free_mem;
+    int policy;
+    uint32_t m;
+    const int64_t *req_cpu, *req_mem;
+    const uint64_t* sel;
+    int64_t* pkey;  // [STREAM_BATCH_MAX * grid]
+    int32_t* pidx;  // [STREAM_BATCH_MAX * grid]
+    uint32_t* pend; // [2 * STREAM_BATCH_MAX]
+    uint32_t* ctl;  // [2]: pending count, rounds
+    int32_t* out_idx;
+    int64_t* out_score;
+    uint32_t max_rounds;
+    uint32_t grid;
+};
+cudaError_t launch_stream_batch(const StreamBatchArgs& a, uint32_t W, cudaStream_t st);
 } // namespace ks

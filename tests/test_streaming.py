@@ -32,9 +32,12 @@ def test_commit_claims_matches_oracle(ks, orc, P, N, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("policy", [0, 1])
-@pytest.mark.parametrize("P,N,seed", [(40, 12, 5), (800, 200, 6), (3000, 1500, 7)])
-def test_stream_bind_matches_oracle_and_never_overcommits(ks, orc, P, N, seed, policy):
-    cl = ks.synth.make(P, N, seed=seed, bound_per_node=3)
+@pytest.mark.parametrize("P,N,seed,keys", [(40, 12, 5, 8), (800, 200, 6, 8), (3000, 1500, 7, 8), (1024, 9, 11, 8), (1, 20000, 12, 8),
+                                           (700, 2600, 13, 32)])
+def test_stream_bind_matches_oracle_and_never_overcommits(ks, orc, P, N, seed, keys, policy):
+    """Batches of <= 1024 pods run the device-side loop (k_stream_batch: one cooperative launch for all rounds), larger
+    ones the host-driven loop (per-cell select + K3 per round); both must equal the oracle's round protocol."""
+    cl = ks.synth.make(P, N, seed=seed, bound_per_node=3, n_keys=keys)
     ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
     with ks.Snapshot(0) as snap:
         snap.set_nodes(ac, am, lab)
@@ -44,6 +47,7 @@ def test_stream_bind_matches_oracle_and_never_overcommits(ks, orc, P, N, seed, p
         fc1, fm1 = snap.free()
         # a second micro-batch sees the committed capacity
         idx2, _, _ = snap.stream_bind(rc[:100], rm[:100], sel[:100], policy=policy)
+        assert snap.last_path() == "stream_batch"
         fc2, fm2 = snap.free()
     ofc, ofm = fc0.copy(), fm0.copy()
     oidx, oscore, orounds = orc.stream_bind_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=policy)

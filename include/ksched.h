@@ -173,6 +173,25 @@ int ks_snapshot_commit_claims(ks_snapshot* s, uint64_t n_claims, const int32_t* 
 int ks_stream_bind(ks_snapshot* s, const ks_pods* pods /* host space */, int policy, int32_t* out_node_idx,
                    int64_t* out_score, uint32_t* out_rounds);
 
+/* ---- asynchronous streaming surface = the reference's Controller queue (src/main.rs:73, :141-148) ----
+ * The reference runs reconcile() for many pods concurrently from a work queue.  ks_stream is that queue in front of
+ * one snapshot: ks_stream_submit appends pending (unbound) pods and returns at once; a dispatcher thread owned by the
+ * library drains everything that has arrived (up to max_batch <= 1024 pods, arrival order) into ONE micro-batch
+ * (ks_stream_bind: device-side round loop with capacity commit) and publishes the results; ks_stream_poll collects
+ * finished pods without blocking.  Results carry the caller's ticket; node -1 = ReconcileError::NoNodeFound
+ * (src/main.rs:116-118).  Pods with spec.nodeName set must be filtered out before submission (src/main.rs:74-76).
+ * While a stream is open its snapshot must not be mutated by other calls (same rule as the reference's node store
+ * being written only by its reflector). */
+typedef struct ks_stream ks_stream;
+int ks_stream_open(ks_snapshot* s, int policy, uint32_t max_batch, ks_stream** out);
+int ks_stream_submit(ks_stream* q, uint64_t n, const int64_t* req_cpu, const int64_t* req_mem, const uint64_t* sel /* [n*W] */,
+                     const uint64_t* tickets /* [n] caller ids, returned by poll */);
+/* up to `max` finished pods; *out_n = how many were written (0 = nothing finished yet); never blocks */
+int ks_stream_poll(ks_stream* q, uint64_t max, uint64_t* out_ticket, int32_t* out_node_idx, int64_t* out_score, uint64_t* out_n);
+int ks_stream_flush(ks_stream* q);  /* blocks until every pod submitted so far has a result waiting in poll */
+int ks_stream_stats(ks_stream* q, uint64_t* batches, uint64_t* rounds, uint64_t* max_batch_seen);
+void ks_stream_close(ks_stream* q); /* stops the dispatcher; unpolled results are dropped */
+
 /* ---- the reference's own selection policy, seeded (src/main.rs:49-71; ATTEMPTS = 5 at :49) ----
  * For every pod: up to `attempts` draws, uniform with replacement over the snapshot's nodes (:56-57); the first
  * draw whose cell is KS_CELL_OK wins (:61-66); none -> -1 (= None -> ReconcileError::NoNodeFound, :70, :116-118)

@@ -13,5 +13,5 @@ from ._capi import (  # noqa: F401
     KsError, lib, LIB_PATH, declared_symbols, mask_row_bytes, device_count, launch_count,
 )
 from . import _capi as capi  # noqa: F401
-from .snapshot import Snapshot, SelectResult  # noqa: F401
+from .snapshot import Snapshot, SelectResult, Stream  # noqa: F401
 from . import synth, objects, host, multigpu  # noqa: F401

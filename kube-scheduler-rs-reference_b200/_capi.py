@@ -78,6 +78,12 @@ _proto("ks_snapshot_commit_claims", C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
 _proto("ks_stream_bind", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_int, C.c_void_p, C.c_void_p,
        C.POINTER(C.c_uint32))
 
+_proto("ks_stream_open", C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_void_p))
+_proto("ks_stream_submit", C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+_proto("ks_stream_poll", C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64))
+_proto("ks_stream_flush", C.c_int, C.c_void_p)
+_proto("ks_stream_stats", C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+_proto("ks_stream_close", None, C.c_void_p)
 _proto("ks_exchange_check", C.c_int, C.c_void_p)
 _proto("ks_ipc_alloc", C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p)
 _proto("ks_ipc_open", C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p))

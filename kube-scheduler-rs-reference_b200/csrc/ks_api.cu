@@ -5,7 +5,10 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <algorithm>
 #include <vector>
 
@@ -951,6 +954,162 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
     }
     if (out_rounds) *out_rounds = rounds;
     return KS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- async streaming
+struct StreamItem {
+    uint64_t ticket;
+    int64_t rc, rm;
+    uint64_t sel[KS_MAX_LABEL_WORDS];
+};
+struct StreamDone {
+    uint64_t ticket;
+    int32_t node;
+    int64_t score;
+};
+struct ks_stream {
+    ks_snapshot* snap = nullptr;
+    int policy = KS_SCORE_LEFTOVER;
+    uint32_t max_batch = STREAM_BATCH_MAX, W = 1;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_idle;
+    std::deque<StreamItem> in;
+    std::deque<StreamDone> out;
+    uint64_t submitted = 0, finished = 0, batches = 0, rounds = 0, max_seen = 0;
+    bool stop = false;
+    int error = KS_OK;
+    std::thread worker;
+};
+
+static void stream_worker(ks_stream* q) {
+    std::vector<int64_t> rc, rm, score;
+    std::vector<uint64_t> sel, tickets;
+    std::vector<int32_t> idx;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(q->mu);
+            q->cv_work.wait(lk, [&] { return q->stop || !q->in.empty(); });
+            if (q->stop) return;
+            const size_t m = std::min<size_t>(q->in.size(), q->max_batch);
+            rc.resize(m);
+            rm.resize(m);
+            sel.resize(m * q->W);
+            tickets.resize(m);
+            for (size_t k = 0; k < m; k++) { // everything that has arrived, in arrival order
+                const StreamItem& it = q->in.front();
+                rc[k] = it.rc;
+                rm[k] = it.rm;
+                tickets[k] = it.ticket;
+                for (uint32_t w = 0; w < q->W; w++) sel[k * q->W + w] = it.sel[w];
+                q->in.pop_front();
+            }
+        }
+        const size_t m = rc.size();
+        idx.assign(m, -1);
+        score.assign(m, 0);
+        uint32_t rounds = 0;
+        ks_pods kp{m, rc.data(), rm.data(), sel.data(), KS_MEM_HOST};
+        const int e = ks_stream_bind(q->snap, &kp, q->policy, idx.data(), score.data(), &rounds);
+        {
+            std::lock_guard<std::mutex> lk(q->mu);
+            if (e) q->error = e;
+            for (size_t k = 0; k < m; k++) q->out.push_back(StreamDone{tickets[k], e ? -1 : idx[k], e ? 0 : score[k]});
+            q->finished += m;
+            q->batches++;
+            q->rounds += rounds;
+            q->max_seen = std::max<uint64_t>(q->max_seen, m);
+        }
+        q->cv_idle.notify_all();
+    }
+}
+
+int ks_stream_open(ks_snapshot* s, int policy, uint32_t max_batch, ks_stream** out) {
+    if (!s || !out) return fail(KS_ERR_INVALID, "NULL argument");
+    if (policy != KS_SCORE_LEFTOVER && policy != KS_SCORE_LEAST_ALLOCATED) return fail(KS_ERR_INVALID, "bad policy");
+    ks_stream* q = new (std::nothrow) ks_stream();
+    if (!q) return fail(KS_ERR_NOMEM, "out of host memory");
+    q->snap = s;
+    q->policy = policy;
+    q->W = s->W;
+    q->max_batch = max_batch == 0 ? STREAM_BATCH_MAX : std::min<uint32_t>(max_batch, STREAM_BATCH_MAX);
+    try {
+        q->worker = std::thread(stream_worker, q);
+    } catch (...) {
+        delete q;
+        return fail(KS_ERR_NOMEM, "cannot start the dispatcher thread");
+    }
+    *out = q;
+    return KS_OK;
+}
+
+int ks_stream_submit(ks_stream* q, uint64_t n, const int64_t* req_cpu, const int64_t* req_mem, const uint64_t* sel,
+                     const uint64_t* tickets) {
+    if (!q || (n && (!req_cpu || !req_mem || !sel || !tickets))) return fail(KS_ERR_INVALID, "NULL argument");
+    if (n == 0) return KS_OK;
+    try {
+        std::lock_guard<std::mutex> lk(q->mu);
+        for (uint64_t i = 0; i < n; i++) {
+            StreamItem it;
+            it.ticket = tickets[i];
+            it.rc = req_cpu[i];
+            it.rm = req_mem[i];
+            for (uint32_t w = 0; w < q->W; w++) it.sel[w] = sel[i * q->W + w];
+            q->in.push_back(it);
+        }
+        q->submitted += n;
+    } catch (...) {
+        return fail(KS_ERR_NOMEM, "out of host memory");
+    }
+    q->cv_work.notify_one();
+    return KS_OK;
+}
+
+int ks_stream_poll(ks_stream* q, uint64_t max, uint64_t* out_ticket, int32_t* out_node_idx, int64_t* out_score, uint64_t* out_n) {
+    if (!q || !out_n || (max && (!out_ticket || !out_node_idx))) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(q->mu);
+    uint64_t k = 0;
+    while (k < max && !q->out.empty()) {
+        const StreamDone& d = q->out.front();
+        out_ticket[k] = d.ticket;
+        out_node_idx[k] = d.node;
+        if (out_score) out_score[k] = d.score;
+        q->out.pop_front();
+        k++;
+    }
+    *out_n = k;
+    if (q->error) {
+        const int e = q->error;
+        q->error = KS_OK;
+        return e; // ks_last_error() of the dispatcher thread is not visible here: the code says what failed
+    }
+    return KS_OK;
+}
+
+int ks_stream_flush(ks_stream* q) {
+    if (!q) return fail(KS_ERR_INVALID, "NULL argument");
+    std::unique_lock<std::mutex> lk(q->mu);
+    q->cv_idle.wait(lk, [&] { return q->finished == q->submitted; });
+    return KS_OK;
+}
+
+int ks_stream_stats(ks_stream* q, uint64_t* batches, uint64_t* rounds, uint64_t* max_batch_seen) {
+    if (!q) return fail(KS_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (batches) *batches = q->batches;
+    if (rounds) *rounds = q->rounds;
+    if (max_batch_seen) *max_batch_seen = q->max_seen;
+    return KS_OK;
+}
+
+void ks_stream_close(ks_stream* q) {
+    if (!q) return;
+    {
+        std::lock_guard<std::mutex> lk(q->mu);
+        q->stop = true;
+    }
+    q->cv_work.notify_all();
+    if (q->worker.joinable()) q->worker.join();
+    delete q;
 }
 
 } // extern "C"

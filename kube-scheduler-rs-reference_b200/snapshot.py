@@ -210,3 +210,55 @@ class Snapshot:
         rc = lib.ks_exchange_check(self._h)
         if rc != capi.KS_OK:
             raise KsError(rc, "ks_exchange_check")
+
+
+class Stream:
+    """ks_stream: the reference's Controller queue in front of one snapshot (asynchronous submit / poll)."""
+
+    def __init__(self, snap, policy=capi.KS_SCORE_LEFTOVER, max_batch=0):
+        h = C.c_void_p()
+        rc = lib.ks_stream_open(snap._h, int(policy), int(max_batch), C.byref(h))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_stream_open")
+        self._h, self._snap = h, snap
+        self._cap = 4096
+        self._t = np.empty(self._cap, np.uint64)
+        self._i = np.empty(self._cap, np.int32)
+        self._s = np.empty(self._cap, np.int64)
+
+    def submit(self, req_cpu, req_mem, sel, tickets):
+        req_cpu, req_mem = _c(req_cpu, np.int64), _c(req_mem, np.int64)
+        sel, tickets = _c(sel, np.uint64), _c(tickets, np.uint64)
+        rc = lib.ks_stream_submit(self._h, req_cpu.shape[0], _ptr(req_cpu), _ptr(req_mem), _ptr(sel), _ptr(tickets))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_stream_submit")
+
+    def poll(self):
+        """(tickets, node_idx, score) of the pods finished since the last poll (possibly empty); never blocks."""
+        n = C.c_uint64()
+        rc = lib.ks_stream_poll(self._h, self._cap, _ptr(self._t), _ptr(self._i), _ptr(self._s), C.byref(n))
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_stream_poll")
+        k = int(n.value)
+        return self._t[:k].copy(), self._i[:k].copy(), self._s[:k].copy()
+
+    def flush(self):
+        rc = lib.ks_stream_flush(self._h)
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_stream_flush")
+
+    def stats(self):
+        b, r, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.ks_stream_stats(self._h, C.byref(b), C.byref(r), C.byref(m))
+        return int(b.value), int(r.value), int(m.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ks_stream_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -138,6 +138,12 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* idx
                                   s->labels.data(), pods->n, pods->req_cpu, pods->req_mem, pods->sel, policy, idx, score, rounds);
 }
 // multi-GPU exchange / IPC entry points: nothing to fake on a CPU box (the ctypes binding only needs the symbols)
+int ks_stream_open(ks_snapshot*, int, uint32_t, ks_stream**) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
+int ks_stream_submit(ks_stream*, uint64_t, const int64_t*, const int64_t*, const uint64_t*, const uint64_t*) { return KS_ERR_NO_DEVICE; }
+int ks_stream_poll(ks_stream*, uint64_t, uint64_t*, int32_t*, int64_t*, uint64_t*) { return KS_ERR_NO_DEVICE; }
+int ks_stream_flush(ks_stream*) { return KS_ERR_NO_DEVICE; }
+int ks_stream_stats(ks_stream*, uint64_t*, uint64_t*, uint64_t*) { return KS_ERR_NO_DEVICE; }
+void ks_stream_close(ks_stream*) {}
 int ks_exchange_check(ks_snapshot*) { return KS_OK; }
 int ks_ipc_alloc(int, uint64_t, void**, uint8_t*) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
 int ks_ipc_open(int, const uint8_t*, void**) { return fail(KS_ERR_NO_DEVICE, "fake device"); }

@@ -81,3 +81,28 @@ def test_c_example_drives_the_abi_on_a_gpu(ks, tmp_path, mode):
     r = subprocess.run([exe] + mode, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert ("round(s)" if mode else "already bound, skipped") in r.stdout
+
+
+def test_rust_shim_binds_only_exported_symbols(ks):
+    """examples/rust_shim/ksched_sys.rs cannot be compiled here (no Rust toolchain); at least every function its
+    `extern "C"` block names must be exported by libksched.so, and every struct field list must match the ctypes
+    mirror of the same header (field names in order)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "examples", "rust_shim", "ksched_sys.rs")).read()
+    fns = re.findall(r"pub fn (ksh?_[a-z0-9_]+)\(", src)
+    assert len(fns) > 40
+    for name in fns:
+        assert hasattr(ks.lib, name), f"{name} is declared in ksched_sys.rs but not exported"
+    assert set(fns) <= set(ks.declared_symbols())
+
+    def rust_fields(struct):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % struct, src, re.S).group(1)
+        return re.findall(r"pub ([a-z_0-9]+):", body)
+
+    assert rust_fields("ks_pod_obj") == [f[0] for f in ks.objects.ks_pod_obj._fields_]
+    assert rust_fields("ks_node_obj") == [f[0] for f in ks.objects.ks_node_obj._fields_]
+    assert rust_fields("ks_bindings") == [f[0] for f in ks.capi.ks_bindings._fields_]
+    assert rust_fields("ks_exchange") == [f[0] for f in ks.capi.ks_exchange._fields_]
+    assert rust_fields("ks_pods") == [f[0] for f in ks.capi.ks_pods._fields_]

@@ -62,3 +62,54 @@ def test_stream_bind_matches_oracle_and_never_overcommits(ks, orc, P, N, seed, k
     bound = idx >= 0
     assert fc0.sum() - fc1.sum() == rc[bound].sum() and fm0.sum() - fm1.sum() == rm[bound].sum()
     assert rounds >= 1 and bound.sum() > 0
+
+
+@pytest.mark.gpu
+def test_async_stream_submit_poll(ks, orc):
+    """ks_stream (the reference's Controller queue, src/main.rs:73,141-148): tickets come back exactly once; with a
+    flush after every submit the batch boundaries are the submit calls, so the result equals the oracle's round
+    protocol batch by batch; free-running submits never oversubscribe and conserve capacity."""
+    cl = ks.synth.make(2400, 500, seed=91, bound_per_node=3)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes(ac, am, lab)
+        snap.set_bound(bn, bc, bm)
+        fc0, fm0 = snap.free()
+        ofc, ofm = fc0.copy(), fm0.copy()
+        got = np.full(cl.P, -2, np.int32)
+        with ks.Stream(snap) as q:
+            lo = 0
+            for size in (1, 7, 300, 900, 2, 190):  # deterministic boundaries: flush after each submit
+                hi = lo + size
+                q.submit(rc[lo:hi], rm[lo:hi], sel[lo:hi], np.arange(lo, hi, dtype=np.uint64))
+                q.flush()
+                t, i, s = q.poll()
+                assert sorted(t.tolist()) == list(range(lo, hi))
+                oidx, oscore, _ = orc.stream_bind_packed(ofc, ofm, ac, am, lab, rc[lo:hi], rm[lo:hi], sel[lo:hi])
+                order = np.argsort(t)
+                assert np.array_equal(i[order], oidx) and np.array_equal(s[order], oscore)
+                got[lo:hi] = oidx
+                lo = hi
+            # free-running: many small submits, poll while the dispatcher works
+            seen = []
+            for a in range(lo, cl.P, 37):
+                b = min(cl.P, a + 37)
+                q.submit(rc[a:b], rm[a:b], sel[a:b], np.arange(a, b, dtype=np.uint64))
+                t, i, _ = q.poll()
+                seen += list(zip(t.tolist(), i.tolist()))
+            q.flush()
+            t, i, _ = q.poll()
+            seen += list(zip(t.tolist(), i.tolist()))
+            assert sorted(x[0] for x in seen) == list(range(lo, cl.P))
+            for tk, nd in seen:
+                got[tk] = nd
+            batches, rounds, max_seen = q.stats()
+            assert batches >= 7 and max_seen <= 1024
+        fc1, fm1 = snap.free()
+    bound = got >= 0
+    assert (got >= -1).all() and bound.sum() > 0
+    assert fc0.sum() - fc1.sum() == rc[bound].sum() and fm0.sum() - fm1.sum() == rm[bound].sum()
+    assert (fc1[fc0 >= 0] >= 0).all() and (fm1[fm0 >= 0] >= 0).all()
+    used_c = np.zeros(cl.N, np.int64)
+    np.add.at(used_c, got[bound], rc[bound])
+    assert np.array_equal(fc0 - used_c, fc1)

@@ -421,8 +421,6 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
     if (rc) return rc;
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");
     if (policy != KS_SCORE_LEFTOVER && policy != KS_SCORE_LEAST_ALLOCATED) return fail(KS_ERR_INVALID, "bad policy");
-    if ((flags & KS_SELECT_FORCE_BITPAR) && policy != KS_SCORE_LEFTOVER)
-        return fail(KS_ERR_INVALID, "the bit-parallel path implements KS_SCORE_LEFTOVER only");
     if ((flags & KS_SELECT_FORCE_BITPAR) && (flags & KS_SELECT_FORCE_DIRECT)) return fail(KS_ERR_INVALID, "bad flags");
     const uint64_t P = pods->n;
     if (out->mask) {
@@ -470,8 +468,7 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
 
     // the per-cell kernel needs no derived state; the bit-parallel index is (re)built lazily
     const bool may_bitpar = (flags & KS_SELECT_FORCE_BITPAR) ||
-                            (!(flags & KS_SELECT_FORCE_DIRECT) && policy == KS_SCORE_LEFTOVER &&
-                             (uint64_t)P * s->N >= (1ull << 24));
+                            (!(flags & KS_SELECT_FORCE_DIRECT) && (uint64_t)P * s->N >= (1ull << 24));
     if (may_bitpar) {
         rc = refresh_derived(s, st);
         if (rc) return rc;

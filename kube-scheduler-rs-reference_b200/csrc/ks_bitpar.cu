@@ -36,11 +36,20 @@ struct NodeKey {
 __device__ __forceinline__ bool key_less(int64_t av, uint32_t ai, int64_t bv, uint32_t bi) {
     return av < bv || (av == bv && ai < bi);
 }
+// KS_SCORE_LEAST_ALLOCATED bound: the score of node n for a pod that requests nothing.  For requests >= 0 the score of
+// every feasible (pod, n) cell is <= least_alloc_bound(n) (same truncating divisions, monotone in the numerators).
+__device__ __forceinline__ int64_t least_alloc_bound(const NodeTable& nt, uint32_t n) {
+    const int64_t fc = nt.free_cpu[n], fm = nt.free_mem[n], ac = nt.alloc_cpu[n], am = nt.alloc_mem[n];
+    const int64_t pc = ac > 0 ? (fc * 100) / ac : 0;
+    const int64_t pm = am > 0 ? (fm * 100) / am : 0;
+    return (pc + pm) / 2;
+}
 __device__ __forceinline__ int64_t order_value(const NodeTable& nt, const int64_t* __restrict__ prio, int k, uint32_t n) {
-    return k == 0 ? nt.free_cpu[n] : (k == 1 ? nt.free_mem[n] : -prio[n]);
+    return k == 0 ? nt.free_cpu[n] : (k == 1 ? nt.free_mem[n] : (k == 2 ? -prio[n] : -least_alloc_bound(nt, n)));
 }
 
 constexpr int RANK_SAMPLES = 1024, RANK_BUCKETS = 256;
+constexpr int N_ORDERS = 4; // free_cpu, free_mem, leftover priority, least-allocated bound
 
 __global__ void __launch_bounds__(RANK_SAMPLES)
     k_node_splitters(NodeTable nt, const int64_t* __restrict__ prio, int64_t* __restrict__ spl_v,
@@ -77,9 +86,9 @@ __global__ void __launch_bounds__(256)
     k_node_bucket(NodeTable nt, const int64_t* __restrict__ prio, const int64_t* __restrict__ spl_v,
                   const uint32_t* __restrict__ spl_i, uint32_t* __restrict__ hist, uint8_t* __restrict__ bkt,
                   uint32_t* __restrict__ loc) {
-    __shared__ int64_t s_v[3][RANK_BUCKETS];
-    __shared__ uint32_t s_i[3][RANK_BUCKETS];
-    for (uint32_t j = threadIdx.x; j < 3 * (RANK_BUCKETS - 1); j += blockDim.x) {
+    __shared__ int64_t s_v[N_ORDERS][RANK_BUCKETS];
+    __shared__ uint32_t s_i[N_ORDERS][RANK_BUCKETS];
+    for (uint32_t j = threadIdx.x; j < N_ORDERS * (RANK_BUCKETS - 1); j += blockDim.x) {
         const uint32_t k = j / (RANK_BUCKETS - 1), q = j % (RANK_BUCKETS - 1);
         s_v[k][q] = spl_v[k * RANK_BUCKETS + q];
         s_i[k][q] = spl_i[k * RANK_BUCKETS + q];
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(256)
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= nt.N) return;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < N_ORDERS; k++) {
         const int64_t v = order_value(nt, prio, k, n);
         uint32_t lo = 0, len = RANK_BUCKETS - 1; // number of splitters < key
         while (len > 0) {
@@ -109,8 +118,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_node_scatter(uint32_t N, const uint32_t* __restrict__ hist, const uint8_t* __restrict__ bkt,
                    const uint32_t* __restrict__ loc, uint32_t* __restrict__ perm) {
-    __shared__ uint32_t s_start[3][RANK_BUCKETS];
-    if (threadIdx.x < 3) {
+    __shared__ uint32_t s_start[N_ORDERS][RANK_BUCKETS];
+    if (threadIdx.x < N_ORDERS) {
         uint32_t acc = 0;
         for (int b = 0; b < RANK_BUCKETS; b++) {
             s_start[threadIdx.x][b] = acc;
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(256)
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
 #pragma unroll
-    for (int k = 0; k < 3; k++)
+    for (int k = 0; k < N_ORDERS; k++)
         perm[(size_t)k * N + s_start[k][bkt[(size_t)k * N + n]] + loc[(size_t)k * N + n]] = n;
 }
 
@@ -130,9 +139,10 @@ __global__ void __launch_bounds__(256)
                 const uint8_t* __restrict__ bkt, const uint32_t* __restrict__ perm, int64_t* __restrict__ sortedC,
                 int64_t* __restrict__ sortedM, uint32_t* __restrict__ gposC, uint32_t* __restrict__ gposM,
                 int64_t* __restrict__ ord_prio, int32_t* __restrict__ ord_idx, uint32_t Nord,
-                int64_t* __restrict__ splC, int64_t* __restrict__ splM, uint32_t spl_stride) {
-    __shared__ uint32_t s_start[3][RANK_BUCKETS + 1];
-    if (threadIdx.x < 3) {
+                int64_t* __restrict__ splC, int64_t* __restrict__ splM, uint32_t spl_stride,
+                int64_t* __restrict__ ordL_s0, int32_t* __restrict__ ordL_idx) {
+    __shared__ uint32_t s_start[N_ORDERS][RANK_BUCKETS + 1];
+    if (threadIdx.x < N_ORDERS) {
         uint32_t acc = 0;
         for (int b = 0; b < RANK_BUCKETS; b++) {
             s_start[threadIdx.x][b] = acc;
@@ -144,9 +154,9 @@ __global__ void __launch_bounds__(256)
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t N = nt.N;
     if (n < N) {
-        uint32_t pos[3];
+        uint32_t pos[N_ORDERS];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < N_ORDERS; k++) {
             const int64_t v = order_value(nt, prio, k, n);
             const uint32_t b = bkt[(size_t)k * N + n];
             uint32_t c = 0;
@@ -165,9 +175,13 @@ __global__ void __launch_bounds__(256)
         if (pos[1] % spl_stride == 0) splM[pos[1] / spl_stride] = fm;
         ord_prio[pos[2]] = prio[n];
         ord_idx[pos[2]] = (int32_t)n;
-    } else if (n < Nord) { // padding of the priority order
+        ordL_s0[pos[3]] = least_alloc_bound(nt, n);
+        ordL_idx[pos[3]] = (int32_t)n;
+    } else if (n < Nord) { // padding of the priority / bound orders
         ord_prio[n] = INT64_MIN;
         ord_idx[n] = -1;
+        ordL_s0[n] = INT64_MIN;
+        ordL_idx[n] = -1;
     }
 }
 
@@ -183,6 +197,13 @@ static bool use_rows_kernel() {
 static int rows_count_mode() { // 0 = 8 POPC per item, 1 = carry-save tree + 4 POPC
     static const int v = [] {
         const char* e = getenv("KS_ROWS_COUNT");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+static int rows_hint_mode() { // 1 = mask stores carry an L2 evict-first policy, rank loads evict-last
+    static const int v = [] {
+        const char* e = getenv("KS_ROWS_HINT");
         return e ? atoi(e) : 0;
     }();
     return v;
@@ -715,6 +736,11 @@ __device__ __forceinline__ uint32_t ldg_u16(const uint16_t* p) { // zero-extende
     asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint32_t ldg_u16_keep(const uint16_t* p, uint64_t pol) { // L2 evict-last: the rank tables are re-read
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
 template <class T>
 __device__ __forceinline__ T* opaque_ptr(T* p) { // keeps a per-thread base pointer in one register pair (the compiler
     asm("" : "+l"(p));                           // would otherwise re-derive its lane part in every iteration)
@@ -744,9 +770,9 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
 
 // one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
 // a_tab = shared-window address of granule t of line 0 of tabC; tabM and the pair columns sit at constant offsets.
-template <int W, bool PSMEM, int CNT>
+template <int W, bool PSMEM, int CNT, bool HINT>
 __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_tab, uint32_t cb, uint32_t t, uint32_t* mask_col,
-                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q) {
+                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q, uint64_t pol_st) {
     const uint32_t aC = a_tab + rC * RW_LINE, aM = a_tab + rM * RW_LINE;
     const uint4 c0 = lds128(aC), c1 = lds128(aC + 128);
     const uint4 m0 = lds128(aM + RW_TAB_BYTES), m1 = lds128(aM + RW_TAB_BYTES + 128);
@@ -800,9 +826,14 @@ __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_
     }
     if (mask_col != nullptr && pid != RW_PID_NONE) {
         uint32_t* dst = mask_col + (size_t)pid * prm.row_words; // 32-byte aligned
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-                     "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                     : "memory");
+        if (HINT) // the mask is write-once streaming data: first in line for eviction from L2
+            asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(dst), "r"(a.x), "r"(a.y),
+                         "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol_st)
+                         : "memory");
+        else
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                         "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                         : "memory");
     }
     if (CNT == 0) {
         return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
@@ -816,11 +847,16 @@ __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_
     }
 }
 
-template <int W, bool PSMEM, int CNT>
+template <int W, bool PSMEM, int CNT, bool HINT>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid & 7, ps = (tid >> 3) & 3;
+    uint64_t pol_st = 0, pol_ld = 0;
+    if (HINT) {
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_st));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_ld));
+    }
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -874,15 +910,25 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
 
         for (; j < j1; j += 32) { // warp-uniform
             const uint4 rA = nA, rB = nB;
-            const uint32_t rCa = ldg_u16(rk_t + (size_t)rA.x * 16u), rMa = ldg_u16(rk_t + (size_t)rA.y * 16u + 8);
-            const uint32_t rCb = ldg_u16(rk_t + (size_t)rB.x * 16u), rMb = ldg_u16(rk_t + (size_t)rB.y * 16u + 8);
+            uint32_t rCa, rMa, rCb, rMb;
+            if (HINT) {
+                rCa = ldg_u16_keep(rk_t + (size_t)rA.x * 16u, pol_ld);
+                rMa = ldg_u16_keep(rk_t + (size_t)rA.y * 16u + 8, pol_ld);
+                rCb = ldg_u16_keep(rk_t + (size_t)rB.x * 16u, pol_ld);
+                rMb = ldg_u16_keep(rk_t + (size_t)rB.y * 16u + 8, pol_ld);
+            } else {
+                rCa = ldg_u16(rk_t + (size_t)rA.x * 16u);
+                rMa = ldg_u16(rk_t + (size_t)rA.y * 16u + 8);
+                rCb = ldg_u16(rk_t + (size_t)rB.x * 16u);
+                rMb = ldg_u16(rk_t + (size_t)rB.y * 16u + 8);
+            }
             fetch_rec(j + 32, nA, nB);
             const uint32_t pidA = rA.z, selA = rA.w, pidB = rB.z, selB = rB.w;
             const uint32_t grp0 = group_of(j);
             if (grp0 > last_grp) continue; // slot past the end of its stratum
 
-            const uint32_t cA = rows_item<W, PSMEM, CNT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + ps);
-            const uint32_t cB = rows_item<W, PSMEM, CNT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 4u + ps);
+            const uint32_t cA = rows_item<W, PSMEM, CNT, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + ps, pol_st);
+            const uint32_t cB = rows_item<W, PSMEM, CNT, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 4u + ps, pol_st);
             if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
                 uint32_t c = cA | (cB << 16);
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -1039,6 +1085,129 @@ __global__ void __launch_bounds__(256)
     exchange_signal(po); // the head kernel's stores completed before this kernel started
 }
 
+// ---- argmax of KS_SCORE_LEAST_ALLOCATED (not separable): bound-ordered scan with early exit ----
+// Nodes are visited in descending order of least_alloc_bound (ties by node index), 256 at a time through the same
+// table machinery (blobL); every feasible node of a tile is scored exactly; the scan stops as soon as the best exact
+// score beats the bound of everything that follows.  One warp per pod: all lanes derive the tile's feasibility mask,
+// lane l scores the set bits of word l&7 whose position is congruent to l>>3 mod 4; shuffle argmax per tile.
+// Pods with a negative request (allowed by the ABI, never produced by a Kubernetes object) void the bound: they scan
+// every tile, which is still exact.
+struct NodeEval { // one row per slot of the bound order
+    int64_t fc, fm, ac, am;
+    double inv_ac, inv_am; // 1/alloc: quotient estimate, corrected to the exact floor below
+    int32_t idx;
+    int32_t pad;
+};
+
+__global__ void __launch_bounds__(256)
+    k_build_eval(NodeTable nt, const int32_t* __restrict__ ordL_idx, uint32_t Nord, NodeEval* __restrict__ ev) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= Nord) return;
+    const int32_t n = ordL_idx[s];
+    NodeEval e;
+    e.idx = n;
+    e.pad = 0;
+    if (n >= 0) {
+        e.fc = nt.free_cpu[n];
+        e.fm = nt.free_mem[n];
+        e.ac = nt.alloc_cpu[n];
+        e.am = nt.alloc_mem[n];
+    } else {
+        e.fc = e.fm = INT64_MIN;
+        e.ac = e.am = 0;
+    }
+    e.inv_ac = e.ac > 0 ? 1.0 / (double)e.ac : 0.0;
+    e.inv_am = e.am > 0 ? 1.0 / (double)e.am : 0.0;
+    ev[s] = e;
+}
+
+// floor(x / d) for x >= 0, d > 0 (both < 2^63): double estimate, then exact correction in integers
+__device__ __forceinline__ int64_t div_floor_pos(int64_t x, int64_t d, double inv_d) {
+    int64_t q = (int64_t)((double)x * inv_d);
+    int64_t r = x - q * d;
+    while (r < 0) {
+        q--;
+        r += d;
+    }
+    while (r >= d) {
+        q++;
+        r -= d;
+    }
+    return q;
+}
+
+// exactly the expression of k_select_direct / the oracle (truncating division; x may be negative only when the
+// request is negative, where the generic operator is used)
+__device__ __forceinline__ int64_t least_alloc_score(const NodeEval& e, int64_t rc, int64_t rm) {
+    int64_t pc = 0, pm = 0;
+    if (e.ac > 0) {
+        const int64_t x = (e.fc - rc) * 100;
+        pc = x >= 0 ? div_floor_pos(x, e.ac, e.inv_ac) : x / e.ac;
+    }
+    if (e.am > 0) {
+        const int64_t x = (e.fm - rm) * 100;
+        pm = x >= 0 ? div_floor_pos(x, e.am, e.inv_am) : x / e.am;
+    }
+    return (pc + pm) / 2;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_least_alloc(const uint8_t* __restrict__ blobL, BitparLayout lay, const NodeEval* __restrict__ ev,
+                  const int64_t* __restrict__ ordL_s0, PodView pv, const uint2* __restrict__ rk, OutView ov, PeerOut po) {
+    const uint32_t lane = threadIdx.x & 31, wq = lane & 7, quarter = lane >> 3;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < pv.P; p += warps) {
+        const PodThreshold t = pod_threshold(blobL, lay, __ldg(rk + p));
+        unsigned long long sel[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+        const int64_t rc = __ldg(pv.req_cpu + p), rm = __ldg(pv.req_mem + p);
+        const bool bounded = rc >= 0 && rm >= 0; // else the bound does not hold: no early exit
+        int64_t best = INT64_MIN;
+        int32_t bidx = -1;
+        for (uint32_t k = 0; k < lay.nt; k++) {
+            if (bounded && bidx >= 0 && best > __ldg(ordL_s0 + (size_t)k * BP_TILE)) break; // warp-uniform
+            uint32_t m[8];
+            ptile_mask<W>(blobL, lay, t, sel, k, m);
+            uint32_t bits = 0; // this lane's share of the tile's feasible slots
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((uint32_t)j == wq) bits = m[j];
+            bits &= 0x11111111u << quarter;
+            while (bits) {
+                const uint32_t b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const NodeEval e = ev[(size_t)k * BP_TILE + wq * 32 + b];
+                const int64_t sc = least_alloc_score(e, rc, rm);
+                if (sc > best || (sc == best && e.idx < bidx)) {
+                    best = sc;
+                    bidx = e.idx;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) { // every lane ends with the tile-merged best
+                const int64_t os = __shfl_xor_sync(0xffffffffu, best, off);
+                const int32_t oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+                if (oi >= 0 && (bidx < 0 || os > best || (os == best && oi < bidx))) {
+                    best = os;
+                    bidx = oi;
+                }
+            }
+        }
+        if (lane == 0) {
+            const int64_t score = bidx >= 0 ? best : 0;
+            if (ov.node_idx) ov.node_idx[p] = bidx;
+            if (ov.score) ov.score[p] = score;
+            for (uint32_t q = 0; q < po.n; q++) {
+                po.idx[q][p] = bidx;
+                po.score[q][p] = score;
+            }
+        }
+    }
+    exchange_signal(po);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -1126,7 +1295,7 @@ void bitpar_release(BitparIndex& ix) {
                     ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
                     ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist,
                     ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.rec_s,
-                    ix.blobR,   ix.rank,   ix.tile_sorted};
+                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -1153,9 +1322,12 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
         if ((e = regrow(ix.ord_idx, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.splC, 1024)) != cudaSuccess) return e;
         if ((e = regrow(ix.splM, 1024)) != cudaSuccess) return e;
-        if ((e = regrow(ix.rk_bkt, 3 * cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.rk_loc, 3 * cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.rk_perm, 3 * cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_bkt, N_ORDERS * cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_loc, N_ORDERS * cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_perm, N_ORDERS * cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.ordL_s0, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.ordL_idx, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.evalL, cap)) != cudaSuccess) return e;
         ix.cap_nodes = cap;
     }
     uint32_t stride = 1;
@@ -1163,16 +1335,16 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
     ix.spl_stride = stride;
     ix.n_spl = (nt.N + stride - 1) / stride;
     if (!ix.rk_hist) {
-        if ((e = regrow(ix.rk_hist, 3 * RANK_BUCKETS)) != cudaSuccess) return e;
-        if ((e = regrow(ix.rk_spl_v, 3 * RANK_BUCKETS)) != cudaSuccess) return e;
-        if ((e = regrow(ix.rk_spl_i, 3 * RANK_BUCKETS)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_hist, N_ORDERS * RANK_BUCKETS)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_spl_v, N_ORDERS * RANK_BUCKETS)) != cudaSuccess) return e;
+        if ((e = regrow(ix.rk_spl_i, N_ORDERS * RANK_BUCKETS)) != cudaSuccess) return e;
     }
-    k_node_splitters<<<3, RANK_SAMPLES, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist);
+    k_node_splitters<<<N_ORDERS, RANK_SAMPLES, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist);
     k_node_bucket<<<(nt.N + 255) / 256, 256, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist, ix.rk_bkt, ix.rk_loc);
     k_node_scatter<<<(nt.N + 255) / 256, 256, 0, st>>>(nt.N, ix.rk_hist, ix.rk_bkt, ix.rk_loc, ix.rk_perm);
     k_node_rank<<<(Nord + 255) / 256, 256, 0, st>>>(nt, prio, ix.rk_hist, ix.rk_bkt, ix.rk_perm, ix.sortedC, ix.sortedM,
                                                     ix.gposC, ix.gposM, ix.ord_prio, ix.ord_idx, Nord, ix.splC, ix.splM,
-                                                    stride);
+                                                    stride, ix.ordL_s0, ix.ordL_idx);
     g_launches += 4;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     BitparLayout lay{}, layP{};
@@ -1180,6 +1352,7 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
     if (layP.blob_bytes > ix.cap_blobP) {
         const size_t cap = (size_t)layP.blob_bytes + layP.blob_bytes / 8;
         if ((e = regrow(ix.blobP, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.blobL, cap)) != cudaSuccess) return e;
         ix.cap_blobP = cap;
     }
     ix.rows_valid = false;
@@ -1226,6 +1399,11 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
     k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ord_idx, ix.blobP, layP);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // KS_SCORE_LEAST_ALLOCATED: the same flat index in descending order of the score bound + per-slot evaluation rows
+    k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ordL_idx, ix.blobL, layP);
+    k_build_eval<<<(Nord + 255) / 256, 256, 0, st>>>(nt, ix.ordL_idx, Nord, ix.evalL);
+    g_launches += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ix.lay = lay;
     ix.layP = layP;
     ix.valid = true;
@@ -1243,9 +1421,13 @@ template <int W>
 static cudaError_t set_smem_attr() {
     cudaError_t e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1325,16 +1507,23 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
         uint32_t* tail_count = ix.tail_list + ix.cap_pods;
         if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), ix.aux)) != cudaSuccess) return e;
-        const bool has_tail = ix.layP.nt > FF_HEAD_TILES;
-        k_first_fit_head<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
-                                                                 ix.pod_ranks, L.ov, ix.tail_list, tail_count, L.po, !has_tail);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (has_tail) {
-            k_first_fit_tail<W><<<sms * 2, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv,
-                                                             ix.pod_ranks, L.ov, ix.tail_list, tail_count, L.po);
+        if (L.policy == KS_SCORE_LEAST_ALLOCATED) {
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)P + 7) / 8);
+            k_least_alloc<W><<<grid, 256, 0, ix.aux>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        } else {
+            const bool has_tail = ix.layP.nt > FF_HEAD_TILES;
+            k_first_fit_head<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks,
+                                                                     L.ov, ix.tail_list, tail_count, L.po, !has_tail);
+            g_launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (has_tail) {
+                k_first_fit_tail<W><<<sms * 2, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
+                                                                 ix.tail_list, tail_count, L.po);
+                g_launches++;
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            }
         }
         // bindings are final here: start their device-to-host copy now, under the mask kernel
         if (L.host_node_idx && L.ov.node_idx) {
@@ -1375,7 +1564,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
             const uint32_t GS = (n_groups + RW_STRATA - 1) / RW_STRATA;
             const uint64_t F = (uint64_t)RW_STRATA * GS * ix.lay_r.ncb;
             const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + 31) / 32);
-            auto kern = rows_count_mode() ? k_mask_rows<W, W <= 4, 1> : k_mask_rows<W, W <= 4, 0>;
+            auto kern = rows_hint_mode() ? (rows_count_mode() ? k_mask_rows<W, W <= 4, 1, true> : k_mask_rows<W, W <= 4, 0, true>)
+                                         : (rows_count_mode() ? k_mask_rows<W, W <= 4, 1, false> : k_mask_rows<W, W <= 4, 0, false>);
             RowsParams prm;
             prm.blob = ix.blobR;
             prm.lay = ix.lay_r;

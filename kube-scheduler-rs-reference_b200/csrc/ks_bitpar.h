@@ -51,6 +51,8 @@ struct RowsLayout {
     uint32_t n_thr;      // thresholds per column block in the rank tables: N + 1
 };
 
+struct NodeEval;
+
 struct BitparIndex {
     // per-snapshot index (device)
     int64_t* sortedC = nullptr;  // [N] free_cpu ascending
@@ -71,6 +73,10 @@ struct BitparIndex {
     uint2* rk_s = nullptr;         // pods in bucket order: thresholds, original pod index, selector words
     uint32_t* pid_s = nullptr;
     unsigned long long* sel_s = nullptr;
+    int64_t* ordL_s0 = nullptr;    // KS_SCORE_LEAST_ALLOCATED: score bound of every node in descending order (ties by index)
+    int32_t* ordL_idx = nullptr;
+    struct NodeEval* evalL = nullptr; // per slot of that order: what the exact score needs
+    uint8_t* blobL = nullptr;      // flat index (layP) in that order
     uint4* rec_s = nullptr;        // rows kernel: {threshold_cpu, threshold_mem, pod index, selector columns} per sorted pod
     uint8_t* blobR = nullptr;      // rows kernel: lay_r.ncb column-block blobs
     uint16_t* rank = nullptr;      // rows kernel: [cb][threshold g][resource][tile] = nodes of the tile at sorted positions < g

@@ -100,15 +100,21 @@ def test_random_clusters_leftover(ks, orc, path, P, N, keys):
         _assert_same(r, _oracle(orc, cl, 0), f"{path} {P}x{N} W={cl.label_words}")
 
 
-@pytest.mark.parametrize("P,N,keys", [(5, 31, 8), (257, 1025, 8), (500, 3000, 8), (64, 2500, 32), (3, 20000, 8)])
-def test_random_clusters_least_allocated(ks, orc, P, N, keys):
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("P,N,keys", [(5, 31, 8), (257, 1025, 8), (500, 3000, 8), (64, 2500, 32), (3, 20000, 8), (4000, 9000, 8),
+                                      (300, 150_000, 8)])
+def test_random_clusters_least_allocated(ks, orc, path, P, N, keys):
+    """KS_SCORE_LEAST_ALLOCATED (not separable): the per-cell kernel and the bit-parallel path (bound-ordered scan with
+    early exit, k_least_alloc) against the oracle - node, score, count and mask."""
     cl = ks.synth.make(P, N, seed=2000 + P + N, n_keys=keys, bound_per_node=4)
     snap, (rc, rm, sel) = _snapshot(ks, cl)
     with snap:
-        r = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, want_mask=True)
-        assert r.path == "direct"
-        _assert_same(r, _oracle(orc, cl, 1), f"least-allocated {P}x{N}")
+        r = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, flags=PATHS[path], want_mask=True)
+        assert r.path == path
+        _assert_same(r, _oracle(orc, cl, 1), f"least-allocated {path} {P}x{N}")
         assert r.score.min() >= 0 and r.score.max() <= 100
+        auto = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED)
+        assert auto.path == ("bitpar" if P * N >= 1 << 24 else "direct") and np.array_equal(auto.node_idx, r.node_idx)
 
 
 def test_reason_codes_match_oracle(ks, orc):
@@ -429,10 +435,11 @@ def test_adversarial_values(ks, orc, path, seed, P, N, W):
         r = snap.select(rc, rm, sel, flags=PATHS[path], want_mask=True)
         o = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel)
         _assert_same(r, o, f"adversarial {path} seed {seed}")
-        if path == "direct":
-            r1 = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, want_mask=False)
-            o1 = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=1, want_mask=False)
-            assert np.array_equal(r1.node_idx, o1[0]) and np.array_equal(r1.score, o1[1])
+        # the non-separable score on the same path; negative requests void the early-exit bound of k_least_alloc
+        r1 = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, flags=PATHS[path], want_mask=False)
+        o1 = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=1, want_mask=False)
+        assert r1.path == path and np.array_equal(r1.node_idx, o1[0]) and np.array_equal(r1.score, o1[1])
+        assert np.array_equal(r1.feasible_cnt, o1[2])
 
 
 def _stream_states(ks, seed, P, first=0):

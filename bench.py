@@ -121,8 +121,10 @@ class ClockSampler:
         self.path = tempfile.mktemp(prefix="ks_clocks_", suffix=".csv")
         self.proc = None
         try:
+            # `timeout`: if this process dies the sampler must not outlive it for long (a profiler wrapping the bench
+            # waits for every child)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                ["timeout", "300", "nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                  "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

@@ -427,7 +427,8 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
         if (out->mask_row_bytes % 32 != 0 || out->mask_row_bytes < ks_mask_row_bytes(s->N))
             return fail(KS_ERR_INVALID, "mask_row_bytes must be a multiple of 32 and >= %llu",
                         (unsigned long long)ks_mask_row_bytes(s->N));
-        if (((uintptr_t)out->mask & 31u) != 0) return fail(KS_ERR_INVALID, "mask must be 32-byte aligned");
+        if (out->mask_space == KS_MEM_DEVICE && ((uintptr_t)out->mask & 31u) != 0)
+            return fail(KS_ERR_INVALID, "a device-space mask must be 32-byte aligned");
     }
     const ks_exchange* xc = out->exchange;
     if (xc) {

@@ -485,7 +485,7 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": cap_info.get("dram_bytes"), "kernel": f"{path}:{os.environ.get('KS_MASK_KERNEL', 'rows')}",
+                "traffic": cap_info.get("dram_bytes"), "kernel": "k_mask_rows" if path == "bitpar" else "k_select_direct",
                 "kernel_ms": k_ms, "kernel_ms_spread": spread(kern_ms),
                 "rest_of_step_ms": sum(scan_ms) / len(scan_ms), "algorithmic_bytes": ab["dominant_kernel"],
                 "step_algorithmic_bytes": ab["step_total"], "step_frac": ab["step_total"] / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -572,7 +572,7 @@ def main():
             "workload": f"{wl_text}, resource_fits + nodeSelector + argmax score ({args.policy}), "
                         f"mask {'emitted' if r['emit_mask'] else 'not emitted'}",
             "label_words": W, "bound_pods": r["B"], "seed": hex(r["seed"]), "path": r["path"],
-            "mask_kernel": os.environ.get("KS_MASK_KERNEL", "rows"),
+            "kernel_switches": {k: os.environ[k] for k in ("KS_ROWS_HINT", "KS_ROWS_SORT") if k in os.environ} or None,
             "parallelism": f"pods sharded x{world}, node table replicated" + (f"; bindings exchange: {r['exchange']}" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": r["t_wall"],
             "clocks_window": "0.4 s untimed soak of the same step + both timed loops (timed region alone is a few ms)",

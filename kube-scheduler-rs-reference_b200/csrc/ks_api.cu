@@ -73,7 +73,7 @@ struct ks_snapshot {
     DevBuf alloc_cpu, alloc_mem, free_cpu, free_mem, prio, labels, flag;
     DevBuf st_rc, st_rm, st_sel, st_idx, st_score, st_cnt, st_mask, st_codes, st_bnode, st_bcpu, st_bmem;
     DevBuf part_key, part_idx, part_cnt, st_samp, xflag;
-    DevBuf sb_pkey, sb_pidx, sb_pend, sb_ctl; // device-side streaming loop (k_stream_batch)
+    DevBuf sb_pkey, sb_pidx, sb_pend; // device-side streaming loop (k_stream_batch)
     void* h_stream = nullptr;                 // pinned staging of one streaming micro-batch (inputs and results)
     int sms = 0, coop = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -178,7 +178,7 @@ void ks_snapshot_destroy(ks_snapshot* s) {
                       &s->flag,      &s->st_rc,     &s->st_rm,    &s->st_sel,   &s->st_idx,   &s->st_score,
                       &s->st_cnt,    &s->st_mask,   &s->st_codes, &s->st_bnode, &s->st_bcpu,  &s->st_bmem,
                       &s->part_key,  &s->part_idx,  &s->part_cnt, &s->st_samp,  &s->xflag,
-                      &s->sb_pkey,   &s->sb_pidx,   &s->sb_pend,  &s->sb_ctl};
+                      &s->sb_pkey,   &s->sb_pidx,   &s->sb_pend};
     if (s->h_stream) cudaFreeHost(s->h_stream);
     for (DevBuf* b : bufs) b->release();
     bitpar_release(s->bp);
@@ -224,7 +224,7 @@ int ks_snapshot_set_nodes(ks_snapshot* s, uint32_t n_nodes, uint32_t label_words
     CU_TRY(s->alloc_mem.ensure(nb));
     CU_TRY(s->free_cpu.ensure(nb));
     CU_TRY(s->free_mem.ensure(nb));
-    CU_TRY(s->prio.ensure(nb));
+    CU_TRY(s->prio.ensure(2 * nb)); // [leftover priority | least-allocated bound]
     CU_TRY(s->labels.ensure(nb * label_words));
     // allocatable: pad with 0; free: pad with INT64_MIN (never feasible)
     for (uint32_t n = 0; n < Npad; n++) h[n] = n < n_nodes ? alloc_cpu[n] : 0;
@@ -849,28 +849,27 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
         // device-side loop: one H2D, ONE cooperative launch that runs every round, one D2H
         std::lock_guard<std::mutex> lk(s->mu);
         CU_TRY(cudaSetDevice(s->device));
-        const size_t o_rc = 0, o_rm = o_rc + STREAM_BATCH_MAX * 8, o_sel = o_rm + STREAM_BATCH_MAX * 8,
-                     o_idx = o_sel + (size_t)STREAM_BATCH_MAX * 8 * KS_MAX_LABEL_WORDS, o_score = o_idx + STREAM_BATCH_MAX * 4,
-                     o_ctl = o_score + STREAM_BATCH_MAX * 8, h_bytes = o_ctl + 16;
-        if (!s->h_stream) CU_TRY(cudaHostAlloc(&s->h_stream, h_bytes, cudaHostAllocDefault));
-        uint8_t* h = static_cast<uint8_t*>(s->h_stream);
-        memcpy(h + o_rc, pods->req_cpu, n * 8);
-        memcpy(h + o_rm, pods->req_mem, n * 8);
-        memcpy(h + o_sel, pods->sel, n * 8 * W);
+        // one pinned staging block: inputs [rc | rm | sel] and results [score | idx | ctl] are contiguous, so the whole
+        // micro-batch costs ONE H2D copy, ONE cooperative launch and ONE D2H copy
+        const size_t in_bytes = n * (16 + 8 * (size_t)W), o_score = 0, o_idx = n * 8, o_ctl = o_idx + ((n * 4 + 7) & ~(size_t)7),
+                     out_bytes = o_ctl + 8;
+        const size_t h_cap = (size_t)STREAM_BATCH_MAX * (16 + 8 * KS_MAX_LABEL_WORDS) + (size_t)STREAM_BATCH_MAX * 12 + 64;
+        if (!s->h_stream) CU_TRY(cudaHostAlloc(&s->h_stream, h_cap, cudaHostAllocDefault));
+        uint8_t* h_in = static_cast<uint8_t*>(s->h_stream);
+        uint8_t* h_out = h_in + (size_t)STREAM_BATCH_MAX * (16 + 8 * KS_MAX_LABEL_WORDS);
+        memcpy(h_in, pods->req_cpu, n * 8);
+        memcpy(h_in + n * 8, pods->req_mem, n * 8);
+        memcpy(h_in + n * 16, pods->sel, n * 8 * W);
         const uint32_t grid = std::max(1u, std::min<uint32_t>((uint32_t)s->sms, (s->N + 127u) / 128u));
-        CU_TRY(s->st_rc.ensure(STREAM_BATCH_MAX * 8));
-        CU_TRY(s->st_rm.ensure(STREAM_BATCH_MAX * 8));
-        CU_TRY(s->st_sel.ensure((size_t)STREAM_BATCH_MAX * 8 * KS_MAX_LABEL_WORDS));
-        CU_TRY(s->st_idx.ensure(STREAM_BATCH_MAX * 4));
-        CU_TRY(s->st_score.ensure(STREAM_BATCH_MAX * 8));
+        CU_TRY(s->st_rc.ensure((size_t)STREAM_BATCH_MAX * (16 + 8 * KS_MAX_LABEL_WORDS))); // device copy of the input block
+        CU_TRY(s->st_score.ensure((size_t)STREAM_BATCH_MAX * 12 + 64));                      // device copy of the result block
         CU_TRY(s->sb_pkey.ensure((size_t)STREAM_BATCH_MAX * s->sms * 8));
         CU_TRY(s->sb_pidx.ensure((size_t)STREAM_BATCH_MAX * s->sms * 4));
         CU_TRY(s->sb_pend.ensure(2 * STREAM_BATCH_MAX * 4));
-        CU_TRY(s->sb_ctl.ensure(16));
         cudaStream_t st = s->stream;
-        CU_TRY(cudaMemcpyAsync(s->st_rc.p, h + o_rc, n * 8, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(s->st_rm.p, h + o_rm, n * 8, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(s->st_sel.p, h + o_sel, n * 8 * W, cudaMemcpyHostToDevice, st));
+        uint8_t* d_in = s->st_rc.as<uint8_t>();
+        uint8_t* d_out = s->st_score.as<uint8_t>();
+        CU_TRY(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
         StreamBatchArgs a;
         a.N = s->N;
         a.Npad = s->Npad;
@@ -881,28 +880,26 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
         a.free_mem = s->free_mem.as<int64_t>();
         a.policy = policy;
         a.m = (uint32_t)n;
-        a.req_cpu = s->st_rc.as<int64_t>();
-        a.req_mem = s->st_rm.as<int64_t>();
-        a.sel = s->st_sel.as<uint64_t>();
+        a.req_cpu = reinterpret_cast<const int64_t*>(d_in);
+        a.req_mem = reinterpret_cast<const int64_t*>(d_in + n * 8);
+        a.sel = reinterpret_cast<const uint64_t*>(d_in + n * 16);
         a.pkey = s->sb_pkey.as<int64_t>();
         a.pidx = s->sb_pidx.as<int32_t>();
         a.pend = s->sb_pend.as<uint32_t>();
-        a.ctl = s->sb_ctl.as<uint32_t>();
-        a.out_idx = s->st_idx.as<int32_t>();
-        a.out_score = s->st_score.as<int64_t>();
+        a.ctl = reinterpret_cast<uint32_t*>(d_out + o_ctl);
+        a.out_idx = reinterpret_cast<int32_t*>(d_out + o_idx);
+        a.out_score = reinterpret_cast<int64_t*>(d_out + o_score);
         a.max_rounds = (uint32_t)n + 1;
         a.grid = grid;
         s->derived_dirty = true; // free[] changes: the bit-parallel index is stale
         s->version++;
         cudaError_t e = launch_stream_batch(a, W, st);
         if (e != cudaSuccess) return fail(KS_ERR_CUDA, "k_stream_batch launch failed: %s", cudaGetErrorString(e));
-        CU_TRY(cudaMemcpyAsync(h + o_idx, s->st_idx.p, n * 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(h + o_score, s->st_score.p, n * 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(h + o_ctl, s->sb_ctl.p, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
-        memcpy(out_node_idx, h + o_idx, n * 4);
-        if (out_score) memcpy(out_score, h + o_score, n * 8);
-        if (out_rounds) *out_rounds = reinterpret_cast<const uint32_t*>(h + o_ctl)[1];
+        memcpy(out_node_idx, h_out + o_idx, n * 4);
+        if (out_score) memcpy(out_score, h_out + o_score, n * 8);
+        if (out_rounds) *out_rounds = reinterpret_cast<const uint32_t*>(h_out + o_ctl)[1];
         s->last_path = "stream_batch";
         return KS_OK;
     }

@@ -1,17 +1,18 @@
 // ks_bitpar.cu — bit-parallel fused feasibility pass for sm_100a (design notes in ks_bitpar.h).
 //
-//   per snapshot   k_node_splitters/_bucket/_scatter/_rank  sample sort: global rank of every node in free_cpu /
-//                                   free_mem / priority order
-//                  k_build_tile     per-tile prefix tables, bucket base+membership, label-pair columns
-//                                   (built twice: node-index order for the mask, priority order for argmax)
-//   per call       k_pod_ranks      request -> global rank threshold (splitters in smem + short global search)
-//                  k_mask_bitpar    persistent; column-block index blob staged in shared memory by TMA bulk
-//                                   copies (cp.async.bulk + mbarrier); 1 thread = 1 (pod, 256-node tile):
-//                                   2x(base + popc(member & low)) -> 2 table rows -> AND label columns ->
-//                                   two 128-bit stores of the mask row segment; counts by segmented warp
-//                                   shuffle + one RED per (pod, warp)
-//                  k_first_fit_head/_tail  argmax KS_SCORE_LEFTOVER = first feasible node in priority order, found
-//                                   256 nodes at a time with the same table machinery (early exit)
+//   per snapshot   k_node_bound, k_node_splitters/_bucket/_scatter/_rank  sample sort: global position of every node in
+//                                   free_cpu / free_mem / leftover-priority / least-allocated-bound order
+//                  k_build_cbtile   per column block (8 tiles of 256 nodes, node-index order): octet-interleaved prefix
+//                                   tables + label-pair columns, staged in shared memory by the mask kernel
+//                  k_build_ranks    rank tables: tile-local rank of every possible threshold (read through L1/L2)
+//                  k_build_tile     flat indexes in priority order / bound order for the argmax kernels
+//   per call       k_pod_ranks      request -> global rank threshold (splitters in smem + short global search), histogram
+//                  k_bucket_scan / k_pod_scatter   counting sort of the pods; one 16-byte record per sorted pod
+//                  k_mask_rows      persistent, 1 CTA per SM; table blob staged by TMA bulk copies (cp.async.bulk + mbarrier);
+//                                   8 lanes = the 8 tiles of one pod: rank load -> 2 table rows (+ label columns) -> AND ->
+//                                   one 256-bit store per lane; counts by shuffle + one RED per pod and column block
+//                  k_first_fit_head/_tail  argmax KS_SCORE_LEFTOVER = first feasible node in priority order (early exit)
+//                  k_least_alloc    argmax KS_SCORE_LEAST_ALLOCATED: bound-ordered scan, exact scores, early exit
 // Semantics per cell are exactly predicates.rs:42 / :45-61 (see include/ksched.h); only the evaluation
 // order differs, and every output is compared bit-for-bit with the oracle in tests/.
 #include "ks_bitpar.h"
@@ -44,8 +45,24 @@ __device__ __forceinline__ int64_t least_alloc_bound(const NodeTable& nt, uint32
     const int64_t pm = am > 0 ? (fm * 100) / am : 0;
     return (pc + pm) / 2;
 }
+// prio[0..Npad) = leftover priority, prio[Npad..Npad+N) = least-allocated bound (k_node_bound, once per build)
 __device__ __forceinline__ int64_t order_value(const NodeTable& nt, const int64_t* __restrict__ prio, int k, uint32_t n) {
-    return k == 0 ? nt.free_cpu[n] : (k == 1 ? nt.free_mem[n] : (k == 2 ? -prio[n] : -least_alloc_bound(nt, n)));
+    return k == 0 ? nt.free_cpu[n] : (k == 1 ? nt.free_mem[n] : (k == 2 ? -prio[n] : -prio[(size_t)nt.Npad + n]));
+}
+
+// least-allocated bound of every node + which label bits some node carries (a selector naming a dead bit is
+// infeasible everywhere: the argmax kernels answer it without scanning)
+__global__ void __launch_bounds__(256) k_node_bound(NodeTable nt, int64_t* __restrict__ bound, unsigned long long* __restrict__ live) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nt.N) return;
+    bound[n] = least_alloc_bound(nt, n);
+    long long* amax = reinterpret_cast<long long*>(live + KS_MAX_LABEL_WORDS); // [2]: max allocatable cpu, memory
+    if (nt.alloc_cpu[n] > __ldcg(amax)) atomicMax(amax, (long long)nt.alloc_cpu[n]);
+    if (nt.alloc_mem[n] > __ldcg(amax + 1)) atomicMax(amax + 1, (long long)nt.alloc_mem[n]);
+    for (uint32_t w = 0; w < nt.W; w++) {
+        const unsigned long long v = nt.labels[(size_t)w * nt.Npad + n];
+        if (v & ~__ldcg(live + w)) atomicOr(live + w, v);
+    }
 }
 
 constexpr int RANK_SAMPLES = 1024, RANK_BUCKETS = 256;
@@ -175,7 +192,7 @@ __global__ void __launch_bounds__(256)
         if (pos[1] % spl_stride == 0) splM[pos[1] / spl_stride] = fm;
         ord_prio[pos[2]] = prio[n];
         ord_idx[pos[2]] = (int32_t)n;
-        ordL_s0[pos[3]] = least_alloc_bound(nt, n);
+        ordL_s0[pos[3]] = prio[(size_t)nt.Npad + n];
         ordL_idx[pos[3]] = (int32_t)n;
     } else if (n < Nord) { // padding of the priority / bound orders
         ord_prio[n] = INT64_MIN;
@@ -185,25 +202,16 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// KS_MASK_KERNEL (A/B switch, read once): "rows" (default) = k_mask_rows; "quads" = the round-1 kernel
-// k_mask_bitpar (kept for one A/B session, then removed)
-static bool use_rows_kernel() {
-    static const bool v = [] {
-        const char* e = getenv("KS_MASK_KERNEL");
-        return !(e && strcmp(e, "quads") == 0);
-    }();
-    return v;
-}
-static int rows_count_mode() { // 0 = 8 POPC per item, 1 = carry-save tree + 4 POPC
-    static const int v = [] {
-        const char* e = getenv("KS_ROWS_COUNT");
-        return e ? atoi(e) : 0;
-    }();
-    return v;
-}
-static int rows_hint_mode() { // 1 = mask stores carry an L2 evict-first policy, rank loads evict-last
-    static const int v = [] {
+static int rows_hint_mode() { // 1 (default) = mask stores carry an L2 evict-first policy, rank loads evict-last
+    static const int v = [] {   // (measured: C3 1.681 -> 1.642 ms, C2 36.6 -> 34.7 us; profiles/r02_experiments.txt)
         const char* e = getenv("KS_ROWS_HINT");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+static int rows_sort_mode() { // 0 = 2-D threshold grid (round 1); 1 = exact cpu threshold (runs of pods share their cpu rows)
+    static const int v = [] {
+        const char* e = getenv("KS_ROWS_SORT");
         return e ? atoi(e) : 0;
     }();
     return v;
@@ -444,6 +452,7 @@ __device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x
 struct BucketParams {
     uint32_t sh_c, sh_m, nb_m, n_bins; // n_bins = 4 selector classes x threshold grid
     uint32_t grid_bins, W;
+    uint32_t exact; // 1: bin = (selector class, exact cpu threshold): consecutive sorted pods share their cpu table rows
 };
 
 __global__ void __launch_bounds__(256)
@@ -473,24 +482,26 @@ __global__ void __launch_bounds__(256)
             out[r] = ans;
         }
         rk[p] = make_uint2(out[0], out[1]);
-        if (cnt_zero) cnt_zero[p] = 0; // k_mask_bitpar accumulates feasible counts with REDs
+        if (cnt_zero) cnt_zero[p] = 0; // k_mask_rows accumulates feasible counts with REDs
         if (hist) {
             // most significant key: number of required label pairs (0,1,2,3+), so that the lanes of a warp run the
             // same number of column ANDs in the mask kernel (no divergence in its selector loop)
             uint32_t n_req = 0;
             for (uint32_t w = 0; w < bk.W; w++) n_req += __popcll(__ldg(pv.sel + (size_t)p * bk.W + w));
-            const uint32_t bin = min(n_req, 3u) * bk.grid_bins + (out[0] >> bk.sh_c) * bk.nb_m + (out[1] >> bk.sh_m);
+            const uint32_t bin = bk.exact ? min(n_req, 3u) * bk.grid_bins + out[0]
+                                          : min(n_req, 3u) * bk.grid_bins + (out[0] >> bk.sh_c) * bk.nb_m + (out[1] >> bk.sh_m);
             pod_bin[p] = bin;
             pod_loc[p] = atomicAdd(hist + bin, 1u); // arrival order inside a bin is irrelevant to every output
         }
     }
 }
 
-// exclusive scan of the <=64k-bin histogram: CTA c scans bins [1024c, 1024c+1024) in place and publishes its
-// total; k_pod_scatter adds the prefix over the (<=64) chunk totals
+// exclusive scan of the bin histogram: CTA c scans bins [1024c, 1024c+1024) in place and publishes its total; the last
+// CTA to finish turns the (<= 1024) chunk totals into exclusive offsets, so k_pod_scatter adds one number per pod
 __global__ void __launch_bounds__(1024)
-    k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_bins, uint32_t* __restrict__ chunk_total) {
+    k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_bins, uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ done) {
     __shared__ uint32_t s_warp[32];
+    __shared__ bool s_last;
     const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
     const uint32_t v = i < n_bins ? hist[i] : 0;
     uint32_t inc = v;
@@ -513,7 +524,37 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     if (i < n_bins) hist[i] = inc - v + (warp ? s_warp[warp - 1] : 0);
-    if (threadIdx.x == 1023) chunk_total[blockIdx.x] = s_warp[31];
+    if (threadIdx.x == 1023) {
+        chunk_total[blockIdx.x] = s_warp[31];
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last CTA: exclusive scan of the chunk totals (gridDim.x <= 1024), in place
+    if (threadIdx.x == 0) *done = 0; // ready for the next call
+    const uint32_t t = threadIdx.x;
+    const uint32_t cv = t < gridDim.x ? __ldcg(chunk_total + t) : 0;
+    uint32_t cinc = cv;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, cinc, off);
+        if (lane >= (uint32_t)off) cinc += o;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = cinc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= (uint32_t)off) w += o;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (t < gridDim.x) chunk_total[t] = cinc - cv + (warp ? s_warp[warp - 1] : 0);
 }
 
 // counting-sort scatter: pods in bucket order with everything the mask kernel needs, contiguous.
@@ -527,23 +568,16 @@ constexpr uint32_t RW_PID_NONE = 0xFFFFFFFFu;
 template <int W>
 __global__ void __launch_bounds__(256)
     k_pod_scatter(PodView pv, const uint2* __restrict__ rk, const uint32_t* __restrict__ start,
-                  const uint32_t* __restrict__ chunk_total, uint32_t n_chunks, const uint32_t* __restrict__ pod_bin,
-                  const uint32_t* __restrict__ pod_loc, uint2* __restrict__ rk_s, uint32_t* __restrict__ pid_s,
-                  unsigned long long* __restrict__ sel_s, uint4* __restrict__ rec_s) {
-    __shared__ uint32_t s_chunk[64];
-    if (threadIdx.x < 64) { // exclusive prefix over the <=64 chunk totals
-        uint32_t acc = 0;
-        for (uint32_t k = 0; k < threadIdx.x && k < n_chunks; k++) acc += chunk_total[k];
-        s_chunk[threadIdx.x] = acc;
-    }
-    __syncthreads();
+                  const uint32_t* __restrict__ chunk_off, uint32_t n_chunks, const uint32_t* __restrict__ pod_bin,
+                  const uint32_t* __restrict__ pod_loc, unsigned long long* __restrict__ sel_s, uint4* __restrict__ rec_s) {
+    (void)n_chunks;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= pv.P) {
-        if (rec_s && p < ((pv.P + 7u) & ~7u)) rec_s[p] = make_uint4(0, 0, RW_PID_NONE, 0); // padding of the last group
+        if (p < ((pv.P + 7u) & ~7u)) rec_s[p] = make_uint4(0, 0, RW_PID_NONE, 0); // padding of the last group
         return;
     }
     const uint32_t bin = pod_bin[p];
-    const uint32_t q = start[bin] + s_chunk[bin >> 10] + pod_loc[p];
+    const uint32_t q = start[bin] + __ldg(chunk_off + (bin >> 10)) + pod_loc[p];
     const uint2 r = rk[p];
     uint32_t cols = 0, n_req = 0;
 #pragma unroll
@@ -557,159 +591,7 @@ __global__ void __launch_bounds__(256)
             n_req++;
         }
     }
-    if (rk_s) {
-        rk_s[q] = r;
-        pid_s[q] = p;
-    }
-    if (rec_s) rec_s[q] = make_uint4(r.x, r.y, p, n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30)));
-}
-
-// Mask kernel.  Pods arrive bucket-sorted by threshold (k_pod_scatter).  One warp = 8 consecutive sorted pods x
-// 4 tiles, tile index fastest: lanes 4j..4j+3 are one pod's 4 tiles and write 128 contiguous bytes of its mask
-// row with one 256-bit store each.  A shared-memory phase of a 128-bit load (8 lanes) is 2 neighbouring pods x 4
-// tiles: the 4 tiles sit in distinct bank groups (quad-interleaved tables) and, with SWAP, the two pods read
-// opposite 16-byte halves of their 32-byte rows, so the 8 lanes always touch 8 different 16-byte bank groups -
-// every row / column load is one wavefront per phase whatever rows the two pods need.
-template <int W, bool SWAP>
-__global__ void __launch_bounds__(BP_THREADS, 1)
-    k_mask_bitpar(const uint8_t* __restrict__ blob, BitparLayout lay, uint32_t P, const uint2* __restrict__ rk_s,
-                  const uint32_t* __restrict__ pid_s, const unsigned long long* __restrict__ sel_s, OutView ov,
-                  uint32_t ctas_per_cb) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, psub = lane >> 2, tsub = lane & 3;
-    const uint32_t nt = lay.nt;
-    const uint32_t n_groups = (P + 7) / 8; // groups of 8 sorted pods
-    // k = ctas_per_cb CTAs share one column block and take its pod groups round-robin (the sort order clusters
-    // pods by selector size, so contiguous ranges would be unbalanced); with more column blocks than CTAs, k = 1
-    // and a CTA walks several column blocks
-    const uint32_t cta_in_cb = blockIdx.x % ctas_per_cb;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-
-    // plain shared-memory loads (not volatile asm): the two tile passes of a thread may overlap; the mbarrier wait
-    // below carries a memory clobber, so nothing is hoisted above it
-    const uint16_t* s_baseC = reinterpret_cast<const uint16_t*>(smem + lay.off_baseC);
-    const uint16_t* s_baseM = reinterpret_cast<const uint16_t*>(smem + lay.off_baseM);
-    const unsigned long long* s_membC = reinterpret_cast<const unsigned long long*>(smem + lay.off_membC);
-    const unsigned long long* s_membM = reinterpret_cast<const unsigned long long*>(smem + lay.off_membM);
-    const uint8_t* s_pairs = smem + lay.off_pairs;
-    const bool want_cnt = ov.cnt != nullptr, want_mask = ov.mask != nullptr;
-    // SWAP: the odd pod of a phase reads the upper 16 bytes of every 32-byte row first, the even pod the lower 16:
-    // the 8 lanes of a phase then always hit 8 different 16-byte bank groups (tile x half), whatever rows and
-    // label-pair columns the two pods need.  h0/h1 = index of the half loaded first / second.
-    const uint32_t h0 = SWAP ? (psub & 1u) : 0u, h1 = h0 ^ 1u;
-    const uint32_t pstride = lay.pstride;
-
-    for (uint32_t cb = blockIdx.x / ctas_per_cb; cb < lay.ncb; cb += gridDim.x / ctas_per_cb) {
-        const uint32_t gb = n_groups;
-
-        // ---- stage this column block's index blob: TMA bulk copies signalled on one mbarrier ----
-        __syncthreads(); // all generic-proxy reads of the previous blob are done
-        if (tid == 0) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bar, lay.blob_bytes);
-            const uint8_t* src = blob + (size_t)cb * lay.blob_bytes;
-            for (uint32_t off = 0; off < lay.blob_bytes; off += 32768u)
-                tma_bulk_g2s(smem + off, src + off, min(32768u, lay.blob_bytes - off), &bar);
-        }
-
-        const uint32_t g_step = ctas_per_cb * (BP_THREADS / 32);
-        uint32_t g = cta_in_cb * (BP_THREADS / 32) + warp;
-        uint32_t q = g * 8 + psub;
-        bool act = g < gb && q < P;
-        uint2 r = act ? __ldg(rk_s + q) : make_uint2(0, 0); // prefetch while the blob is in flight
-        uint32_t pid = act ? __ldg(pid_s + q) : 0;
-        unsigned long long sel[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) sel[w] = act ? __ldg(sel_s + (size_t)q * W + w) : 0ull;
-
-        mbar_wait(&bar, phase);
-        phase ^= 1;
-
-        while (g < gb) { // warp-uniform
-            const uint2 cr = r;
-            const uint32_t cpid = pid;
-            const bool cact = act;
-            unsigned long long csel[W];
-#pragma unroll
-            for (int w = 0; w < W; w++) csel[w] = sel[w];
-            // software prefetch of the next group's pod data
-            g += g_step;
-            q = g * 8 + psub;
-            act = g < gb && q < P;
-            if (act) {
-                r = __ldg(rk_s + q);
-                pid = __ldg(pid_s + q);
-#pragma unroll
-                for (int w = 0; w < W; w++) sel[w] = __ldg(sel_s + (size_t)q * W + w);
-            }
-
-            uint32_t c = 0;
-            const uint32_t hc = (cr.x >> 6) * nt, hm = (cr.y >> 6) * nt;
-            const unsigned long long lowC = (1ull << (cr.x & 63)) - 1ull, lowM = (1ull << (cr.y & 63)) - 1ull;
-            for (uint32_t tb = 0; tb < nt; tb += 4) {
-                const uint32_t ct = tb + tsub;
-                if (cact && ct < nt) {
-                    // tile-local rank of each threshold = tile nodes at global positions < threshold
-                    const uint32_t bc = s_baseC[hc + ct], bm = s_baseM[hm + ct];
-                    const unsigned long long mc = s_membC[hc + ct], mm = s_membM[hm + ct];
-                    const uint32_t rankC = bc + __popcll(mc & lowC);
-                    const uint32_t rankM = bm + __popcll(mm & lowM);
-                    const uint4* tc = reinterpret_cast<const uint4*>(smem + lay.off_tabC + table_row_offset(ct, rankC));
-                    const uint4* tm = reinterpret_cast<const uint4*>(smem + lay.off_tabM + table_row_offset(ct, rankM));
-                    const uint4 c0 = tc[h0], c1 = tc[h1];
-                    const uint4 m0 = tm[h0], m1 = tm[h1];
-                    uint4 a = make_uint4(c0.x & m0.x, c0.y & m0.y, c0.z & m0.z, c0.w & m0.w);
-                    uint4 b = make_uint4(c1.x & m1.x, c1.y & m1.y, c1.z & m1.z, c1.w & m1.w);
-#pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        unsigned long long bits = csel[w];
-                        while (bits) { // AND the node column of every required (key,value) pair (predicates.rs:48-53)
-                            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-                            bits &= bits - 1;
-                            const uint4* col = reinterpret_cast<const uint4*>(s_pairs + bit * pstride + ct * 32);
-                            const uint4 q0 = col[h0], q1 = col[h1];
-                            a.x &= q0.x; a.y &= q0.y; a.z &= q0.z; a.w &= q0.w;
-                            b.x &= q1.x; b.y &= q1.y; b.z &= q1.z; b.w &= q1.w;
-                        }
-                    }
-                    c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) +
-                         __popc(b.w);
-                    if (want_mask) {
-                        const uint32_t word = (cb * nt + ct) * 8;
-                        if (word < ov.mask_valid_words) {
-                            uint32_t* dst = ov.mask + (size_t)cpid * ov.mask_row_words + word; // 32-byte aligned
-                            if (SWAP) // a = half h0, b = half h1: two predicated stores, each lane runs one
-                                asm volatile("{ .reg .pred p; setp.ne.u32 p, %9, 0;\n\t"
-                                             "@p st.global.v8.b32 [%0], {%5,%6,%7,%8,%1,%2,%3,%4};\n\t"
-                                             "@!p st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}; }" ::"l"(dst),
-                                             "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w),
-                                             "r"(h0)
-                                             : "memory");
-                            else
-                                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x),
-                                             "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                                             : "memory");
-                        }
-                    }
-                }
-            }
-            if (want_cnt) { // the 4 lanes of a pod are adjacent
-                c += __shfl_xor_sync(0xffffffffu, c, 1);
-                c += __shfl_xor_sync(0xffffffffu, c, 2);
-                if (cact && tsub == 0) {
-                    if (lay.ncb == 1) ov.cnt[cpid] = c; // single writer, no zero-init needed
-                    else if (c) atomicAdd(&ov.cnt[cpid], c);
-                }
-            }
-        }
-    }
+    rec_s[q] = make_uint4(r.x, r.y, p, n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30)));
 }
 
 // ------------------------------------------------------------------------------------------------ rows kernel
@@ -750,12 +632,6 @@ __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x 
 __device__ __forceinline__ uint4 and4(uint4 a, uint4 b, uint4 c) {
     return make_uint4(a.x & b.x & c.x, a.y & b.y & c.y, a.z & b.z & c.z, a.w & b.w & c.w);
 }
-// carry-save adder on bit columns: (a, b, c) -> sum (weight 1) and carry (weight 2), one LOP3 each
-__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
-    sum = a ^ b ^ c;
-    carry = (a & b) | (a & c) | (b & c);
-}
-
 struct RowsParams { // kernel parameters stay in the constant bank: the loop reads them from there on demand
     const uint8_t* blob;
     RowsLayout lay;
@@ -770,11 +646,17 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
 
 // one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
 // a_tab = shared-window address of granule t of line 0 of tabC; tabM and the pair columns sit at constant offsets.
-template <int W, bool PSMEM, int CNT, bool HINT>
+// c0/c1 = the pod's cpu table row; `reuse` = they already hold the right row (the previous pod of this thread has the
+// same cpu threshold: with the exact sort that is the common case, P >> N makes runs of equal thresholds)
+template <int W, bool PSMEM, bool HINT>
 __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_tab, uint32_t cb, uint32_t t, uint32_t* mask_col,
-                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q, uint64_t pol_st) {
+                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q, uint64_t pol_st,
+                                              uint4& c0, uint4& c1, bool reuse) {
     const uint32_t aC = a_tab + rC * RW_LINE, aM = a_tab + rM * RW_LINE;
-    const uint4 c0 = lds128(aC), c1 = lds128(aC + 128);
+    if (!reuse) {
+        c0 = lds128(aC);
+        c1 = lds128(aC + 128);
+    }
     const uint4 m0 = lds128(aM + RW_TAB_BYTES), m1 = lds128(aM + RW_TAB_BYTES + 128);
     uint4 a, b;
     auto column = [&](uint32_t bit, uint4& q0, uint4& q1) { // node column of one required pair (predicates.rs:48-53)
@@ -835,19 +717,10 @@ __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_
                          "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                          : "memory");
     }
-    if (CNT == 0) {
-        return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-    } else { // 8 words -> {s3, b.w} (weight 1), t (weight 2), f (weight 4): 4 POPC + 8 LOP3
-        uint32_t s1, c1_, s2, c2_, s3, c3_, tw, fw;
-        csa(a.x, a.y, a.z, s1, c1_);
-        csa(a.w, b.x, b.y, s2, c2_);
-        csa(s1, s2, b.z, s3, c3_);
-        csa(c1_, c2_, c3_, tw, fw);
-        return __popc(s3) + __popc(b.w) + 2 * __popc(tw) + 4 * __popc(fw);
-    }
+    return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
 }
 
-template <int W, bool PSMEM, int CNT, bool HINT>
+template <int W, bool PSMEM, bool HINT>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -885,7 +758,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         }
         // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
         const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
-        const uint4* rec_t = opaque_ptr(prm.rec_s + ps);
+        const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
 
         // pod records are fetched one iteration ahead; loads are unconditional (slot clamped into the list),
         // validity only decides whether the item is computed
@@ -894,7 +767,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
             const uint4* rp = rec_t + (size_t)min(group_of(j), last_grp) * 8u;
             ra = __ldg(rp);
-            rb = __ldg(rp + 4);
+            rb = __ldg(rp + 1);
         };
         uint32_t j = j0 + warp;
         uint4 nA, nB; // records of the next iteration
@@ -911,15 +784,16 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         for (; j < j1; j += 32) { // warp-uniform
             const uint4 rA = nA, rB = nB;
             uint32_t rCa, rMa, rCb, rMb;
+            const bool same_c = rB.x == rA.x; // same cpu threshold: same rank, same table row
             if (HINT) {
                 rCa = ldg_u16_keep(rk_t + (size_t)rA.x * 16u, pol_ld);
                 rMa = ldg_u16_keep(rk_t + (size_t)rA.y * 16u + 8, pol_ld);
-                rCb = ldg_u16_keep(rk_t + (size_t)rB.x * 16u, pol_ld);
+                rCb = same_c ? rCa : ldg_u16_keep(rk_t + (size_t)rB.x * 16u, pol_ld);
                 rMb = ldg_u16_keep(rk_t + (size_t)rB.y * 16u + 8, pol_ld);
             } else {
                 rCa = ldg_u16(rk_t + (size_t)rA.x * 16u);
                 rMa = ldg_u16(rk_t + (size_t)rA.y * 16u + 8);
-                rCb = ldg_u16(rk_t + (size_t)rB.x * 16u);
+                rCb = same_c ? rCa : ldg_u16(rk_t + (size_t)rB.x * 16u);
                 rMb = ldg_u16(rk_t + (size_t)rB.y * 16u + 8);
             }
             fetch_rec(j + 32, nA, nB);
@@ -927,8 +801,11 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
             const uint32_t grp0 = group_of(j);
             if (grp0 > last_grp) continue; // slot past the end of its stratum
 
-            const uint32_t cA = rows_item<W, PSMEM, CNT, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + ps, pol_st);
-            const uint32_t cB = rows_item<W, PSMEM, CNT, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 4u + ps, pol_st);
+            uint4 c0, c1;
+            const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps,
+                                                               pol_st, c0, c1, false);
+            const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u,
+                                                               pol_st, c0, c1, same_c);
             if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
                 uint32_t c = cA | (cB << 16);
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -1029,13 +906,22 @@ template <int W>
 __global__ void __launch_bounds__(256)
     k_first_fit_head(const uint8_t* __restrict__ blobP, BitparLayout lay, const int32_t* __restrict__ ord_idx,
                      const int64_t* __restrict__ ord_prio, PodView pv, const uint2* __restrict__ rk, OutView ov,
-                     uint32_t* __restrict__ tail_list, uint32_t* __restrict__ tail_count, PeerOut po, bool last_kernel) {
+                     uint32_t* __restrict__ tail_list, uint32_t* __restrict__ tail_count, PeerOut po, bool last_kernel,
+                     const unsigned long long* __restrict__ live, uint32_t N) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < pv.P) {
-        const PodThreshold t = pod_threshold(blobP, lay, __ldg(rk + p));
+        const uint2 r = __ldg(rk + p);
+        const PodThreshold t = pod_threshold(blobP, lay, r);
         unsigned long long sel[W];
+        bool dead = r.x >= N || r.y >= N; // the request exceeds every node's free cpu / memory
 #pragma unroll
-        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+        for (int w = 0; w < W; w++) {
+            sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+            dead |= (sel[w] & ~__ldg(live + w)) != 0; // a required pair that no node carries
+        }
+        if (dead) { // infeasible everywhere: answered without scanning the 196 tiles in the tail kernel
+            write_binding(ov, pv, po, p, -1, ord_idx, ord_prio);
+        } else {
         uint32_t m0[8], m1[8];
         ptile_mask<W>(blobP, lay, t, sel, 0, m0);
         ptile_mask<W>(blobP, lay, t, sel, min(1u, lay.nt - 1), m1);
@@ -1046,6 +932,7 @@ __global__ void __launch_bounds__(256)
         }
         if (slot >= 0 || lay.nt <= FF_HEAD_TILES) write_binding(ov, pv, po, p, slot, ord_idx, ord_prio);
         else tail_list[atomicAdd(tail_count, 1u)] = p; // order of the list does not affect any result
+        }
     }
     if (last_kernel) exchange_signal(po); // no tail kernel follows: this rank's bindings are complete
 }
@@ -1154,20 +1041,30 @@ __device__ __forceinline__ int64_t least_alloc_score(const NodeEval& e, int64_t 
 template <int W>
 __global__ void __launch_bounds__(256)
     k_least_alloc(const uint8_t* __restrict__ blobL, BitparLayout lay, const NodeEval* __restrict__ ev,
-                  const int64_t* __restrict__ ordL_s0, PodView pv, const uint2* __restrict__ rk, OutView ov, PeerOut po) {
+                  const int64_t* __restrict__ ordL_s0, PodView pv, const uint2* __restrict__ rk, OutView ov, PeerOut po,
+                  const unsigned long long* __restrict__ live, uint32_t N) {
+    const longlong2 amax = *reinterpret_cast<const longlong2*>(live + KS_MAX_LABEL_WORDS); // max allocatable cpu / memory
     const uint32_t lane = threadIdx.x & 31, wq = lane & 7, quarter = lane >> 3;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < pv.P; p += warps) {
-        const PodThreshold t = pod_threshold(blobL, lay, __ldg(rk + p));
+        const uint2 r = __ldg(rk + p);
+        const PodThreshold t = pod_threshold(blobL, lay, r);
         unsigned long long sel[W];
+        bool dead = r.x >= N || r.y >= N; // the request exceeds every node's free cpu / memory
 #pragma unroll
-        for (int w = 0; w < W; w++) sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+        for (int w = 0; w < W; w++) {
+            sel[w] = __ldg(pv.sel + (size_t)p * W + w);
+            dead |= (sel[w] & ~__ldg(live + w)) != 0; // a required pair that no node carries
+        }
         const int64_t rc = __ldg(pv.req_cpu + p), rm = __ldg(pv.req_mem + p);
         const bool bounded = rc >= 0 && rm >= 0; // else the bound does not hold: no early exit
+        // per-pod slack: floor((f-r)*100/a) <= floor(f*100/a) - floor(r*100/a) and a <= a_max, so every feasible cell
+        // scores <= bound(n) - D with D = (rc*100/ac_max + rm*100/am_max) / 2
+        const int64_t D = bounded ? ((amax.x > 0 ? (rc * 100) / amax.x : 0) + (amax.y > 0 ? (rm * 100) / amax.y : 0)) / 2 : 0;
         int64_t best = INT64_MIN;
         int32_t bidx = -1;
-        for (uint32_t k = 0; k < lay.nt; k++) {
-            if (bounded && bidx >= 0 && best > __ldg(ordL_s0 + (size_t)k * BP_TILE)) break; // warp-uniform
+        for (uint32_t k = 0; k < (dead ? 0u : lay.nt); k++) {
+            if (bounded && bidx >= 0 && best > __ldg(ordL_s0 + (size_t)k * BP_TILE) - D) break; // warp-uniform
             uint32_t m[8];
             ptile_mask<W>(blobL, lay, t, sel, k, m);
             uint32_t bits = 0; // this lane's share of the tile's feasible slots
@@ -1240,20 +1137,6 @@ static bool fill_offsets(BitparLayout* lay, uint32_t W) {
     return true;
 }
 
-// column-block layout for the mask kernel: as many tiles per block as fit in shared memory
-static bool make_layout_smem(uint32_t N, uint32_t W, BitparLayout* lay) {
-    const uint32_t n_tiles = (N + BP_TILE - 1) / BP_TILE;
-    lay->nb = (N >> 6) + 1;
-    const uint64_t avail = BP_SMEM_MAX - 1024;
-    const uint32_t nt_max = (uint32_t)std::min<uint64_t>(32, avail / per_tile_bytes(lay->nb, W));
-    if (n_tiles == 0 || nt_max == 0) return false;
-    uint32_t nt = 1; // power of two: the lanes of one pod form an aligned group of a warp
-    while (nt * 2 <= nt_max && nt < n_tiles) nt *= 2;
-    lay->nt = nt;
-    lay->ncb = (n_tiles + nt - 1) / nt;
-    return fill_offsets(lay, W) && lay->blob_bytes <= (uint32_t)BP_SMEM_MAX;
-}
-
 // "rows" format (ks_bitpar.h): column blocks of RW_TILES tiles; the pair columns are staged with the tables when
 // everything fits in shared memory (W <= 4), else they are read through L1/L2
 static bool make_layout_rows(uint32_t N, uint32_t W, RowsLayout* lay) {
@@ -1292,10 +1175,10 @@ static cudaError_t regrow(T*& p, size_t count) {
 
 void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
-                    ix.ord_idx, ix.splC,  ix.splM,  ix.blob,    ix.blobP,    ix.pod_ranks, ix.tail_list,
-                    ix.pod_bin, ix.pod_loc, ix.rk_s, ix.pid_s, ix.sel_s, ix.hist,
+                    ix.ord_idx, ix.splC,  ix.splM,  ix.blobP,    ix.pod_ranks, ix.tail_list,
+                    ix.pod_bin, ix.pod_loc, ix.sel_s, ix.hist,
                     ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.rec_s,
-                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL};
+                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.aux) cudaStreamDestroy(ix.aux);
@@ -1304,7 +1187,7 @@ void bitpar_release(BitparIndex& ix) {
     ix = BitparIndex();
 }
 
-cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* prio, cudaStream_t st) {
+cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cudaStream_t st) {
     ix.valid = false;
     ix.N = nt.N;
     ix.W = nt.W;
@@ -1339,6 +1222,12 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
         if ((e = regrow(ix.rk_spl_v, N_ORDERS * RANK_BUCKETS)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_spl_i, N_ORDERS * RANK_BUCKETS)) != cudaSuccess) return e;
     }
+    if (!ix.live) {
+        if ((e = regrow(ix.live, KS_MAX_LABEL_WORDS + 2)) != cudaSuccess) return e; // + max allocatable cpu, memory
+    }
+    if ((e = cudaMemsetAsync(ix.live, 0, (KS_MAX_LABEL_WORDS + 2) * 8, st)) != cudaSuccess) return e;
+    k_node_bound<<<(nt.N + 255) / 256, 256, 0, st>>>(nt, prio + nt.Npad, ix.live);
+    g_launches++;
     k_node_splitters<<<N_ORDERS, RANK_SAMPLES, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist);
     k_node_bucket<<<(nt.N + 255) / 256, 256, 0, st>>>(nt, prio, ix.rk_spl_v, ix.rk_spl_i, ix.rk_hist, ix.rk_bkt, ix.rk_loc);
     k_node_scatter<<<(nt.N + 255) / 256, 256, 0, st>>>(nt.N, ix.rk_hist, ix.rk_bkt, ix.rk_loc, ix.rk_perm);
@@ -1355,8 +1244,7 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
         if ((e = regrow(ix.blobL, cap)) != cudaSuccess) return e;
         ix.cap_blobP = cap;
     }
-    ix.rows_valid = false;
-    if (use_rows_kernel()) {
+    {
         RowsLayout lr{};
         if (!make_layout_rows(nt.N, nt.W, &lr)) return cudaSuccess; // direct path only
         const size_t need = (size_t)lr.ncb * lr.cb_stride;
@@ -1382,19 +1270,8 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* pr
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ix.lay_r = lr;
-        ix.rows_valid = true;
         lay.nt = RW_TILES; // bitpar_profitable: (pod, tile) items
         lay.ncb = lr.ncb;
-    } else {
-        if (!make_layout_smem(nt.N, nt.W, &lay)) return cudaSuccess; // direct path only
-        const size_t need = (size_t)lay.ncb * lay.blob_bytes;
-        if (need > ix.cap_blob) {
-            if ((e = regrow(ix.blob, need + need / 8)) != cudaSuccess) return e;
-            ix.cap_blob = need + need / 8;
-        }
-        k_build_tile<<<lay.ncb * lay.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, nullptr, ix.blob, lay);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ord_idx, ix.blobP, layP);
     g_launches++;
@@ -1419,15 +1296,9 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
 
 template <int W>
 static cudaError_t set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(k_mask_bitpar<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1452,8 +1323,6 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = regrow(ix.tail_list, cap + 1)) != cudaSuccess) return e; // [cap] = the list length counter
         if ((e = regrow(ix.pod_bin, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.pod_loc, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.rk_s, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.pid_s, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rec_s, cap + 8)) != cudaSuccess) return e;
         ix.cap_pods = cap;
         ix.cap_sel = 0;
@@ -1463,8 +1332,14 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = regrow(ix.sel_s, cap)) != cudaSuccess) return e;
         ix.cap_sel = cap;
     }
-    if (!ix.hist)
-        if ((e = regrow(ix.hist, 65536 + 64)) != cudaSuccess) return e; // bins + chunk totals
+    { // histogram: [cap_bins bins | 1024 chunk offsets | completion counter]
+        const size_t want_bins = std::max<size_t>(65536, ((size_t)4 * (ix.N + 1) + 1023) / 1024 * 1024);
+        if (want_bins > ix.cap_bins) {
+            if ((e = regrow(ix.hist, want_bins + 1024 + 16)) != cudaSuccess) return e;
+            if ((e = cudaMemset(ix.hist + want_bins + 1024, 0, 64)) != cudaSuccess) return e;
+            ix.cap_bins = want_bins;
+        }
+    }
     ix.epoch = g_regrow_epoch.load();
     return cudaSuccess;
 }
@@ -1478,8 +1353,12 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const bool need_mask_pass = L.ov.mask || L.ov.cnt;
     const int sms = ix.sms;
     // bucket grid over (rank_cpu, rank_mem): <= 64k bins, the finest shifts that fit
-    BucketParams bk{0, 0, 0, 0, 0, ix.W};
-    {
+    BucketParams bk{0, 0, 0, 0, 0, ix.W, 0};
+    if (rows_sort_mode() == 1 && (uint64_t)4 * (ix.N + 1) <= (1ull << 20)) {
+        bk.exact = 1; // bin = (selector class, exact cpu threshold)
+        bk.grid_bins = ix.N + 1;
+        bk.n_bins = 4 * bk.grid_bins;
+    } else {
         uint32_t sh = 0;
         while ((uint64_t)((ix.N >> sh) + 1) * ((ix.N >> sh) + 1) > 16384ull) sh++;
         bk.sh_c = sh;
@@ -1509,13 +1388,14 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), ix.aux)) != cudaSuccess) return e;
         if (L.policy == KS_SCORE_LEAST_ALLOCATED) {
             const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)P + 7) / 8);
-            k_least_alloc<W><<<grid, 256, 0, ix.aux>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po);
+            k_least_alloc<W><<<grid, 256, 0, ix.aux>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live,
+                                                       ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         } else {
             const bool has_tail = ix.layP.nt > FF_HEAD_TILES;
             k_first_fit_head<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks,
-                                                                     L.ov, ix.tail_list, tail_count, L.po, !has_tail);
+                                                                     L.ov, ix.tail_list, tail_count, L.po, !has_tail, ix.live, ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (has_tail) {
@@ -1547,25 +1427,23 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     if (want_bind && overlap_bind)
         if ((e = enqueue_bind()) != cudaSuccess) return e;
     if (need_mask_pass) {
-        const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 64
-        k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, ix.hist + 65536);
+        const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 1024
+        uint32_t* chunk_off = ix.hist + ix.cap_bins;
+        k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, chunk_off, chunk_off + 1024);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        const bool rows = ix.rows_valid;
-        k_pod_scatter<W><<<(((P + 7u) & ~7u) + 255) / 256, 256, 0, L.stream>>>(
-            L.pv, ix.pod_ranks, ix.hist, ix.hist + 65536, n_chunks, ix.pod_bin, ix.pod_loc, rows ? nullptr : ix.rk_s,
-            ix.pid_s, ix.sel_s, rows ? ix.rec_s : nullptr);
+        k_pod_scatter<W><<<(((P + 7u) & ~7u) + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.pod_ranks, ix.hist, chunk_off, n_chunks, ix.pod_bin,
+                                                                                ix.pod_loc, ix.sel_s, ix.rec_s);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-        const uint32_t n_groups = (P + 7) / 8;
-        if (rows) {
+        {
+            const uint32_t n_groups = (P + 7) / 8;
             const uint32_t GS = (n_groups + RW_STRATA - 1) / RW_STRATA;
             const uint64_t F = (uint64_t)RW_STRATA * GS * ix.lay_r.ncb;
             const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + 31) / 32);
-            auto kern = rows_hint_mode() ? (rows_count_mode() ? k_mask_rows<W, W <= 4, 1, true> : k_mask_rows<W, W <= 4, 0, true>)
-                                         : (rows_count_mode() ? k_mask_rows<W, W <= 4, 1, false> : k_mask_rows<W, W <= 4, 0, false>);
+            auto kern = rows_hint_mode() ? k_mask_rows<W, W <= 4, true> : k_mask_rows<W, W <= 4, false>;
             RowsParams prm;
             prm.blob = ix.blobR;
             prm.lay = ix.lay_r;
@@ -1578,12 +1456,6 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
             prm.row_words = (uint32_t)L.ov.mask_row_words;
             prm.cnt = L.ov.cnt;
             kern<<<grid, BP_THREADS, ix.lay_r.smem_bytes, L.stream>>>(prm);
-        } else {
-            uint32_t ctas_per_cb = std::max<uint32_t>(1u, (uint32_t)sms / ix.lay.ncb);
-            ctas_per_cb = std::min<uint32_t>(ctas_per_cb, (n_groups + 31) / 32); // no CTA without a group
-            const uint32_t grid = ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb * ix.lay.ncb : (uint32_t)sms;
-            k_mask_bitpar<W, true><<<grid, BP_THREADS, ix.lay.blob_bytes, L.stream>>>(
-                ix.blob, ix.lay, P, ix.rk_s, ix.pid_s, ix.sel_s, L.ov, ix.lay.ncb <= (uint32_t)sms ? ctas_per_cb : 1u);
         }
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

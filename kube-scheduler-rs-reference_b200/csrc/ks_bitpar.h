@@ -63,27 +63,24 @@ struct BitparIndex {
     int32_t* ord_idx = nullptr;
     int64_t* splC = nullptr;     // every `spl_stride`-th element of sortedC / sortedM (<= 1024 splitters)
     int64_t* splM = nullptr;
-    uint8_t* blob = nullptr;     // ncb blobs of lay.blob_bytes: node-index order, staged in shared memory
     uint8_t* blobP = nullptr;    // one blob of layP.blob_bytes: priority order (tile k = priority ranks 256k..),
                                  // read through L1/L2 by k_first_fit_bp
     uint2* pod_ranks = nullptr;  // per-call scratch [P]
     uint32_t* tail_list = nullptr; // per-call scratch [cap_pods + 1]: pods left for k_first_fit_tail, then the count
     uint32_t* pod_bin = nullptr;   // per-call scratch: threshold bucket of each pod, slot inside the bucket
     uint32_t* pod_loc = nullptr;
-    uint2* rk_s = nullptr;         // pods in bucket order: thresholds, original pod index, selector words
-    uint32_t* pid_s = nullptr;
     unsigned long long* sel_s = nullptr;
     int64_t* ordL_s0 = nullptr;    // KS_SCORE_LEAST_ALLOCATED: score bound of every node in descending order (ties by index)
     int32_t* ordL_idx = nullptr;
     struct NodeEval* evalL = nullptr; // per slot of that order: what the exact score needs
     uint8_t* blobL = nullptr;      // flat index (layP) in that order
+    unsigned long long* live = nullptr; // [KS_MAX_LABEL_WORDS] label bits carried by at least one node
     uint4* rec_s = nullptr;        // rows kernel: {threshold_cpu, threshold_mem, pod index, selector columns} per sorted pod
     uint8_t* blobR = nullptr;      // rows kernel: lay_r.ncb column-block blobs
     uint16_t* rank = nullptr;      // rows kernel: [cb][threshold g][resource][tile] = nodes of the tile at sorted positions < g
     uint32_t* tile_sorted = nullptr; // build scratch: per tile, its nodes' global positions in ascending order
     size_t cap_blobR = 0, cap_rank = 0, cap_tsorted = 0;
     RowsLayout lay_r{};
-    bool rows_valid = false;
     uint64_t epoch = 0;            // bumped whenever a device buffer of the index is reallocated (CUDA-graph cache key)
     uint32_t* hist = nullptr;      // [65536] bucket histogram -> exclusive scan
     uint32_t* rk_hist = nullptr;   // node sample sort scratch: [3][256] bucket counts, splitters, per-node bucket / slot, lists
@@ -92,16 +89,16 @@ struct BitparIndex {
     uint8_t* rk_bkt = nullptr;
     uint32_t* rk_loc = nullptr;
     uint32_t* rk_perm = nullptr;
-    size_t cap_nodes = 0, cap_blob = 0, cap_blobP = 0, cap_pods = 0, cap_sel = 0;
+    size_t cap_nodes = 0, cap_blobP = 0, cap_pods = 0, cap_sel = 0, cap_bins = 0;
     uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
     BitparLayout lay{}, layP{};
     bool valid = false;
     int sms = 0;
-    cudaStream_t aux = nullptr; // k_first_fit_bp runs here, overlapped with k_mask_bitpar
+    cudaStream_t aux = nullptr; // the argmax kernels run here, overlapped with k_mask_rows
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
-cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, const int64_t* prio, cudaStream_t st);
+cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cudaStream_t st);
 bool bitpar_profitable(const BitparIndex& ix, uint32_t P);
 cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P);
 cudaError_t bitpar_select(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask);

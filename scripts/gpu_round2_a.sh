@@ -8,7 +8,7 @@ B="python bench.py --no-cpu-baseline --no-secondary --no-objects"
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_streaming.py tests/test_abi.py tests/test_host_layer.py -m gpu -q --maxfail=8 \
     --deselect tests/test_gpu_parity.py::test_config_c3_full_size_bit_exact > gpurun_out/a_pytest.log 2>&1
 echo "pytest rc=$? $(tail -1 gpurun_out/a_pytest.log)"
-# 2. A/B: round-1 kernel (quads) vs rows, POPC vs carry-save count, L2 hints
+# 2. A/B as run in session A (the quads kernel and the carry-save count were deleted afterwards; kept for the record)
 for rep in 1 2; do
   for w in c3 c2; do
     for k in quads rows rows_csa rows_hint; do

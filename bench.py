@@ -471,6 +471,14 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
             assert g_idx[r, :n_r].min() >= -1 and g_idx[r, :n_r].max() < N
     barrier()
 
+    # store-only ceiling of this device, measured on the mask buffer itself (a plain 256-bit-store fill): the copy-based
+    # HBM peak counts read + write bytes, a kernel that only writes cannot reach it
+    write_peak = None
+    if emit_mask and d_mask is not None and d_mask.numel() >= (1 << 20):
+        try:
+            write_peak = ks.capi.measure_write_bandwidth(local, d_mask.data_ptr(), d_mask.numel() // 32 * 32, 4)
+        except Exception:
+            write_peak = None
     ab = algorithmic_bytes(P, N, W, cl.B, emit_mask)
     peak, peak_src = hbm_peak()
     k_ms = sum(kern_ms) / len(kern_ms)
@@ -489,7 +497,9 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
                 "kernel_ms": k_ms, "kernel_ms_spread": spread(kern_ms),
                 "rest_of_step_ms": sum(scan_ms) / len(scan_ms), "algorithmic_bytes": ab["dominant_kernel"],
                 "step_algorithmic_bytes": ab["step_total"], "step_frac": ab["step_total"] / (ms_per_step * 1e-3) / 1e9 / peak,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "write_peak": write_peak,
+                "frac_of_write_peak": (achieved / write_peak) if write_peak else None,
+                "write_peak_source": "ks_measure_write_bandwidth: store-only fill of the mask buffer in this run (GB/s)",
                 "ncu": {k: v for k, v in cap_info.items() if k != "dram_bytes"} or None}
     res = {
         "workload": workload, "P": P, "N": N, "W": W, "B": cl.B, "seed": seed, "path": path, "value": value,

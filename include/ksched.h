@@ -137,6 +137,10 @@ int ks_ipc_alloc(int device, uint64_t bytes, void** out_ptr, uint8_t out_handle[
 int ks_ipc_open(int device, const uint8_t handle[64], void** out_ptr);
 int ks_ipc_close(int device, void* ptr);
 int ks_ipc_free(int device, void* ptr);
+/* store-only bandwidth of the device: best of `iters` passes of a plain coalesced 256-bit-store fill over dev_buf
+ * (bytes >= 1 MiB, 32-byte aligned; its contents are overwritten).  MEASURED_PEAKS-style HBM peaks are copies
+ * (read + write bytes); a kernel that only writes - the feasible-mask pass - is bounded by this figure instead. */
+int ks_measure_write_bandwidth(int device, void* dev_buf, uint64_t bytes, int iters, double* out_gbs);
 /* synchronising device-to-host copy of `bytes` bytes (reading a gather buffer allocated with ks_ipc_alloc) */
 int ks_device_read(int device, const void* dev_ptr, void* host_ptr, uint64_t bytes);
 

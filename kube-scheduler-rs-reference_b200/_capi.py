@@ -89,6 +89,7 @@ _proto("ks_ipc_alloc", C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.c_
 _proto("ks_ipc_open", C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p))
 _proto("ks_ipc_close", C.c_int, C.c_int, C.c_void_p)
 _proto("ks_ipc_free", C.c_int, C.c_int, C.c_void_p)
+_proto("ks_measure_write_bandwidth", C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double))
 _proto("ks_device_read", C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
 _proto("ks_select_sampling", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p,
        C.c_void_p, C.c_void_p, C.c_void_p)
@@ -111,6 +112,15 @@ def declared_symbols():
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names += re.findall(r"\b(ksh?_[a-z0-9_]+)\s*\(", text)
     return sorted(set(names))
+
+
+def measure_write_bandwidth(device, dev_ptr, nbytes, iters=4):
+    """GB/s of a store-only fill over a device buffer (its contents are overwritten)."""
+    out = C.c_double()
+    rc = lib.ks_measure_write_bandwidth(int(device), C.c_void_p(int(dev_ptr)), int(nbytes), int(iters), C.byref(out))
+    if rc != KS_OK:
+        raise KsError(rc, "ks_measure_write_bandwidth")
+    return float(out.value)
 
 
 def mask_row_bytes(n_nodes):

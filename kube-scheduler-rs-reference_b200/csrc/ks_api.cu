@@ -754,6 +754,30 @@ int ks_ipc_close(int device, void* ptr) {
     return KS_OK;
 }
 
+int ks_measure_write_bandwidth(int device, void* dev_buf, uint64_t bytes, int iters, double* out_gbs) {
+    if (!dev_buf || !out_gbs || bytes < (1u << 20) || ((uintptr_t)dev_buf & 31u)) return fail(KS_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int it = 0; it < std::max(2, iters); it++) { // first pass untimed
+        CU_TRY(cudaEventRecord(e0, nullptr));
+        CU_TRY(launch_fill256(dev_buf, bytes, 0x5a5a0000u + (uint32_t)it, sms, nullptr));
+        CU_TRY(cudaEventRecord(e1, nullptr));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (it > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *out_gbs = (double)(bytes / 32 * 32) / (best * 1e-3) / 1e9;
+    return KS_OK;
+}
+
 int ks_device_read(int device, const void* dev_ptr, void* host_ptr, uint64_t bytes) {
     if (!dev_ptr || !host_ptr) return fail(KS_ERR_INVALID, "NULL argument");
     CU_TRY(cudaSetDevice(device));

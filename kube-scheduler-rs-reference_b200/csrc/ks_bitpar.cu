@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) k_node_bound(NodeTable nt, int64_t* __res
 }
 
 constexpr int RANK_SAMPLES = 1024, RANK_BUCKETS = 256;
+constexpr int RANK_SPLITTERS = 2048; // per resource, in k_pod_ranks' shared memory (32 KB)
 constexpr int N_ORDERS = 4; // free_cpu, free_mem, leftover priority, least-allocated bound
 
 __global__ void __launch_bounds__(RANK_SAMPLES)
@@ -445,7 +446,7 @@ __device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x
 }
 
 // rank = number of nodes with free < request; nodes at sorted positions >= rank satisfy request <= free
-// (predicates.rs:42).  Two-level search: <=1024 splitters per resource in shared memory, then a window of
+// (predicates.rs:42).  Two-level search: <=2048 splitters per resource in shared memory, then a window of
 // spl_stride-1 elements of the global sorted array.  The pod is also dropped into bucket
 // (rank_cpu >> sh_c, rank_mem >> sh_m) of a <=64k-bin histogram: the counting sort that follows places pods with
 // equal or neighbouring thresholds next to each other, which is what lets the mask kernel share table rows.
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(256)
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
                 uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, BucketParams bk, uint32_t* __restrict__ hist,
                 uint32_t* __restrict__ pod_bin, uint32_t* __restrict__ pod_loc) {
-    __shared__ int64_t s_spl[2][1024];
+    __shared__ int64_t s_spl[2][RANK_SPLITTERS];
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
         s_spl[1][k] = splM[k];
@@ -1203,8 +1204,8 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cu
         if ((e = regrow(ix.gposM, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.ord_prio, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.ord_idx, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.splC, 1024)) != cudaSuccess) return e;
-        if ((e = regrow(ix.splM, 1024)) != cudaSuccess) return e;
+        if ((e = regrow(ix.splC, RANK_SPLITTERS)) != cudaSuccess) return e;
+        if ((e = regrow(ix.splM, RANK_SPLITTERS)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_bkt, N_ORDERS * cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_loc, N_ORDERS * cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rk_perm, N_ORDERS * cap)) != cudaSuccess) return e;
@@ -1214,7 +1215,7 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cu
         ix.cap_nodes = cap;
     }
     uint32_t stride = 1;
-    while ((nt.N + stride - 1) / stride > 1024) stride <<= 1;
+    while ((nt.N + stride - 1) / stride > (uint32_t)RANK_SPLITTERS) stride <<= 1;
     ix.spl_stride = stride;
     ix.n_spl = (nt.N + stride - 1) / stride;
     if (!ix.rk_hist) {
@@ -1369,7 +1370,7 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     }
     if (need_mask_pass)
         if ((e = cudaMemsetAsync(ix.hist, 0, (size_t)bk.n_bins * 4, L.stream)) != cudaSuccess) return e;
-    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 4, ((uint64_t)P + 255) / 256);
+    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256); // 6 CTAs x 32 KB of splitters per SM
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl,
                                                  ix.spl_stride, ix.pod_ranks,
                                                  (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, bk,

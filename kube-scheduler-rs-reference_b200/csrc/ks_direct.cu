@@ -119,6 +119,20 @@ cudaError_t launch_exchange_wait(const PeerOut& po, int* error_flag, cudaStream_
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ store ceiling
+// What a kernel that ONLY writes can reach on this device (ks_measure_write_bandwidth): coalesced 256-bit stores,
+// grid-stride, nothing else.  The mask kernel is compared with this next to the copy-based HBM peak.
+__global__ void __launch_bounds__(256) k_fill256(uint8_t* __restrict__ dst, uint64_t n32, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (uint64_t)gridDim.x * blockDim.x)
+        asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(dst + i * 32), "r"(v) : "memory");
+}
+
+cudaError_t launch_fill256(void* dst, uint64_t bytes, uint32_t v, int sms, cudaStream_t st) {
+    k_fill256<<<sms * 8, 256, 0, st>>>(static_cast<uint8_t*>(dst), bytes / 32, v);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 __device__ __forceinline__ int cell_code(int64_t rc, int64_t rm, const uint64_t* __restrict__ sel, int64_t fc,
                                          int64_t fm, const uint64_t* __restrict__ labels, uint32_t n,

@@ -16,6 +16,7 @@ cudaError_t launch_select_sampling(const NodeTable& nt, const PodView& pv, uint3
 // multi-GPU exchange helpers (ks_direct.cu): push finished bindings to the peers (per-cell path), wait for all ranks
 cudaError_t launch_exchange_push(const PeerOut& po, const int32_t* node_idx, const int64_t* score, uint32_t P, cudaStream_t st);
 cudaError_t launch_exchange_wait(const PeerOut& po, int* error_flag, cudaStream_t st);
+cudaError_t launch_fill256(void* dst, uint64_t bytes, uint32_t v, int sms, cudaStream_t st);
 uint32_t direct_pods_per_cta(uint32_t W);
 cudaError_t prepare_select_direct(uint32_t W);
 cudaError_t launch_select_direct(const SelectLaunch& L, const PartialView& part, uint32_t n_chunks,

@@ -59,6 +59,40 @@ __global__ void k_rows_pattern(uint8_t* __restrict__ dst, uint32_t n_rows, uint3
     }
 }
 
+// generalised row pattern: `chunk` contiguous bytes per (row, column block) written by chunk/32 lanes.
+//   mode 0: column-block-major (a CTA stays in one column block and walks the rows: the mask kernel's order)
+//   mode 1: row-major "lockstep": CTA i owns column block i % n_cb and every (gridDim/n_cb)-th row group; all CTAs walk the
+//           rows in the same order, so the pieces of one row are written at about the same time by n_cb different CTAs
+//   scramble: rows visited in a pseudo-random order (sorted pods) or in index order
+__global__ void k_rows_general(uint8_t* __restrict__ dst, uint32_t n_rows, uint32_t row_bytes, uint32_t chunk, int mode, int scramble,
+                               uint32_t v) {
+    const uint32_t lpc = chunk / 32;              // lanes per chunk
+    const uint32_t cpw = 32 / lpc;                // chunks (rows) per warp instruction
+    const uint32_t l = threadIdx.x & 31, sub = l / lpc, lane = l % lpc, warp = threadIdx.x >> 5, wpc = blockDim.x / 32;
+    const uint32_t n_cb = row_bytes / chunk, n_groups = n_rows / cpw;
+    if (mode == 0) {
+        const uint64_t total = (uint64_t)n_cb * n_groups, per = (total + gridDim.x - 1) / gridDim.x;
+        const uint64_t f0 = per * blockIdx.x, f1 = f0 + per < total ? f0 + per : total;
+        for (uint64_t f = f0 + warp; f < f1; f += wpc) {
+            const uint32_t cb = (uint32_t)(f / n_groups), g = (uint32_t)(f % n_groups);
+            uint32_t row = g * cpw + sub;
+            if (scramble) row = (uint32_t)(((uint64_t)row * 2654435761ull) % n_rows);
+            asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(dst + (size_t)row * row_bytes + (size_t)cb * chunk + lane * 32), "r"(v)
+                         : "memory");
+        }
+    } else {
+        const uint32_t per_cb = gridDim.x / n_cb; // CTAs per column block; the rest of the grid idles
+        if (blockIdx.x >= per_cb * n_cb) return;
+        const uint32_t cb = blockIdx.x % n_cb, j = blockIdx.x / n_cb;
+        for (uint32_t g = j * wpc + warp; g < n_groups; g += per_cb * wpc) {
+            uint32_t row = g * cpw + sub;
+            if (scramble) row = (uint32_t)(((uint64_t)row * 2654435761ull) % n_rows);
+            asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(dst + (size_t)row * row_bytes + (size_t)cb * chunk + lane * 32), "r"(v)
+                         : "memory");
+        }
+    }
+}
+
 // TMA bulk stores: shared -> global through the copy engine of the SM instead of the LSU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 template <int CHUNK>
@@ -132,6 +166,18 @@ int main(int argc, char** argv) {
     timeit("st256_evict_first", (double)bytes, [&] { k_st256<1><<<sms * 8, 256>>>(a, n32, 7); });
     timeit("st256_persistent_1024thr", (double)bytes, [&] { k_st256<0><<<sms, 1024>>>(a, n32, 7); });
     timeit("rows_pattern_256B_chunks", (double)bytes, [&] { k_rows_pattern<<<sms, 1024>>>(a, n_rows, row_bytes, 7); });
+    {
+        const uint32_t rb = 6144; // row pitch divisible by every chunk size below
+        const uint32_t nr = (uint32_t)(bytes / rb) / 32 * 32;
+        static char names[32][64];
+        int ni = 0;
+        for (uint32_t chunk : {128u, 256u, 512u, 1024u, 2048u})
+            for (int mode = 0; mode < 2; mode++)
+                for (int scr = 0; scr < 2; scr++) {
+                    snprintf(names[ni], 64, "rows_chunk%u_%s_%s", chunk, mode ? "rowmajor_lockstep" : "cbmajor", scr ? "scrambled" : "inorder");
+                    timeit(names[ni++], (double)nr * rb, [&] { k_rows_general<<<sms, 1024>>>(a, nr, rb, chunk, mode, scr, 7); });
+                }
+    }
     CK(cudaFuncSetAttribute(k_tma_store<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     timeit("tma_bulk_store_32KB", (double)(bytes / 32768 * 32768), [&] { k_tma_store<32768><<<sms * 2, 256, 32768>>>(a, bytes, 7); });
     timeit("tma_bulk_store_2KB", (double)(bytes / 2048 * 2048), [&] { k_tma_store<2048><<<sms * 8, 256, 2048>>>(a, bytes, 7); });

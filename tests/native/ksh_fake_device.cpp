@@ -149,5 +149,6 @@ int ks_ipc_alloc(int, uint64_t, void**, uint8_t*) { return fail(KS_ERR_NO_DEVICE
 int ks_ipc_open(int, const uint8_t*, void**) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
 int ks_ipc_close(int, void*) { return KS_OK; }
 int ks_ipc_free(int, void*) { return KS_OK; }
+int ks_measure_write_bandwidth(int, void*, uint64_t, int, double*) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
 int ks_device_read(int, const void*, void*, uint64_t) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
 }

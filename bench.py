@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--policy", default="leftover", choices=["leftover", "least_allocated"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how the bindings are all-gathered")
     ap.add_argument("--no-mask", action="store_true", help="do not emit the feasible mask (bindings only)")
+    ap.add_argument("--mask-pitch", default="aligned", choices=["aligned", "minimal"],
+                    help="row pitch of the mask buffer: ks_mask_row_bytes_aligned (256-byte blocks) or the smallest legal one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the secondary c2 object")
     ap.add_argument("--no-objects", action="store_true", help="N=1: skip the object-level end-to-end figure")
@@ -289,7 +291,7 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
     P = cl.P
 
     stream = torch.cuda.Stream()
-    row = ks.mask_row_bytes(N)
+    row = ks.mask_row_bytes_aligned(N) if args.mask_pitch == "aligned" else ks.mask_row_bytes(N)
     d_rc = torch.from_numpy(rc).to(dev)
     d_rm = torch.from_numpy(rm).to(dev)
     d_sel = torch.from_numpy(np.ascontiguousarray(sel).view(np.int64)).to(dev)
@@ -506,7 +508,7 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
         "ms_per_step": ms_per_step, "step_ms": spread(step_ms), "e2e_value": e2e_value, "e2e_ms": spread([1e3 * t for t in e2e_t]),
         "launches": int(launches), "roofline": roofline, "t_wall": t_wall, "call_ms": sum(call_ms) / len(call_ms),
         "total_pods": total_pods, "strong": strong, "exchange": exchange_note, "emit_mask": emit_mask,
-        "h2d": P * (16 + 8 * W), "d2h": P * 16,
+        "h2d": P * (16 + 8 * W), "d2h": P * 16, "row": row,
     }
     if world == 1:
         # for information: the reference's own policy (<=5 seeded draws per pod, src/main.rs:49-71) on the same batch,
@@ -582,6 +584,7 @@ def main():
             "workload": f"{wl_text}, resource_fits + nodeSelector + argmax score ({args.policy}), "
                         f"mask {'emitted' if r['emit_mask'] else 'not emitted'}",
             "label_words": W, "bound_pods": r["B"], "seed": hex(r["seed"]), "path": r["path"],
+            "mask_row_pitch_bytes": r["row"], "mask_row_min_bytes": ks.mask_row_bytes(N),
             "kernel_switches": {k: os.environ[k] for k in ("KS_ROWS_HINT", "KS_ROWS_SORT") if k in os.environ} or None,
             "parallelism": f"pods sharded x{world}, node table replicated" + (f"; bindings exchange: {r['exchange']}" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": r["t_wall"],

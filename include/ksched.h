@@ -98,7 +98,7 @@ typedef struct ks_bindings { /* outputs; any pointer may be NULL to skip that ou
     uint32_t* feasible_cnt;  /* [n] number of feasible nodes */
     int32_t mem_space;       /* space of the three arrays above */
     uint8_t* mask;           /* [n rows] feasible bit-mask, bit (n%8) of byte n/8 of the row */
-    uint64_t mask_row_bytes; /* row pitch; multiple of 32, >= ks_mask_row_bytes(N) */
+    uint64_t mask_row_bytes; /* row pitch; multiple of 32, >= ks_mask_row_bytes(N); ks_mask_row_bytes_aligned(N) is fastest */
     int32_t mask_space;      /* space of mask (may differ: keep a 6 GB mask in HBM, bindings on host) */
     void* bindings_ready_event; /* optional cudaEvent_t (NULL = none), device-space outputs only: recorded as soon as
                                    node_idx and score are final - on the bit-parallel path that is well before the
@@ -110,7 +110,13 @@ const char* ks_last_error(void);
 int ks_version(void);
 int ks_device_count(void);           /* number of CUDA devices visible; 0 when none */
 uint64_t ks_launch_count(void);      /* kernels launched by this library since load */
-uint64_t ks_mask_row_bytes(uint32_t n_nodes); /* 32 * ceil(n_nodes/256) */
+uint64_t ks_mask_row_bytes(uint32_t n_nodes); /* 32 * ceil(n_nodes/256): the smallest legal row pitch */
+/* 256 * ceil(n_nodes/2048): the recommended pitch for a device-space mask.  The mask kernel writes one 256-byte block
+ * per (pod, 2048-node column block); with this pitch (and a 256-byte-aligned base) every block is whole and aligned,
+ * which the memory system of a B200 rewards with ~1.35x the store bandwidth of straddling blocks.  Bytes of a row
+ * beyond ks_mask_row_bytes(n_nodes) carry no information: up to the aligned size the bit-parallel path writes them
+ * as zeros (whole 32-byte tiles that fit the pitch), the per-cell path leaves them untouched. */
+uint64_t ks_mask_row_bytes_aligned(uint32_t n_nodes);
 
 /* ---- snapshot: device-resident node table (replaces node_store.state(), src/main.rs:56) ---- */
 int ks_snapshot_create(int device, ks_snapshot** out);

@@ -61,6 +61,7 @@ _proto("ks_version", C.c_int)
 _proto("ks_device_count", C.c_int)
 _proto("ks_launch_count", C.c_uint64)
 _proto("ks_mask_row_bytes", C.c_uint64, C.c_uint32)
+_proto("ks_mask_row_bytes_aligned", C.c_uint64, C.c_uint32)
 _proto("ks_snapshot_create", C.c_int, C.c_int, C.POINTER(C.c_void_p))
 _proto("ks_snapshot_destroy", None, C.c_void_p)
 _proto("ks_snapshot_set_nodes", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p)
@@ -125,6 +126,10 @@ def measure_write_bandwidth(device, dev_ptr, nbytes, iters=4):
 
 def mask_row_bytes(n_nodes):
     return int(lib.ks_mask_row_bytes(int(n_nodes)))
+
+
+def mask_row_bytes_aligned(n_nodes):
+    return int(lib.ks_mask_row_bytes_aligned(int(n_nodes)))
 
 
 def device_count():

@@ -136,6 +136,7 @@ int ks_device_count(void) {
 }
 uint64_t ks_launch_count(void) { return g_launches.load(); }
 uint64_t ks_mask_row_bytes(uint32_t n_nodes) { return 32ull * ((n_nodes + 255ull) / 256ull); }
+uint64_t ks_mask_row_bytes_aligned(uint32_t n_nodes) { return 256ull * ((n_nodes + 2047ull) / 2048ull); }
 
 int ks_snapshot_create(int device, ks_snapshot** out) {
     if (!out) return fail(KS_ERR_INVALID, "out is NULL");

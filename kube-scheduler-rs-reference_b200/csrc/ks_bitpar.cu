@@ -780,7 +780,12 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         asm volatile("mov.u32 %0, 0;" : "=r"(tok)::"memory");
         const uint32_t a_tab = smem_u32(smem) + t * 16u + tok;
         const uint32_t tile = cb * RW_TILES + t;
-        uint32_t* mask_col = (prm.mask != nullptr && tile < prm.lay.n_tiles) ? opaque_ptr(prm.mask + (size_t)tile * 8u) : nullptr;
+        // a tile is written when it holds nodes, or when the caller's row pitch has room for it (a pitch that is a multiple
+        // of 256 bytes - ks_mask_row_bytes_aligned - lets the 8 lanes of a pod always store one whole, 256-byte-aligned
+        // block: partial blocks cost a third of the store bandwidth, profiles/r02_write_bw_v2.txt); padding tiles hold zeros
+        uint32_t* mask_col = (prm.mask != nullptr && (tile < prm.lay.n_tiles || (tile + 1u) * 8u <= prm.row_words))
+                                 ? opaque_ptr(prm.mask + (size_t)tile * 8u)
+                                 : nullptr;
 
         for (; j < j1; j += 32) { // warp-uniform
             const uint4 rA = nA, rB = nB;

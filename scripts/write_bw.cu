@@ -156,6 +156,7 @@ int main(int argc, char** argv) {
             if (it > 0) best = std::min(best, ms);
         }
         res.push_back({name, moved_bytes / (best * 1e-3) / 1e9});
+        fprintf(stderr, "%s %.1f GB/s\n", name, res.back().second);
     };
     const size_t n16 = bytes / 16, n32 = bytes / 32;
     timeit("cudaMemset", (double)bytes, [&] { CK(cudaMemsetAsync(a, 0x5a, bytes)); });
@@ -171,7 +172,7 @@ int main(int argc, char** argv) {
         const uint32_t nr = (uint32_t)(bytes / rb) / 32 * 32;
         static char names[32][64];
         int ni = 0;
-        for (uint32_t chunk : {128u, 256u, 512u, 1024u, 2048u})
+        for (uint32_t chunk : {128u, 256u, 512u, 1024u}) // chunk / 32 lanes <= one warp
             for (int mode = 0; mode < 2; mode++)
                 for (int scr = 0; scr < 2; scr++) {
                     snprintf(names[ni], 64, "rows_chunk%u_%s_%s", chunk, mode ? "rowmajor_lockstep" : "cbmajor", scr ? "scrambled" : "inorder");

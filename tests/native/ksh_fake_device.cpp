@@ -144,6 +144,7 @@ int ks_stream_poll(ks_stream*, uint64_t, uint64_t*, int32_t*, int64_t*, uint64_t
 int ks_stream_flush(ks_stream*) { return KS_ERR_NO_DEVICE; }
 int ks_stream_stats(ks_stream*, uint64_t*, uint64_t*, uint64_t*) { return KS_ERR_NO_DEVICE; }
 void ks_stream_close(ks_stream*) {}
+uint64_t ks_mask_row_bytes_aligned(uint32_t n) { return 256ull * ((n + 2047ull) / 2048ull); }
 int ks_exchange_check(ks_snapshot*) { return KS_OK; }
 int ks_ipc_alloc(int, uint64_t, void**, uint8_t*) { return fail(KS_ERR_NO_DEVICE, "fake device"); }
 int ks_ipc_open(int, const uint8_t*, void**) { return fail(KS_ERR_NO_DEVICE, "fake device"); }

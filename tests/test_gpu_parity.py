@@ -188,24 +188,28 @@ def test_incremental_bind_equals_rebuild(ks, orc):
             assert np.array_equal(ra.node_idx, rb.node_idx) and np.array_equal(ra.mask, rb.mask)
 
 
-def test_device_buffers_and_user_stream(ks, orc):
-    """KS_MEM_DEVICE arguments (torch tensors only provide the memory and the stream)."""
+@pytest.mark.parametrize("pitch", ["minimal", "aligned", "odd"])
+def test_device_buffers_and_user_stream(ks, orc, pitch):
+    """KS_MEM_DEVICE arguments (torch tensors only provide the memory and the stream), with the smallest legal mask row
+    pitch, the recommended 256-byte-block pitch (ks_mask_row_bytes_aligned) and a pitch in between."""
     import torch
-    cl = ks.synth.make(5000, 4000, seed=9)
+    cl = ks.synth.make(5000, 4500, seed=9)  # 18 tiles: 576-byte rows, 768 aligned
     snap, (rc, rm, sel) = _snapshot(ks, cl)
     o = _oracle(orc, cl, 0)
     dev = torch.device("cuda:0")
     t = [torch.from_numpy(np.ascontiguousarray(x.view(np.int64))).to(dev) for x in (rc, rm, sel)]
-    row = ks.mask_row_bytes(cl.N)
+    row_min = ks.mask_row_bytes(cl.N)
+    row = {"minimal": row_min, "aligned": ks.mask_row_bytes_aligned(cl.N), "odd": row_min + 64}[pitch]
+    assert row % 32 == 0 and row >= row_min and ks.mask_row_bytes_aligned(cl.N) % 256 == 0
     idx = torch.empty(cl.P, dtype=torch.int32, device=dev)
     score = torch.empty(cl.P, dtype=torch.int64, device=dev)
     cnt = torch.empty(cl.P, dtype=torch.int32, device=dev)
     mask = torch.zeros((cl.P, row), dtype=torch.uint8, device=dev)
     st = torch.cuda.Stream()
     with snap:
-        for flag in PATHS.values():
+        for name, flag in PATHS.items():
             idx.fill_(-7)
-            mask.zero_()
+            mask.fill_(0xA5 if name == "bitpar" else 0)  # the bit-parallel path overwrites every whole tile of the pitch
             torch.cuda.synchronize()
             snap.select_raw(cl.P, t[0], t[1], t[2], ks.KS_MEM_DEVICE, idx, score, cnt, ks.KS_MEM_DEVICE, mask=mask,
                             mask_row_bytes=row, mask_space=ks.KS_MEM_DEVICE, flags=flag, stream=st.cuda_stream)
@@ -213,7 +217,9 @@ def test_device_buffers_and_user_stream(ks, orc):
             assert np.array_equal(idx.cpu().numpy(), o[0])
             assert np.array_equal(score.cpu().numpy(), o[1])
             assert np.array_equal(cnt.cpu().numpy().view(np.uint32), o[2])
-            assert np.array_equal(mask.cpu().numpy(), o[3])
+            m = mask.cpu().numpy()
+            assert np.array_equal(m[:, :row_min], o[3])
+            assert (m[:, row_min:] == 0).all()
 
 
 def test_bad_arguments_are_status_codes(ks):
@@ -261,7 +267,7 @@ def test_config_c3_full_size_bit_exact(ks, orc):
     fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
     P, N = cl.P, cl.N
     dev = torch.device("cuda:0")
-    row = ks.mask_row_bytes(N)
+    row_min, row = ks.mask_row_bytes(N), ks.mask_row_bytes_aligned(N)  # 6272 and 6400: the pitch bench.py uses
     t = [torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).to(dev) for x in (rc, rm, sel)]
     idx = torch.empty(P, dtype=torch.int32, device=dev)
     score = torch.empty(P, dtype=torch.int64, device=dev)
@@ -296,7 +302,9 @@ def test_config_c3_full_size_bit_exact(ks, orc):
         o = orc.run_packed(fc, fm, ac, am, lab, rc[lo:hi], rm[lo:hi], sel[lo:hi], want_mask=True, nthreads=0)
         assert np.array_equal(g_idx[lo:hi], o[0]) and np.array_equal(g_score[lo:hi], o[1]), f"bindings, slab {k}"
         assert np.array_equal(g_cnt[lo:hi], o[2]), f"feasible_cnt, slab {k}"
-        assert np.array_equal(mask[lo:hi].cpu().numpy(), o[3]), f"mask, slab {k}"
+        m = mask[lo:hi].cpu().numpy()
+        assert np.array_equal(m[:, :row_min], o[3]), f"mask, slab {k}"
+        assert (m[:, row_min:] == 0).all(), f"mask padding, slab {k}"
         done += 1
         if t_first is None:
             t_first = time.perf_counter() - t0

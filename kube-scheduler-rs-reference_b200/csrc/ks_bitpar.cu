@@ -450,23 +450,48 @@ __device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x
 // spl_stride-1 elements of the global sorted array.  The pod is also dropped into bucket
 // (rank_cpu >> sh_c, rank_mem >> sh_m) of a <=64k-bin histogram: the counting sort that follows places pods with
 // equal or neighbouring thresholds next to each other, which is what lets the mask kernel share table rows.
+constexpr uint32_t RW_SEL_GENERIC = 0xFFFFFFFFu;
+constexpr uint32_t RW_PID_NONE = 0xFFFFFFFFu;
+
+// the selector of a pod as record word: up to three required label-pair bit indices (10 bits each) + their number in
+// bits 30-31; RW_SEL_GENERIC when it names more than three pairs (the mask kernel then walks the selector words)
+template <class LoadWord>
+__device__ __forceinline__ uint32_t selector_record(uint32_t W, LoadWord word) {
+    uint32_t cols = 0, n_req = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        unsigned long long bits = word(w);
+        while (bits) { // required (key,value) pairs of the selector (predicates.rs:48)
+            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (n_req < 3) cols |= bit << (10 * n_req);
+            n_req++;
+        }
+    }
+    return n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30));
+}
+
 struct BucketParams {
     uint32_t sh_c, sh_m, nb_m, n_bins; // n_bins = 4 selector classes x threshold grid
     uint32_t grid_bins, W;
     uint32_t exact; // 1: bin = (selector class, exact cpu threshold): consecutive sorted pods share their cpu table rows
+                    // 2: no sort at all - the mask kernel takes the pods in index order (records written here)
 };
 
 __global__ void __launch_bounds__(256)
     k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM, uint32_t N,
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
                 uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, BucketParams bk, uint32_t* __restrict__ hist,
-                uint32_t* __restrict__ pod_bin, uint32_t* __restrict__ pod_loc) {
+                uint32_t* __restrict__ pod_bin, uint32_t* __restrict__ pod_loc, uint4* __restrict__ rec,
+                unsigned long long* __restrict__ sel_copy) {
     __shared__ int64_t s_spl[2][RANK_SPLITTERS];
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
         s_spl[1][k] = splM[k];
     }
     __syncthreads();
+    if (rec) // padding of the last group of 8
+        for (uint32_t p = pv.P + blockIdx.x * blockDim.x + threadIdx.x; p < ((pv.P + 7u) & ~7u); p += gridDim.x * blockDim.x)
+            rec[p] = make_uint4(0, 0, RW_PID_NONE, 0);
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pv.P; p += gridDim.x * blockDim.x) {
         uint32_t out[2];
 #pragma unroll
@@ -484,7 +509,13 @@ __global__ void __launch_bounds__(256)
         }
         rk[p] = make_uint2(out[0], out[1]);
         if (cnt_zero) cnt_zero[p] = 0; // k_mask_rows accumulates feasible counts with REDs
-        if (hist) {
+        if (rec) { // unsorted mode: the record goes out here, position = pod index
+            rec[p] = make_uint4(out[0], out[1], p, selector_record(bk.W, [&](uint32_t w) {
+                                    const unsigned long long v = __ldg(pv.sel + (size_t)p * bk.W + w);
+                                    sel_copy[(size_t)p * bk.W + w] = v;
+                                    return v;
+                                }));
+        } else if (hist) {
             // most significant key: number of required label pairs (0,1,2,3+), so that the lanes of a warp run the
             // same number of column ANDs in the mask kernel (no divergence in its selector loop)
             uint32_t n_req = 0;
@@ -563,9 +594,6 @@ __global__ void __launch_bounds__(1024)
 // "selector columns" = up to three required label-pair bit indices (10 bits each) + their number in bits 30-31,
 // RW_SEL_GENERIC when the selector names more than three pairs (the kernel then walks sel_s).  The list is padded
 // to a multiple of 8 with inactive records (pod index 0xFFFFFFFF).
-constexpr uint32_t RW_SEL_GENERIC = 0xFFFFFFFFu;
-constexpr uint32_t RW_PID_NONE = 0xFFFFFFFFu;
-
 template <int W>
 __global__ void __launch_bounds__(256)
     k_pod_scatter(PodView pv, const uint2* __restrict__ rk, const uint32_t* __restrict__ start,
@@ -580,19 +608,12 @@ __global__ void __launch_bounds__(256)
     const uint32_t bin = pod_bin[p];
     const uint32_t q = start[bin] + __ldg(chunk_off + (bin >> 10)) + pod_loc[p];
     const uint2 r = rk[p];
-    uint32_t cols = 0, n_req = 0;
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        unsigned long long bits = __ldg(pv.sel + (size_t)p * W + w);
-        sel_s[(size_t)q * W + w] = bits;
-        while (bits) { // required (key,value) pairs of the selector (predicates.rs:48)
-            const uint32_t bit = w * 64 + __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            if (n_req < 3) cols |= bit << (10 * n_req);
-            n_req++;
-        }
-    }
-    rec_s[q] = make_uint4(r.x, r.y, p, n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30)));
+    const uint32_t selrec = selector_record(W, [&](uint32_t w) {
+        const unsigned long long v = __ldg(pv.sel + (size_t)p * W + w);
+        sel_s[(size_t)q * W + w] = v;
+        return v;
+    });
+    rec_s[q] = make_uint4(r.x, r.y, p, selrec);
 }
 
 // ------------------------------------------------------------------------------------------------ rows kernel
@@ -1360,7 +1381,9 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const int sms = ix.sms;
     // bucket grid over (rank_cpu, rank_mem): <= 64k bins, the finest shifts that fit
     BucketParams bk{0, 0, 0, 0, 0, ix.W, 0};
-    if (rows_sort_mode() == 1 && (uint64_t)4 * (ix.N + 1) <= (1ull << 20)) {
+    if (rows_sort_mode() == 2) {
+        bk.exact = 2; // no sort
+    } else if (rows_sort_mode() == 1 && (uint64_t)4 * (ix.N + 1) <= (1ull << 20)) {
         bk.exact = 1; // bin = (selector class, exact cpu threshold)
         bk.grid_bins = ix.N + 1;
         bk.n_bins = 4 * bk.grid_bins;
@@ -1373,13 +1396,15 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         bk.grid_bins = ((ix.N >> bk.sh_c) + 1) * bk.nb_m;
         bk.n_bins = 4 * bk.grid_bins; // <= 65536
     }
-    if (need_mask_pass)
+    const bool sorted_pods = bk.exact != 2;
+    if (need_mask_pass && sorted_pods)
         if ((e = cudaMemsetAsync(ix.hist, 0, (size_t)bk.n_bins * 4, L.stream)) != cudaSuccess) return e;
     const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256); // 6 CTAs x 32 KB of splitters per SM
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl,
                                                  ix.spl_stride, ix.pod_ranks,
                                                  (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, bk,
-                                                 need_mask_pass ? ix.hist : nullptr, ix.pod_bin, ix.pod_loc);
+                                                 (need_mask_pass && sorted_pods) ? ix.hist : nullptr, ix.pod_bin, ix.pod_loc,
+                                                 (need_mask_pass && !sorted_pods) ? ix.rec_s : nullptr, ix.sel_s);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // argmax scan (needs only the pod ranks).  Normally it runs on an auxiliary stream so that it overlaps the mask
@@ -1433,15 +1458,17 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     if (want_bind && overlap_bind)
         if ((e = enqueue_bind()) != cudaSuccess) return e;
     if (need_mask_pass) {
-        const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 1024
-        uint32_t* chunk_off = ix.hist + ix.cap_bins;
-        k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, chunk_off, chunk_off + 1024);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        k_pod_scatter<W><<<(((P + 7u) & ~7u) + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.pod_ranks, ix.hist, chunk_off, n_chunks, ix.pod_bin,
-                                                                                ix.pod_loc, ix.sel_s, ix.rec_s);
-        g_launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (sorted_pods) {
+            const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 1024
+            uint32_t* chunk_off = ix.hist + ix.cap_bins;
+            k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, chunk_off, chunk_off + 1024);
+            g_launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            k_pod_scatter<W><<<(((P + 7u) & ~7u) + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.pod_ranks, ix.hist, chunk_off, n_chunks,
+                                                                                    ix.pod_bin, ix.pod_loc, ix.sel_s, ix.rec_s);
+            g_launches++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
         {

@@ -13,7 +13,7 @@ run() { # name, nproc, args...
   echo "$name rc=$? $(tail -1 gpurun_out/m${N}_$name.json | cut -c1-260)"
 }
 # the two-rank exchange test uses two different GPUs here (stores cross NVLink)
-timeout 400 python -m pytest tests/test_exchange_gpu.py -m gpu -q > gpurun_out/m${N}_pytest_exchange.log 2>&1
+timeout 300 python -m pytest tests/test_exchange_gpu.py -m gpu -q > gpurun_out/m${N}_pytest_exchange.log 2>&1
 echo "pytest exchange rc=$? $(tail -1 gpurun_out/m${N}_pytest_exchange.log)"
 for np in 2 4 8; do
   [ $np -le $N ] || continue

@@ -210,10 +210,17 @@ static int rows_hint_mode() { // 1 (default) = mask stores carry an L2 evict-fir
     }();
     return v;
 }
-static int rows_sort_mode() { // 2 (default) = pods in index order, no sort; 0 = 2-D threshold grid (round 1); 1 = exact cpu threshold
-    static const int v = [] {   // measured at C3, aligned pitch: 1326 us unsorted vs 1365 (grid) / 1368 (exact); step 1383 vs 1514 us
-        const char* e = getenv("KS_ROWS_SORT");
-        return e ? atoi(e) : 2;
+static int rows_threads() { // threads per CTA of the mask kernel: 1024 (default) or 768 (leaves room for the argmax kernels)
+    static const int v = [] {
+        const char* e = getenv("KS_ROWS_THREADS");
+        return e && atoi(e) == 768 ? 768 : 1024;
+    }();
+    return v;
+}
+static int rows_pipe() { // 1 (default) = pod records one iteration ahead; 2 = records two ahead and ranks one ahead
+    static const int v = [] {
+        const char* e = getenv("KS_ROWS_PIPE");
+        return e && atoi(e) == 2 ? 2 : 1;
     }();
     return v;
 }
@@ -447,9 +454,10 @@ __device__ __forceinline__ uint32_t lower_bound_i64(Ptr a, uint32_t n, int64_t x
 
 // rank = number of nodes with free < request; nodes at sorted positions >= rank satisfy request <= free
 // (predicates.rs:42).  Two-level search: <=2048 splitters per resource in shared memory, then a window of
-// spl_stride-1 elements of the global sorted array.  The pod is also dropped into bucket
-// (rank_cpu >> sh_c, rank_mem >> sh_m) of a <=64k-bin histogram: the counting sort that follows places pods with
-// equal or neighbouring thresholds next to each other, which is what lets the mask kernel share table rows.
+// spl_stride-1 elements of the global sorted array.
+// The same kernel writes the mask kernel's pod records (thresholds, pod index, selector columns) in pod order: round 1
+// sorted the pods by threshold to tame shared-memory bank conflicts; the rows format is conflict-free for any order and
+// measured faster without the sort (profiles/r02_experiments.txt).
 constexpr uint32_t RW_SEL_GENERIC = 0xFFFFFFFFu;
 constexpr uint32_t RW_PID_NONE = 0xFFFFFFFFu;
 
@@ -470,19 +478,10 @@ __device__ __forceinline__ uint32_t selector_record(uint32_t W, LoadWord word) {
     return n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30));
 }
 
-struct BucketParams {
-    uint32_t sh_c, sh_m, nb_m, n_bins; // n_bins = 4 selector classes x threshold grid
-    uint32_t grid_bins, W;
-    uint32_t exact; // 1: bin = (selector class, exact cpu threshold): consecutive sorted pods share their cpu table rows
-                    // 2: no sort at all - the mask kernel takes the pods in index order (records written here)
-};
-
 __global__ void __launch_bounds__(256)
     k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM, uint32_t N,
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
-                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, BucketParams bk, uint32_t* __restrict__ hist,
-                uint32_t* __restrict__ pod_bin, uint32_t* __restrict__ pod_loc, uint4* __restrict__ rec,
-                unsigned long long* __restrict__ sel_copy) {
+                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, uint32_t W, uint4* __restrict__ rec) {
     __shared__ int64_t s_spl[2][RANK_SPLITTERS];
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
@@ -509,111 +508,9 @@ __global__ void __launch_bounds__(256)
         }
         rk[p] = make_uint2(out[0], out[1]);
         if (cnt_zero) cnt_zero[p] = 0; // k_mask_rows accumulates feasible counts with REDs
-        if (rec) { // unsorted mode: the record goes out here, position = pod index
-            rec[p] = make_uint4(out[0], out[1], p, selector_record(bk.W, [&](uint32_t w) {
-                                    const unsigned long long v = __ldg(pv.sel + (size_t)p * bk.W + w);
-                                    sel_copy[(size_t)p * bk.W + w] = v;
-                                    return v;
-                                }));
-        } else if (hist) {
-            // most significant key: number of required label pairs (0,1,2,3+), so that the lanes of a warp run the
-            // same number of column ANDs in the mask kernel (no divergence in its selector loop)
-            uint32_t n_req = 0;
-            for (uint32_t w = 0; w < bk.W; w++) n_req += __popcll(__ldg(pv.sel + (size_t)p * bk.W + w));
-            const uint32_t bin = bk.exact ? min(n_req, 3u) * bk.grid_bins + out[0]
-                                          : min(n_req, 3u) * bk.grid_bins + (out[0] >> bk.sh_c) * bk.nb_m + (out[1] >> bk.sh_m);
-            pod_bin[p] = bin;
-            pod_loc[p] = atomicAdd(hist + bin, 1u); // arrival order inside a bin is irrelevant to every output
-        }
+        if (rec) // the mask kernel's 16-byte pod record, in pod order
+            rec[p] = make_uint4(out[0], out[1], p, selector_record(W, [&](uint32_t w) { return __ldg(pv.sel + (size_t)p * W + w); }));
     }
-}
-
-// exclusive scan of the bin histogram: CTA c scans bins [1024c, 1024c+1024) in place and publishes its total; the last
-// CTA to finish turns the (<= 1024) chunk totals into exclusive offsets, so k_pod_scatter adds one number per pod
-__global__ void __launch_bounds__(1024)
-    k_bucket_scan(uint32_t* __restrict__ hist, uint32_t n_bins, uint32_t* __restrict__ chunk_total, uint32_t* __restrict__ done) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ bool s_last;
-    const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
-    const uint32_t v = i < n_bins ? hist[i] : 0;
-    uint32_t inc = v;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
-        if (lane >= (uint32_t)off) inc += o;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, w, off);
-            if (lane >= (uint32_t)off) w += o;
-        }
-        s_warp[lane] = w;
-    }
-    __syncthreads();
-    if (i < n_bins) hist[i] = inc - v + (warp ? s_warp[warp - 1] : 0);
-    if (threadIdx.x == 1023) {
-        chunk_total[blockIdx.x] = s_warp[31];
-        __threadfence();
-        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // last CTA: exclusive scan of the chunk totals (gridDim.x <= 1024), in place
-    if (threadIdx.x == 0) *done = 0; // ready for the next call
-    const uint32_t t = threadIdx.x;
-    const uint32_t cv = t < gridDim.x ? __ldcg(chunk_total + t) : 0;
-    uint32_t cinc = cv;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, cinc, off);
-        if (lane >= (uint32_t)off) cinc += o;
-    }
-    __syncthreads();
-    if (lane == 31) s_warp[warp] = cinc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, w, off);
-            if (lane >= (uint32_t)off) w += o;
-        }
-        s_warp[lane] = w;
-    }
-    __syncthreads();
-    if (t < gridDim.x) chunk_total[t] = cinc - cv + (warp ? s_warp[warp - 1] : 0);
-}
-
-// counting-sort scatter: pods in bucket order with everything the mask kernel needs, contiguous.
-// rows kernel: one 16-byte record per sorted pod {threshold_cpu, threshold_mem, pod index, selector columns};
-// "selector columns" = up to three required label-pair bit indices (10 bits each) + their number in bits 30-31,
-// RW_SEL_GENERIC when the selector names more than three pairs (the kernel then walks sel_s).  The list is padded
-// to a multiple of 8 with inactive records (pod index 0xFFFFFFFF).
-template <int W>
-__global__ void __launch_bounds__(256)
-    k_pod_scatter(PodView pv, const uint2* __restrict__ rk, const uint32_t* __restrict__ start,
-                  const uint32_t* __restrict__ chunk_off, uint32_t n_chunks, const uint32_t* __restrict__ pod_bin,
-                  const uint32_t* __restrict__ pod_loc, unsigned long long* __restrict__ sel_s, uint4* __restrict__ rec_s) {
-    (void)n_chunks;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pv.P) {
-        if (p < ((pv.P + 7u) & ~7u)) rec_s[p] = make_uint4(0, 0, RW_PID_NONE, 0); // padding of the last group
-        return;
-    }
-    const uint32_t bin = pod_bin[p];
-    const uint32_t q = start[bin] + __ldg(chunk_off + (bin >> 10)) + pod_loc[p];
-    const uint2 r = rk[p];
-    const uint32_t selrec = selector_record(W, [&](uint32_t w) {
-        const unsigned long long v = __ldg(pv.sel + (size_t)p * W + w);
-        sel_s[(size_t)q * W + w] = v;
-        return v;
-    });
-    rec_s[q] = make_uint4(r.x, r.y, p, selrec);
 }
 
 // ------------------------------------------------------------------------------------------------ rows kernel
@@ -659,7 +556,7 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
     RowsLayout lay;
     const uint16_t* rank;            // [cb][threshold g][resource][tile] u16: 32 bytes per (cb, g)
     const uint4* rec_s;              // sorted pod records, padded to a multiple of 8
-    const unsigned long long* sel_s; // sorted selector words (generic path only)
+    const unsigned long long* sel_s; // the pods' selector words, pod order (generic path only)
     uint32_t n_groups, GS;           // groups of 8 sorted pods; groups per stratum
     uint32_t* mask;                  // may be nullptr
     uint32_t row_words;              // mask row pitch in 32-bit words
@@ -668,17 +565,11 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
 
 // one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
 // a_tab = shared-window address of granule t of line 0 of tabC; tabM and the pair columns sit at constant offsets.
-// c0/c1 = the pod's cpu table row; `reuse` = they already hold the right row (the previous pod of this thread has the
-// same cpu threshold: with the exact sort that is the common case, P >> N makes runs of equal thresholds)
 template <int W, bool PSMEM, bool HINT>
 __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_tab, uint32_t cb, uint32_t t, uint32_t* mask_col,
-                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q, uint64_t pol_st,
-                                              uint4& c0, uint4& c1, bool reuse) {
+                                              uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q, uint64_t pol_st) {
     const uint32_t aC = a_tab + rC * RW_LINE, aM = a_tab + rM * RW_LINE;
-    if (!reuse) {
-        c0 = lds128(aC);
-        c1 = lds128(aC + 128);
-    }
+    const uint4 c0 = lds128(aC), c1 = lds128(aC + 128);
     const uint4 m0 = lds128(aM + RW_TAB_BYTES), m1 = lds128(aM + RW_TAB_BYTES + 128);
     uint4 a, b;
     auto column = [&](uint32_t bit, uint4& q0, uint4& q1) { // node column of one required pair (predicates.rs:48-53)
@@ -742,10 +633,13 @@ __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_
     return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
 }
 
-template <int W, bool PSMEM, bool HINT>
+// (launch bounds of 1024 threads for both block sizes: 64 registers per thread, so that a 768-thread CTA leaves a quarter
+// of the register file to the argmax CTAs that run beside it)
+template <int W, bool PSMEM, bool HINT, int THREADS, int PIPE>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
+    constexpr uint32_t WARPS = THREADS / 32;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid & 7, ps = (tid >> 3) & 3;
     uint64_t pol_st = 0, pol_ld = 0;
     if (HINT) {
@@ -782,8 +676,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
         const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
 
-        // pod records are fetched one iteration ahead; loads are unconditional (slot clamped into the list),
-        // validity only decides whether the item is computed
+        // loads are unconditional (slot clamped into the list); validity only decides whether the item is computed
         const uint32_t last_grp = prm.n_groups - 1;
         auto group_of = [&](uint32_t j) { return (j & (RW_STRATA - 1u)) * prm.GS + (j >> 5); };
         auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
@@ -791,9 +684,29 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
             ra = __ldg(rp);
             rb = __ldg(rp + 1);
         };
+        auto fetch_ranks = [&](const uint4& ra, const uint4& rb, uint32_t& rCa, uint32_t& rMa, uint32_t& rCb, uint32_t& rMb) {
+            if (HINT) {
+                rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
+                rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
+                rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
+                rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
+            } else {
+                rCa = ldg_u16(rk_t + (size_t)ra.x * 16u);
+                rMa = ldg_u16(rk_t + (size_t)ra.y * 16u + 8);
+                rCb = ldg_u16(rk_t + (size_t)rb.x * 16u);
+                rMb = ldg_u16(rk_t + (size_t)rb.y * 16u + 8);
+            }
+        };
         uint32_t j = j0 + warp;
-        uint4 nA, nB; // records of the next iteration
+        // PIPE 1: records of iteration k+1 in flight while k computes (its ranks are loaded at the top of k).
+        // PIPE 2: records of k+2 and ranks of k+1 in flight while k computes.
+        uint4 nA, nB, n2A, n2B;
+        uint32_t kCa = 0, kMa = 0, kCb = 0, kMb = 0;
         fetch_rec(j, nA, nB);
+        if (PIPE == 2) {
+            fetch_rec(j + WARPS, n2A, n2B);
+            fetch_ranks(nA, nB, kCa, kMa, kCb, kMb);
+        }
 
         mbar_wait(&bar, phase);
         phase ^= 1;
@@ -808,31 +721,24 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
                                  ? opaque_ptr(prm.mask + (size_t)tile * 8u)
                                  : nullptr;
 
-        for (; j < j1; j += 32) { // warp-uniform
-            const uint4 rA = nA, rB = nB;
+        for (; j < j1; j += WARPS) { // warp-uniform
+            const uint32_t pidA = nA.z, selA = nA.w, pidB = nB.z, selB = nB.w;
             uint32_t rCa, rMa, rCb, rMb;
-            const bool same_c = rB.x == rA.x; // same cpu threshold: same rank, same table row
-            if (HINT) {
-                rCa = ldg_u16_keep(rk_t + (size_t)rA.x * 16u, pol_ld);
-                rMa = ldg_u16_keep(rk_t + (size_t)rA.y * 16u + 8, pol_ld);
-                rCb = same_c ? rCa : ldg_u16_keep(rk_t + (size_t)rB.x * 16u, pol_ld);
-                rMb = ldg_u16_keep(rk_t + (size_t)rB.y * 16u + 8, pol_ld);
+            if (PIPE == 2) {
+                rCa = kCa, rMa = kMa, rCb = kCb, rMb = kMb;
+                nA = n2A;
+                nB = n2B;
+                fetch_ranks(nA, nB, kCa, kMa, kCb, kMb); // ranks of iteration k+1
+                fetch_rec(j + 2 * WARPS, n2A, n2B);      // records of iteration k+2
             } else {
-                rCa = ldg_u16(rk_t + (size_t)rA.x * 16u);
-                rMa = ldg_u16(rk_t + (size_t)rA.y * 16u + 8);
-                rCb = same_c ? rCa : ldg_u16(rk_t + (size_t)rB.x * 16u);
-                rMb = ldg_u16(rk_t + (size_t)rB.y * 16u + 8);
+                fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
+                fetch_rec(j + WARPS, nA, nB);
             }
-            fetch_rec(j + 32, nA, nB);
-            const uint32_t pidA = rA.z, selA = rA.w, pidB = rB.z, selB = rB.w;
             const uint32_t grp0 = group_of(j);
             if (grp0 > last_grp) continue; // slot past the end of its stratum
 
-            uint4 c0, c1;
-            const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps,
-                                                               pol_st, c0, c1, false);
-            const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u,
-                                                               pol_st, c0, c1, same_c);
+            const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps, pol_st);
+            const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u, pol_st);
             if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
                 uint32_t c = cA | (cB << 16);
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -1203,7 +1109,6 @@ static cudaError_t regrow(T*& p, size_t count) {
 void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
                     ix.ord_idx, ix.splC,  ix.splM,  ix.blobP,    ix.pod_ranks, ix.tail_list,
-                    ix.pod_bin, ix.pod_loc, ix.sel_s, ix.hist,
                     ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.rec_s,
                     ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live};
     for (void* p : ptrs)
@@ -1321,11 +1226,18 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
     return ix.valid && (uint64_t)P * ix.N >= (1ull << 24) && (uint64_t)P * ix.lay.nt < (1ull << 31);
 }
 
+template <int W, bool HINT, int THREADS, int PIPE>
+static cudaError_t set_smem_attr1() {
+    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, HINT, THREADS, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+}
 template <int W>
 static cudaError_t set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(k_mask_rows<W, W <= 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    cudaError_t e;
+    if ((e = set_smem_attr1<W, true, 1024, 1>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, false, 1024, 1>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 1024, 2>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 768, 1>()) != cudaSuccess) return e;
+    return set_smem_attr1<W, true, 768, 2>();
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1348,24 +1260,8 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         const size_t cap = (size_t)P + P / 8 + 64;
         if ((e = regrow(ix.pod_ranks, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.tail_list, cap + 1)) != cudaSuccess) return e; // [cap] = the list length counter
-        if ((e = regrow(ix.pod_bin, cap)) != cudaSuccess) return e;
-        if ((e = regrow(ix.pod_loc, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.rec_s, cap + 8)) != cudaSuccess) return e;
         ix.cap_pods = cap;
-        ix.cap_sel = 0;
-    }
-    if ((size_t)P * ix.W > ix.cap_sel) {
-        const size_t cap = ((size_t)P + P / 8 + 64) * ix.W;
-        if ((e = regrow(ix.sel_s, cap)) != cudaSuccess) return e;
-        ix.cap_sel = cap;
-    }
-    { // histogram: [cap_bins bins | 1024 chunk offsets | completion counter]
-        const size_t want_bins = std::max<size_t>(65536, ((size_t)4 * (ix.N + 1) + 1023) / 1024 * 1024);
-        if (want_bins > ix.cap_bins) {
-            if ((e = regrow(ix.hist, want_bins + 1024 + 16)) != cudaSuccess) return e;
-            if ((e = cudaMemset(ix.hist + want_bins + 1024, 0, 64)) != cudaSuccess) return e;
-            ix.cap_bins = want_bins;
-        }
     }
     ix.epoch = g_regrow_epoch.load();
     return cudaSuccess;
@@ -1379,117 +1275,91 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     if ((e = bitpar_prepare(ix, P)) != cudaSuccess) return e; // no-op when the caller prepared already
     const bool need_mask_pass = L.ov.mask || L.ov.cnt;
     const int sms = ix.sms;
-    // bucket grid over (rank_cpu, rank_mem): <= 64k bins, the finest shifts that fit
-    BucketParams bk{0, 0, 0, 0, 0, ix.W, 0};
-    if (rows_sort_mode() == 2) {
-        bk.exact = 2; // no sort
-    } else if (rows_sort_mode() == 1 && (uint64_t)4 * (ix.N + 1) <= (1ull << 20)) {
-        bk.exact = 1; // bin = (selector class, exact cpu threshold)
-        bk.grid_bins = ix.N + 1;
-        bk.n_bins = 4 * bk.grid_bins;
-    } else {
-        uint32_t sh = 0;
-        while ((uint64_t)((ix.N >> sh) + 1) * ((ix.N >> sh) + 1) > 16384ull) sh++;
-        bk.sh_c = sh;
-        bk.sh_m = (sh > 0 && (uint64_t)((ix.N >> sh) + 1) * ((ix.N >> (sh - 1)) + 1) <= 16384ull) ? sh - 1 : sh;
-        bk.nb_m = (ix.N >> bk.sh_m) + 1;
-        bk.grid_bins = ((ix.N >> bk.sh_c) + 1) * bk.nb_m;
-        bk.n_bins = 4 * bk.grid_bins; // <= 65536
-    }
-    const bool sorted_pods = bk.exact != 2;
-    if (need_mask_pass && sorted_pods)
-        if ((e = cudaMemsetAsync(ix.hist, 0, (size_t)bk.n_bins * 4, L.stream)) != cudaSuccess) return e;
     const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256); // 6 CTAs x 32 KB of splitters per SM
-    k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl,
-                                                 ix.spl_stride, ix.pod_ranks,
-                                                 (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, bk,
-                                                 (need_mask_pass && sorted_pods) ? ix.hist : nullptr, ix.pod_bin, ix.pod_loc,
-                                                 (need_mask_pass && !sorted_pods) ? ix.rec_s : nullptr, ix.sel_s);
+    k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
+                                                 ix.pod_ranks, (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, ix.W,
+                                                 need_mask_pass ? ix.rec_s : nullptr);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // argmax scan (needs only the pod ranks).  Normally it runs on an auxiliary stream so that it overlaps the mask
-    // kernel; with per-kernel timing requested it runs after the mask kernel instead, so that the event pair around
-    // the mask kernel times that kernel alone.
+    // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here.  Three orders:
+    //  * timing mode: after the mask kernel, so that the event pair around the mask kernel times that kernel alone;
+    //  * 768-thread mask CTAs on a long pass: the mask kernel is launched FIRST and takes every SM, the argmax CTAs
+    //    (256 threads, no shared memory) fill the room it leaves and run beside it for the whole pass;
+    //  * else: argmax first - it is over in tens of microseconds and the mask CTAs start as its CTAs drain.
     const bool want_bind = L.ov.node_idx || L.ov.score;
     const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
-    auto enqueue_bind = [&]() -> cudaError_t {
+    const int threads = rows_threads();
+    const bool mask_first = overlap_bind && need_mask_pass && threads == 768 && (uint64_t)P * ix.N >= (1ull << 33);
+    if (want_bind) {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
+    }
+    auto enqueue_bind = [&](cudaStream_t bs) -> cudaError_t {
         uint32_t* tail_count = ix.tail_list + ix.cap_pods;
-        if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), ix.aux)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), bs)) != cudaSuccess) return e;
         if (L.policy == KS_SCORE_LEAST_ALLOCATED) {
             const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)P + 7) / 8);
-            k_least_alloc<W><<<grid, 256, 0, ix.aux>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live,
-                                                       ix.N);
+            k_least_alloc<W><<<grid, 256, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live, ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         } else {
             const bool has_tail = ix.layP.nt > FF_HEAD_TILES;
-            k_first_fit_head<W><<<(P + 255) / 256, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks,
-                                                                     L.ov, ix.tail_list, tail_count, L.po, !has_tail, ix.live, ix.N);
+            k_first_fit_head<W><<<(P + 255) / 256, 256, 0, bs>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
+                                                                 ix.tail_list, tail_count, L.po, !has_tail, ix.live, ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (has_tail) {
-                k_first_fit_tail<W><<<sms * 2, 256, 0, ix.aux>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
-                                                                 ix.tail_list, tail_count, L.po);
+                k_first_fit_tail<W><<<sms * 2, 256, 0, bs>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
+                                                             ix.tail_list, tail_count, L.po);
                 g_launches++;
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
             }
         }
         // bindings are final here: start their device-to-host copy now, under the mask kernel
         if (L.host_node_idx && L.ov.node_idx) {
-            if ((e = cudaMemcpyAsync(L.host_node_idx, L.ov.node_idx, (size_t)P * 4, cudaMemcpyDeviceToHost, ix.aux)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(L.host_node_idx, L.ov.node_idx, (size_t)P * 4, cudaMemcpyDeviceToHost, bs)) != cudaSuccess) return e;
             L.host_node_idx = nullptr;
         }
         if (L.host_score && L.ov.score) {
-            if ((e = cudaMemcpyAsync(L.host_score, L.ov.score, (size_t)P * 8, cudaMemcpyDeviceToHost, ix.aux)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(L.host_score, L.ov.score, (size_t)P * 8, cudaMemcpyDeviceToHost, bs)) != cudaSuccess) return e;
             L.host_score = nullptr;
         }
         if (L.ready_event) { // tell the caller that node_idx / score are final (the mask pass may still be running)
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-            if ((e = cudaStreamIsCapturing(ix.aux, &cs)) != cudaSuccess) return e;
-            e = cudaEventRecordWithFlags(L.ready_event, ix.aux,
+            if ((e = cudaStreamIsCapturing(bs, &cs)) != cudaSuccess) return e;
+            e = cudaEventRecordWithFlags(L.ready_event, bs,
                                          cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
             if (e != cudaSuccess) return e;
             L.ready_event = nullptr;
         }
-        return cudaEventRecord(ix.ev_join, ix.aux);
+        return cudaSuccess;
     };
-    if (want_bind && overlap_bind)
-        if ((e = enqueue_bind()) != cudaSuccess) return e;
+    if (want_bind && overlap_bind && !mask_first)
+        if ((e = enqueue_bind(ix.aux)) != cudaSuccess) return e;
     if (need_mask_pass) {
-        if (sorted_pods) {
-            const uint32_t n_chunks = (bk.n_bins + 1023) / 1024; // <= 1024
-            uint32_t* chunk_off = ix.hist + ix.cap_bins;
-            k_bucket_scan<<<n_chunks, 1024, 0, L.stream>>>(ix.hist, bk.n_bins, chunk_off, chunk_off + 1024);
-            g_launches++;
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            k_pod_scatter<W><<<(((P + 7u) & ~7u) + 255) / 256, 256, 0, L.stream>>>(L.pv, ix.pod_ranks, ix.hist, chunk_off, n_chunks,
-                                                                                    ix.pod_bin, ix.pod_loc, ix.sel_s, ix.rec_s);
-            g_launches++;
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        }
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-        {
-            const uint32_t n_groups = (P + 7) / 8;
-            const uint32_t GS = (n_groups + RW_STRATA - 1) / RW_STRATA;
-            const uint64_t F = (uint64_t)RW_STRATA * GS * ix.lay_r.ncb;
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + 31) / 32);
-            auto kern = rows_hint_mode() ? k_mask_rows<W, W <= 4, true> : k_mask_rows<W, W <= 4, false>;
-            RowsParams prm;
-            prm.blob = ix.blobR;
-            prm.lay = ix.lay_r;
-            prm.rank = ix.rank;
-            prm.rec_s = ix.rec_s;
-            prm.sel_s = ix.sel_s;
-            prm.n_groups = n_groups;
-            prm.GS = GS;
-            prm.mask = L.ov.mask;
-            prm.row_words = (uint32_t)L.ov.mask_row_words;
-            prm.cnt = L.ov.cnt;
-            kern<<<grid, BP_THREADS, ix.lay_r.smem_bytes, L.stream>>>(prm);
-        }
+        const uint32_t n_groups = (P + 7) / 8;
+        const uint32_t GS = (n_groups + RW_STRATA - 1) / RW_STRATA;
+        const uint64_t F = (uint64_t)RW_STRATA * GS * ix.lay_r.ncb;
+        const uint32_t warps = (uint32_t)threads / 32;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + warps - 1) / warps);
+        RowsParams prm;
+        prm.blob = ix.blobR;
+        prm.lay = ix.lay_r;
+        prm.rank = ix.rank;
+        prm.rec_s = ix.rec_s;
+        prm.sel_s = reinterpret_cast<const unsigned long long*>(L.pv.sel); // pod order: the caller's selector words
+        prm.n_groups = n_groups;
+        prm.GS = GS;
+        prm.mask = L.ov.mask;
+        prm.row_words = (uint32_t)L.ov.mask_row_words;
+        prm.cnt = L.ov.cnt;
+        void (*kern)(RowsParams);
+        if (threads == 768) kern = rows_pipe() == 2 ? k_mask_rows<W, W <= 4, true, 768, 2> : k_mask_rows<W, W <= 4, true, 768, 1>;
+        else if (rows_pipe() == 2) kern = k_mask_rows<W, W <= 4, true, 1024, 2>;
+        else kern = rows_hint_mode() ? k_mask_rows<W, W <= 4, true, 1024, 1> : k_mask_rows<W, W <= 4, false, 1024, 1>;
+        kern<<<grid, threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)
@@ -1497,10 +1367,14 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     } else if (before_mask) {
         if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
     }
-    if (want_bind && !overlap_bind)
-        if ((e = enqueue_bind()) != cudaSuccess) return e;
-    if (want_bind)
+    if (want_bind && mask_first)
+        if ((e = enqueue_bind(ix.aux)) != cudaSuccess) return e;
+    if (want_bind && !overlap_bind) // timing mode: on the main stream, behind the mask kernel
+        if ((e = enqueue_bind(L.stream)) != cudaSuccess) return e;
+    if (want_bind) { // join the auxiliary stream (it holds the argmax kernels unless timing mode put them on the main one)
+        if ((e = cudaEventRecord(ix.ev_join, ix.aux)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(L.stream, ix.ev_join, 0)) != cudaSuccess) return e;
+    }
     if (after_mask && !need_mask_pass)
         if ((e = cudaEventRecord(after_mask, L.stream)) != cudaSuccess) return e;
     return cudaSuccess;

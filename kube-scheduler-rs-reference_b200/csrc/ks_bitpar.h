@@ -67,9 +67,6 @@ struct BitparIndex {
                                  // read through L1/L2 by k_first_fit_bp
     uint2* pod_ranks = nullptr;  // per-call scratch [P]
     uint32_t* tail_list = nullptr; // per-call scratch [cap_pods + 1]: pods left for k_first_fit_tail, then the count
-    uint32_t* pod_bin = nullptr;   // per-call scratch: threshold bucket of each pod, slot inside the bucket
-    uint32_t* pod_loc = nullptr;
-    unsigned long long* sel_s = nullptr;
     int64_t* ordL_s0 = nullptr;    // KS_SCORE_LEAST_ALLOCATED: score bound of every node in descending order (ties by index)
     int32_t* ordL_idx = nullptr;
     struct NodeEval* evalL = nullptr; // per slot of that order: what the exact score needs
@@ -82,14 +79,13 @@ struct BitparIndex {
     size_t cap_blobR = 0, cap_rank = 0, cap_tsorted = 0;
     RowsLayout lay_r{};
     uint64_t epoch = 0;            // bumped whenever a device buffer of the index is reallocated (CUDA-graph cache key)
-    uint32_t* hist = nullptr;      // [65536] bucket histogram -> exclusive scan
     uint32_t* rk_hist = nullptr;   // node sample sort scratch: [3][256] bucket counts, splitters, per-node bucket / slot, lists
     int64_t* rk_spl_v = nullptr;
     uint32_t* rk_spl_i = nullptr;
     uint8_t* rk_bkt = nullptr;
     uint32_t* rk_loc = nullptr;
     uint32_t* rk_perm = nullptr;
-    size_t cap_nodes = 0, cap_blobP = 0, cap_pods = 0, cap_sel = 0, cap_bins = 0;
+    size_t cap_nodes = 0, cap_blobP = 0, cap_pods = 0;
     uint32_t N = 0, Nord = 0, W = 0, spl_stride = 1, n_spl = 0;
     BitparLayout lay{}, layP{};
     bool valid = false;

@@ -210,17 +210,25 @@ static int rows_hint_mode() { // 1 (default) = mask stores carry an L2 evict-fir
     }();
     return v;
 }
-static int rows_threads() { // threads per CTA of the mask kernel: 1024 (default) or 768 (leaves room for the argmax kernels)
-    static const int v = [] {
+static int rows_threads() { // threads per CTA of the mask kernel.  768 (default) measured best: C3 K2 1291 us vs 1338 us at 1024
+    static const int v = [] {   // (profiles/r02_experiments.txt); it also leaves a quarter of the SM to the argmax kernels
         const char* e = getenv("KS_ROWS_THREADS");
-        return e && atoi(e) == 768 ? 768 : 1024;
+        const int t = e ? atoi(e) : 768;
+        return (t == 512 || t == 640 || t == 768 || t == 896 || t == 1024) ? t : 768;
     }();
     return v;
 }
-static int rows_pipe() { // 1 (default) = pod records one iteration ahead; 2 = records two ahead and ranks one ahead
+static int rows_mask_first() { // -1 (default) = by problem size; 0 / 1 force the launch order of mask and argmax kernels
     static const int v = [] {
-        const char* e = getenv("KS_ROWS_PIPE");
-        return e && atoi(e) == 2 ? 2 : 1;
+        const char* e = getenv("KS_ROWS_MASK_FIRST");
+        return e ? atoi(e) : -1;
+    }();
+    return v;
+}
+static int rows_strata() { // 1 (default) = the pod groups of a column block are dealt to the warps in 32 strata; 0 = in order
+    static const int v = [] {
+        const char* e = getenv("KS_ROWS_STRATA");
+        return e ? atoi(e) : 1;
     }();
     return v;
 }
@@ -557,7 +565,8 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
     const uint16_t* rank;            // [cb][threshold g][resource][tile] u16: 32 bytes per (cb, g)
     const uint4* rec_s;              // sorted pod records, padded to a multiple of 8
     const unsigned long long* sel_s; // the pods' selector words, pod order (generic path only)
-    uint32_t n_groups, GS;           // groups of 8 sorted pods; groups per stratum
+    uint32_t n_groups, GS;           // groups of 8 pods; groups per stratum
+    uint32_t strata;                 // 1 = deal the groups of a column block to the warps in RW_STRATA strata
     uint32_t* mask;                  // may be nullptr
     uint32_t row_words;              // mask row pitch in 32-bit words
     uint32_t* cnt;                   // may be nullptr
@@ -635,7 +644,7 @@ __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_
 
 // (launch bounds of 1024 threads for both block sizes: 64 registers per thread, so that a 768-thread CTA leaves a quarter
 // of the register file to the argmax CTAs that run beside it)
-template <int W, bool PSMEM, bool HINT, int THREADS, int PIPE>
+template <int W, bool PSMEM, bool HINT, int THREADS>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -678,7 +687,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
 
         // loads are unconditional (slot clamped into the list); validity only decides whether the item is computed
         const uint32_t last_grp = prm.n_groups - 1;
-        auto group_of = [&](uint32_t j) { return (j & (RW_STRATA - 1u)) * prm.GS + (j >> 5); };
+        auto group_of = [&](uint32_t j) { return prm.strata ? (j & (RW_STRATA - 1u)) * prm.GS + (j >> 5) : j; };
         auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
             const uint4* rp = rec_t + (size_t)min(group_of(j), last_grp) * 8u;
             ra = __ldg(rp);
@@ -698,15 +707,10 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
             }
         };
         uint32_t j = j0 + warp;
-        // PIPE 1: records of iteration k+1 in flight while k computes (its ranks are loaded at the top of k).
-        // PIPE 2: records of k+2 and ranks of k+1 in flight while k computes.
-        uint4 nA, nB, n2A, n2B;
-        uint32_t kCa = 0, kMa = 0, kCb = 0, kMb = 0;
+        // records of iteration k+1 are in flight while k computes (its ranks are loaded at the top of k; a deeper pipeline
+        // - records two ahead, ranks one ahead - measured 2 % slower: profiles/r02_experiments.txt)
+        uint4 nA, nB;
         fetch_rec(j, nA, nB);
-        if (PIPE == 2) {
-            fetch_rec(j + WARPS, n2A, n2B);
-            fetch_ranks(nA, nB, kCa, kMa, kCb, kMb);
-        }
 
         mbar_wait(&bar, phase);
         phase ^= 1;
@@ -724,16 +728,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         for (; j < j1; j += WARPS) { // warp-uniform
             const uint32_t pidA = nA.z, selA = nA.w, pidB = nB.z, selB = nB.w;
             uint32_t rCa, rMa, rCb, rMb;
-            if (PIPE == 2) {
-                rCa = kCa, rMa = kMa, rCb = kCb, rMb = kMb;
-                nA = n2A;
-                nB = n2B;
-                fetch_ranks(nA, nB, kCa, kMa, kCb, kMb); // ranks of iteration k+1
-                fetch_rec(j + 2 * WARPS, n2A, n2B);      // records of iteration k+2
-            } else {
-                fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
-                fetch_rec(j + WARPS, nA, nB);
-            }
+            fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
+            fetch_rec(j + WARPS, nA, nB);
             const uint32_t grp0 = group_of(j);
             if (grp0 > last_grp) continue; // slot past the end of its stratum
 
@@ -1226,18 +1222,19 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
     return ix.valid && (uint64_t)P * ix.N >= (1ull << 24) && (uint64_t)P * ix.lay.nt < (1ull << 31);
 }
 
-template <int W, bool HINT, int THREADS, int PIPE>
+template <int W, bool HINT, int THREADS>
 static cudaError_t set_smem_attr1() {
-    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, HINT, THREADS, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, HINT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 template <int W>
 static cudaError_t set_smem_attr() {
     cudaError_t e;
-    if ((e = set_smem_attr1<W, true, 1024, 1>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, false, 1024, 1>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 1024, 2>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 768, 1>()) != cudaSuccess) return e;
-    return set_smem_attr1<W, true, 768, 2>();
+    if ((e = set_smem_attr1<W, false, 768>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 512>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 640>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 768>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 896>()) != cudaSuccess) return e;
+    return set_smem_attr1<W, true, 1024>();
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1283,13 +1280,14 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here.  Three orders:
     //  * timing mode: after the mask kernel, so that the event pair around the mask kernel times that kernel alone;
-    //  * 768-thread mask CTAs on a long pass: the mask kernel is launched FIRST and takes every SM, the argmax CTAs
+    //  * <= 768-thread mask CTAs on a long pass: the mask kernel is launched FIRST and takes every SM, the argmax CTAs
     //    (256 threads, no shared memory) fill the room it leaves and run beside it for the whole pass;
     //  * else: argmax first - it is over in tens of microseconds and the mask CTAs start as its CTAs drain.
     const bool want_bind = L.ov.node_idx || L.ov.score;
     const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
     const int threads = rows_threads();
-    const bool mask_first = overlap_bind && need_mask_pass && threads == 768 && (uint64_t)P * ix.N >= (1ull << 33);
+    const bool mask_first = overlap_bind && need_mask_pass && threads <= 768 &&
+                            (rows_mask_first() < 0 ? (uint64_t)P * ix.N >= (1ull << 33) : rows_mask_first() != 0);
     if (want_bind) {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
@@ -1355,11 +1353,16 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         prm.mask = L.ov.mask;
         prm.row_words = (uint32_t)L.ov.mask_row_words;
         prm.cnt = L.ov.cnt;
+        prm.strata = (uint32_t)rows_strata();
         void (*kern)(RowsParams);
-        if (threads == 768) kern = rows_pipe() == 2 ? k_mask_rows<W, W <= 4, true, 768, 2> : k_mask_rows<W, W <= 4, true, 768, 1>;
-        else if (rows_pipe() == 2) kern = k_mask_rows<W, W <= 4, true, 1024, 2>;
-        else kern = rows_hint_mode() ? k_mask_rows<W, W <= 4, true, 1024, 1> : k_mask_rows<W, W <= 4, false, 1024, 1>;
-        kern<<<grid, threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
+        if (!rows_hint_mode()) kern = k_mask_rows<W, W <= 4, false, 768>;
+        else if (threads == 512) kern = k_mask_rows<W, W <= 4, true, 512>;
+        else if (threads == 640) kern = k_mask_rows<W, W <= 4, true, 640>;
+        else if (threads == 896) kern = k_mask_rows<W, W <= 4, true, 896>;
+        else if (threads == 1024) kern = k_mask_rows<W, W <= 4, true, 1024>;
+        else kern = k_mask_rows<W, W <= 4, true, 768>;
+        const int launch_threads = rows_hint_mode() ? threads : 768;
+        kern<<<grid, launch_threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)

@@ -210,25 +210,11 @@ static int rows_hint_mode() { // 1 (default) = mask stores carry an L2 evict-fir
     }();
     return v;
 }
-static int rows_threads() { // threads per CTA of the mask kernel.  768 (default) measured best: C3 K2 1291 us vs 1338 us at 1024
-    static const int v = [] {   // (profiles/r02_experiments.txt); it also leaves a quarter of the SM to the argmax kernels
+static int rows_threads() { // threads per CTA of the mask kernel.  Measured at C3 (K2 / step, us): 512: 1693 / 1783, 640: 1384 / 1494,
+    static const int v = [] {   // 768: 1297 / 1396, 896: 1275 / 1331, 1024: 1338 / 1396 (profiles/r02_experiments.txt) -> 896
         const char* e = getenv("KS_ROWS_THREADS");
-        const int t = e ? atoi(e) : 768;
-        return (t == 512 || t == 640 || t == 768 || t == 896 || t == 1024) ? t : 768;
-    }();
-    return v;
-}
-static int rows_mask_first() { // -1 (default) = by problem size; 0 / 1 force the launch order of mask and argmax kernels
-    static const int v = [] {
-        const char* e = getenv("KS_ROWS_MASK_FIRST");
-        return e ? atoi(e) : -1;
-    }();
-    return v;
-}
-static int rows_strata() { // 1 (default) = the pod groups of a column block are dealt to the warps in 32 strata; 0 = in order
-    static const int v = [] {
-        const char* e = getenv("KS_ROWS_STRATA");
-        return e ? atoi(e) : 1;
+        const int t = e ? atoi(e) : 896;
+        return (t == 768 || t == 832 || t == 896 || t == 960 || t == 1024) ? t : 896;
     }();
     return v;
 }
@@ -532,9 +518,7 @@ __global__ void __launch_bounds__(256)
 //     of their own 256-byte line -> conflict-free for any ranks, plain (unswapped) stores;
 //   * work = flattened (column block, pod group) space cut into gridDim.x equal contiguous ranges: every SM gets
 //     the same share whatever ncb is, a CTA re-stages the table blob only when its range crosses a column block;
-//     inside a column block the sorted pod list is dealt in RW_STRATA strata so that every CTA sees every
-//     selector-size class;
-//   * pod records are fetched two iterations ahead and ranks one iteration ahead (software pipeline).
+//   * pod records (pod order: no sort) are fetched one iteration ahead.
 __device__ __forceinline__ uint4 lds128(uint32_t a) { // pure: scheduled freely; ordered after the blob wait by the
     uint4 v;                                          // address dependence on the post-wait token
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -565,8 +549,7 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
     const uint16_t* rank;            // [cb][threshold g][resource][tile] u16: 32 bytes per (cb, g)
     const uint4* rec_s;              // sorted pod records, padded to a multiple of 8
     const unsigned long long* sel_s; // the pods' selector words, pod order (generic path only)
-    uint32_t n_groups, GS;           // groups of 8 pods; groups per stratum
-    uint32_t strata;                 // 1 = deal the groups of a column block to the warps in RW_STRATA strata
+    uint32_t n_groups;               // groups of 8 pods
     uint32_t* mask;                  // may be nullptr
     uint32_t row_words;              // mask row pitch in 32-bit words
     uint32_t* cnt;                   // may be nullptr
@@ -662,7 +645,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
     __syncthreads();
     uint32_t phase = 0;
 
-    const uint64_t n_slots = (uint64_t)RW_STRATA * prm.GS; // pod-group slots per column block (>= n_groups)
+    const uint64_t n_slots = prm.n_groups; // pod groups per column block
     const uint64_t F = n_slots * prm.lay.ncb;
     uint64_t f = F * blockIdx.x / gridDim.x;
     const uint64_t f_end = F * (blockIdx.x + 1) / gridDim.x;
@@ -685,11 +668,10 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
         const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
 
-        // loads are unconditional (slot clamped into the list); validity only decides whether the item is computed
+        // loads are unconditional (group index clamped into the list)
         const uint32_t last_grp = prm.n_groups - 1;
-        auto group_of = [&](uint32_t j) { return prm.strata ? (j & (RW_STRATA - 1u)) * prm.GS + (j >> 5) : j; };
         auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
-            const uint4* rp = rec_t + (size_t)min(group_of(j), last_grp) * 8u;
+            const uint4* rp = rec_t + (size_t)min(j, last_grp) * 8u;
             ra = __ldg(rp);
             rb = __ldg(rp + 1);
         };
@@ -730,9 +712,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
             uint32_t rCa, rMa, rCb, rMb;
             fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
             fetch_rec(j + WARPS, nA, nB);
-            const uint32_t grp0 = group_of(j);
-            if (grp0 > last_grp) continue; // slot past the end of its stratum
-
+            const uint32_t grp0 = j; // group of 8 consecutive pods
             const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps, pol_st);
             const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u, pol_st);
             if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
@@ -1229,11 +1209,11 @@ static cudaError_t set_smem_attr1() {
 template <int W>
 static cudaError_t set_smem_attr() {
     cudaError_t e;
-    if ((e = set_smem_attr1<W, false, 768>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 512>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 640>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, false, 896>()) != cudaSuccess) return e;
     if ((e = set_smem_attr1<W, true, 768>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 832>()) != cudaSuccess) return e;
     if ((e = set_smem_attr1<W, true, 896>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr1<W, true, 960>()) != cudaSuccess) return e;
     return set_smem_attr1<W, true, 1024>();
 }
 
@@ -1278,16 +1258,13 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
                                                  need_mask_pass ? ix.rec_s : nullptr);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here.  Three orders:
-    //  * timing mode: after the mask kernel, so that the event pair around the mask kernel times that kernel alone;
-    //  * <= 768-thread mask CTAs on a long pass: the mask kernel is launched FIRST and takes every SM, the argmax CTAs
-    //    (256 threads, no shared memory) fill the room it leaves and run beside it for the whole pass;
-    //  * else: argmax first - it is over in tens of microseconds and the mask CTAs start as its CTAs drain.
+    // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here: it is over in tens of microseconds and the
+    // mask CTAs start as its CTAs drain (launching the mask kernel first and letting the argmax CTAs fill the room a
+    // 768-thread mask CTA leaves made no difference: profiles/r02_experiments.txt).  In timing mode it runs after the mask
+    // kernel instead, so that the event pair around the mask kernel times that kernel alone.
     const bool want_bind = L.ov.node_idx || L.ov.score;
     const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
     const int threads = rows_threads();
-    const bool mask_first = overlap_bind && need_mask_pass && threads <= 768 &&
-                            (rows_mask_first() < 0 ? (uint64_t)P * ix.N >= (1ull << 33) : rows_mask_first() != 0);
     if (want_bind) {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
@@ -1332,14 +1309,13 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         }
         return cudaSuccess;
     };
-    if (want_bind && overlap_bind && !mask_first)
+    if (want_bind && overlap_bind)
         if ((e = enqueue_bind(ix.aux)) != cudaSuccess) return e;
     if (need_mask_pass) {
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
         const uint32_t n_groups = (P + 7) / 8;
-        const uint32_t GS = (n_groups + RW_STRATA - 1) / RW_STRATA;
-        const uint64_t F = (uint64_t)RW_STRATA * GS * ix.lay_r.ncb;
+        const uint64_t F = (uint64_t)n_groups * ix.lay_r.ncb;
         const uint32_t warps = (uint32_t)threads / 32;
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + warps - 1) / warps);
         RowsParams prm;
@@ -1349,19 +1325,17 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         prm.rec_s = ix.rec_s;
         prm.sel_s = reinterpret_cast<const unsigned long long*>(L.pv.sel); // pod order: the caller's selector words
         prm.n_groups = n_groups;
-        prm.GS = GS;
         prm.mask = L.ov.mask;
         prm.row_words = (uint32_t)L.ov.mask_row_words;
         prm.cnt = L.ov.cnt;
-        prm.strata = (uint32_t)rows_strata();
         void (*kern)(RowsParams);
-        if (!rows_hint_mode()) kern = k_mask_rows<W, W <= 4, false, 768>;
-        else if (threads == 512) kern = k_mask_rows<W, W <= 4, true, 512>;
-        else if (threads == 640) kern = k_mask_rows<W, W <= 4, true, 640>;
-        else if (threads == 896) kern = k_mask_rows<W, W <= 4, true, 896>;
+        if (!rows_hint_mode()) kern = k_mask_rows<W, W <= 4, false, 896>;
+        else if (threads == 768) kern = k_mask_rows<W, W <= 4, true, 768>;
+        else if (threads == 832) kern = k_mask_rows<W, W <= 4, true, 832>;
+        else if (threads == 960) kern = k_mask_rows<W, W <= 4, true, 960>;
         else if (threads == 1024) kern = k_mask_rows<W, W <= 4, true, 1024>;
-        else kern = k_mask_rows<W, W <= 4, true, 768>;
-        const int launch_threads = rows_hint_mode() ? threads : 768;
+        else kern = k_mask_rows<W, W <= 4, true, 896>;
+        const int launch_threads = rows_hint_mode() ? threads : 896;
         kern<<<grid, launch_threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1370,8 +1344,6 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     } else if (before_mask) {
         if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
     }
-    if (want_bind && mask_first)
-        if ((e = enqueue_bind(ix.aux)) != cudaSuccess) return e;
     if (want_bind && !overlap_bind) // timing mode: on the main stream, behind the mask kernel
         if ((e = enqueue_bind(L.stream)) != cudaSuccess) return e;
     if (want_bind) { // join the auxiliary stream (it holds the argmax kernels unless timing mode put them on the main one)

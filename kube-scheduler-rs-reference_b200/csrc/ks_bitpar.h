@@ -39,7 +39,6 @@ struct BitparLayout { // byte offsets inside one column-block blob
 constexpr uint32_t RW_TILES = 8;                            // tiles per column block
 constexpr uint32_t RW_LINE = 256;                           // bytes per table row / pair column of a column block
 constexpr uint32_t RW_TAB_BYTES = (uint32_t)BP_ROWS * RW_LINE; // 65792
-constexpr uint32_t RW_STRATA = 32;                          // the sorted pod list is dealt to the warps in 32 strata
 
 struct RowsLayout {
     uint32_t ncb;        // column blocks

@@ -57,7 +57,8 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"])
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "bitpar"])
     ap.add_argument("--policy", default="leftover", choices=["leftover", "least_allocated"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how the bindings are all-gathered")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "none"],
+                    help="N>1: how the bindings are all-gathered (none = diagnostic only: shards are not exchanged)")
     ap.add_argument("--no-mask", action="store_true", help="do not emit the feasible mask (bindings only)")
     ap.add_argument("--mask-pitch", default="aligned", choices=["aligned", "minimal"],
                     help="row pitch of the mask buffer: ks_mask_row_bytes_aligned (256-byte blocks) or the smallest legal one")
@@ -313,9 +314,11 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
                 xch.close()
                 xch, use_nccl = None, True
                 exchange_note = "NCCL all-gather (CUDA IPC unavailable on another rank)"
-        else:
+        elif args.exchange == "nccl":
             use_nccl = True
             exchange_note = "1 NCCL all-gather of bindings/step (side stream, under the mask kernel)"
+        else:
+            exchange_note = "NONE (diagnostic run: every rank keeps its shard's bindings; not a valid C4 number)"
     if xch is not None:
         p_idx, p_score = xch.node_idx_ptr, xch.score_ptr
         d_bind = None
@@ -401,6 +404,23 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ks.launch_count() - launches0
+    # device-clock stamps of the last timed step (us from the first kernel of the step seen by the stamps)
+    xtrace = None
+    if xch is not None or os.environ.get("KS_TRACE") == "1":
+        marks = {}
+        if os.environ.get("KS_TRACE") == "1":
+            tr = snap.last_trace()
+            t0 = tr.pop("t0_ns")
+            for name, v in tr.items():
+                if isinstance(v, tuple):
+                    marks[name + "_start"], marks[name + "_end"] = t0 + 1e3 * v[0], t0 + 1e3 * v[1]
+                else:
+                    marks[name] = t0 + 1e3 * v
+        if xch is not None:
+            marks.update({"exchange_" + k: v for k, v in xch.trace_ns().items() if v})
+        if marks:
+            t0 = min(marks.values())
+            xtrace = {k: round((v - t0) / 1e3, 2) for k, v in sorted(marks.items(), key=lambda kv: kv[1])}
     # same K steps again with per-kernel CUDA events inside the library (dominant-kernel duration for the roofline;
     # in this mode the library runs the argmax scan after the mask kernel instead of beside it, so the event pair
     # times the mask kernel alone - the measured HBM peak it is compared with is also a kernel timed alone)
@@ -508,6 +528,7 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
         "ms_per_step": ms_per_step, "step_ms": spread(step_ms), "e2e_value": e2e_value, "e2e_ms": spread([1e3 * t for t in e2e_t]),
         "launches": int(launches), "roofline": roofline, "t_wall": t_wall, "call_ms": sum(call_ms) / len(call_ms),
         "total_pods": total_pods, "strong": strong, "exchange": exchange_note, "emit_mask": emit_mask,
+        "xtrace": xtrace,
         "h2d": P * (16 + 8 * W), "d2h": P * 16, "row": row,
     }
     if world == 1:
@@ -585,11 +606,12 @@ def main():
                         f"mask {'emitted' if r['emit_mask'] else 'not emitted'}",
             "label_words": W, "bound_pods": r["B"], "seed": hex(r["seed"]), "path": r["path"],
             "mask_row_pitch_bytes": r["row"], "mask_row_min_bytes": ks.mask_row_bytes(N),
-            "kernel_switches": {k: os.environ[k] for k in ("KS_ROWS_HINT", "KS_ROWS_SORT") if k in os.environ} or None,
+            "kernel_switches": {k: os.environ[k] for k in ("KS_ROWS_HINT", "KS_ROWS_THREADS") if k in os.environ} or None,
             "parallelism": f"pods sharded x{world}, node table replicated" + (f"; bindings exchange: {r['exchange']}" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": r["t_wall"],
             "clocks_window": "0.4 s untimed soak of the same step + both timed loops (timed region alone is a few ms)",
             "call_ms_inside_library": r["call_ms"], "step_ms": r["step_ms"], "e2e_ms": r["e2e_ms"],
+            **({"trace_us_rank0_last_timed_step": r["xtrace"]} if r.get("xtrace") else {}),
         },
         "clocks": clocks or None,
         "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],

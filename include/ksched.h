@@ -89,7 +89,10 @@ typedef struct ks_exchange {
     int64_t* peer_score[KS_MAX_PEERS];    /* same for score */
     uint32_t* peer_flag[KS_MAX_PEERS];    /* peer k's arrival flag for THIS rank */
     uint32_t* local_flags;                /* this rank's flags [world]; entry r is written by rank r */
-    uint32_t* local_state;                /* this rank's private words [2]: step sequence number, CTA counter (zeroed) */
+    uint32_t* local_state;                /* this rank's private words [16], zeroed, 8-byte aligned: [0] step sequence
+                                             number, [1] CTA counter, [2..11] five 64-bit %globaltimer stamps (ns) of
+                                             the last step: first argmax CTA, flags published, wait started, wait done,
+                                             second argmax kernel started */
 } ks_exchange;
 
 typedef struct ks_bindings { /* outputs; any pointer may be NULL to skip that output */
@@ -164,6 +167,12 @@ int ks_select(ks_snapshot* s, const ks_pods* pods, int policy, uint32_t flags, k
 int ks_last_timings(ks_snapshot* s, float ms[3]);
 /* name of the dominant kernel path the last ks_select used: "direct" or "bitpar" */
 const char* ks_last_path(const ks_snapshot* s);
+/* Timeline of the last bit-parallel ks_select on this snapshot, from %globaltimer stamps written by the kernels
+ * themselves (the streams of a step overlap, which per-kernel profilers serialise).  Only when the process runs with
+ * KS_TRACE=1 in its environment (else KS_ERR_INVALID); synchronises the device.  out_ns[k], nanoseconds of the
+ * device clock, 0 = kernel did not run:  0/1 pod-rank kernel first CTA start / last CTA end, 2/3 first argmax kernel,
+ * 4/5 second argmax kernel, 6/7 mask kernel, 8 end of the mask CTA that finished first; 9..15 reserved (0). */
+int ks_last_trace(ks_snapshot* s, uint64_t out_ns[16]);
 
 /* ---- streaming reconcile (BASELINE.json config C5): micro-batches against the resident snapshot ----
  * The reference re-LISTs bound pods for every cell (src/predicates.rs:34), so a pod always sees earlier binds.

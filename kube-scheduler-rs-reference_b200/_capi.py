@@ -75,6 +75,7 @@ _proto("ks_check_cells", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_void_p)
 _proto("ks_select", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_int, C.c_uint32, C.POINTER(ks_bindings), C.c_void_p)
 _proto("ks_last_timings", C.c_int, C.c_void_p, C.POINTER(C.c_float))
 _proto("ks_last_path", C.c_char_p, C.c_void_p)
+_proto("ks_last_trace", C.c_int, C.c_void_p, C.POINTER(C.c_uint64))
 _proto("ks_snapshot_commit_claims", C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 _proto("ks_stream_bind", C.c_int, C.c_void_p, C.POINTER(ks_pods), C.c_int, C.c_void_p, C.c_void_p,
        C.POINTER(C.c_uint32))

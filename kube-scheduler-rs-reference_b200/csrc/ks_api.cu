@@ -706,6 +706,18 @@ int ks_last_timings(ks_snapshot* s, float ms[3]) {
 
 const char* ks_last_path(const ks_snapshot* s) { return s ? s->last_path : "none"; }
 
+int ks_last_trace(ks_snapshot* s, uint64_t out_ns[16]) {
+    if (!s || !out_ns) return fail(KS_ERR_INVALID, "NULL argument");
+    static_assert(BP_TRACE_WORDS == 16, "ks_last_trace layout");
+    CU_TRY(cudaSetDevice(s->device));
+    unsigned long long tmp[BP_TRACE_WORDS];
+    const cudaError_t e = bitpar_read_trace(s->bp, tmp);
+    if (e == cudaErrorNotSupported) return fail(KS_ERR_INVALID, "no trace: run the process with KS_TRACE=1");
+    if (e != cudaSuccess) return fail(KS_ERR_CUDA, "trace read failed: %s", cudaGetErrorString(e));
+    for (int k = 0; k < BP_TRACE_WORDS; k++) out_ns[k] = tmp[k];
+    return KS_OK;
+}
+
 int ks_exchange_check(ks_snapshot* s) {
     if (!s) return fail(KS_ERR_INVALID, "snapshot is NULL");
     std::lock_guard<std::mutex> lk(s->mu);

@@ -6,8 +6,8 @@
 //                                   tables + label-pair columns, staged in shared memory by the mask kernel
 //                  k_build_ranks    rank tables: tile-local rank of every possible threshold (read through L1/L2)
 //                  k_build_tile     flat indexes in priority order / bound order for the argmax kernels
-//   per call       k_pod_ranks      request -> global rank threshold (splitters in smem + short global search), histogram
-//                  k_bucket_scan / k_pod_scatter   counting sort of the pods; one 16-byte record per sorted pod
+//   per call       k_pod_ranks      request -> global rank threshold (splitters in smem + short global search) and the mask
+//                                   kernel's 16-byte pod record, in pod order
 //                  k_mask_rows      persistent, 1 CTA per SM; table blob staged by TMA bulk copies (cp.async.bulk + mbarrier);
 //                                   8 lanes = the 8 tiles of one pod: rank load -> 2 table rows (+ label columns) -> AND ->
 //                                   one 256-bit store per lane; counts by shuffle + one RED per pod and column block
@@ -22,6 +22,31 @@
 #include <cstring>
 
 namespace ks {
+
+// ------------------------------------------------------------------------------------------------ step trace
+// KS_TRACE=1 (environment, read when the index is created): every kernel of a select stamps %globaltimer into a small
+// device buffer - first CTA at its start, every CTA at its end (atomic max) - so that the timeline of one step can be read
+// back with ks_last_trace (nsys is not available on the target boxes and ncu serialises the streams).  Off: one
+// constant-bank load per CTA.
+__constant__ unsigned long long* c_trace = nullptr;
+enum TraceSlot : int {
+    TR_RANKS_START = 0, TR_RANKS_END, TR_ARGMAX1_START, TR_ARGMAX1_END, TR_ARGMAX2_START, TR_ARGMAX2_END,
+    TR_MASK_START, TR_MASK_END, TR_MASK_FIRST_CTA_END_INV, TR_SLOTS
+};
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// call with one thread per CTA
+__device__ __forceinline__ void trace_start(int slot) {
+    unsigned long long* tr = c_trace;
+    if (tr && blockIdx.x == 0) tr[slot] = global_ns();
+}
+__device__ __forceinline__ void trace_end(int slot) {
+    unsigned long long* tr = c_trace;
+    if (tr) atomicMax(tr + slot, global_ns());
+}
 
 // ------------------------------------------------------------------------------------------------ build
 // ---- node ranking: sample sort ------------------------------------------------------------------------------
@@ -477,6 +502,7 @@ __global__ void __launch_bounds__(256)
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
                 uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, uint32_t W, uint4* __restrict__ rec) {
     __shared__ int64_t s_spl[2][RANK_SPLITTERS];
+    if (threadIdx.x == 0) trace_start(TR_RANKS_START);
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
         s_spl[1][k] = splM[k];
@@ -505,6 +531,21 @@ __global__ void __launch_bounds__(256)
         if (rec) // the mask kernel's 16-byte pod record, in pod order
             rec[p] = make_uint4(out[0], out[1], p, selector_record(W, [&](uint32_t w) { return __ldg(pv.sel + (size_t)p * W + w); }));
     }
+    if (c_trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace_end(TR_RANKS_END);
+    }
+}
+
+// Threads per CTA of the argmax kernels (128 or 256; KS_ARGMAX_THREADS overrides).  A 128-thread CTA of <= 64 registers
+// fits into the eighth of the register file that an 896-thread mask CTA leaves free, a 256-thread one does not.
+static uint32_t argmax_threads() {
+    static const uint32_t v = [] {
+        const char* e = getenv("KS_ARGMAX_THREADS");
+        const int t = e ? atoi(e) : 256;
+        return (t == 128 || t == 256) ? (uint32_t)t : 256u;
+    }();
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------ rows kernel
@@ -641,6 +682,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
+        trace_start(TR_MASK_START);
     }
     __syncthreads();
     uint32_t phase = 0;
@@ -733,6 +775,14 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
             }
         }
     }
+    if (c_trace) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long now = global_ns();
+            atomicMax(c_trace + TR_MASK_END, now);
+            atomicMax(c_trace + TR_MASK_FIRST_CTA_END_INV, ~now); // = ~(earliest CTA end)
+        }
+    }
 }
 
 // ---- argmax of the separable score = first feasible node in descending priority order ----
@@ -818,6 +868,8 @@ __global__ void __launch_bounds__(256)
                      uint32_t* __restrict__ tail_list, uint32_t* __restrict__ tail_count, PeerOut po, bool last_kernel,
                      const unsigned long long* __restrict__ live, uint32_t N) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) exchange_stamp(po, 0);
+    if (threadIdx.x == 0) trace_start(TR_ARGMAX1_START);
     if (p < pv.P) {
         const uint2 r = __ldg(rk + p);
         const PodThreshold t = pod_threshold(blobP, lay, r);
@@ -843,6 +895,10 @@ __global__ void __launch_bounds__(256)
         else tail_list[atomicAdd(tail_count, 1u)] = p; // order of the list does not affect any result
         }
     }
+    if (c_trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace_end(TR_ARGMAX1_END);
+    }
     if (last_kernel) exchange_signal(po); // no tail kernel follows: this rank's bindings are complete
 }
 
@@ -854,6 +910,8 @@ __global__ void __launch_bounds__(256)
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t n = *tail_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) exchange_stamp(po, 4);
+    if (threadIdx.x == 0) trace_start(TR_ARGMAX2_START);
     for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
         const uint32_t p = tail_list[i];
         const PodThreshold t = pod_threshold(blobP, lay, __ldg(rk + p));
@@ -877,6 +935,10 @@ __global__ void __launch_bounds__(256)
             }
         }
         if (lane == 0) write_binding(ov, pv, po, p, slot, ord_idx, ord_prio);
+    }
+    if (c_trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace_end(TR_ARGMAX2_END);
     }
     exchange_signal(po); // the head kernel's stores completed before this kernel started
 }
@@ -955,6 +1017,8 @@ __global__ void __launch_bounds__(256)
     const longlong2 amax = *reinterpret_cast<const longlong2*>(live + KS_MAX_LABEL_WORDS); // max allocatable cpu / memory
     const uint32_t lane = threadIdx.x & 31, wq = lane & 7, quarter = lane >> 3;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) exchange_stamp(po, 0);
+    if (threadIdx.x == 0) trace_start(TR_ARGMAX1_START);
     for (uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < pv.P; p += warps) {
         const uint2 r = __ldg(rk + p);
         const PodThreshold t = pod_threshold(blobL, lay, r);
@@ -1010,6 +1074,10 @@ __global__ void __launch_bounds__(256)
                 po.score[q][p] = score;
             }
         }
+    }
+    if (c_trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) trace_end(TR_ARGMAX1_END);
     }
     exchange_signal(po);
 }
@@ -1089,6 +1157,11 @@ void bitpar_release(BitparIndex& ix) {
                     ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (ix.trace) {
+        unsigned long long* none = nullptr;
+        cudaMemcpyToSymbol(c_trace, &none, sizeof(none));
+        cudaFree(ix.trace);
+    }
     if (ix.aux) cudaStreamDestroy(ix.aux);
     if (ix.ev_fork) cudaEventDestroy(ix.ev_fork);
     if (ix.ev_join) cudaEventDestroy(ix.ev_join);
@@ -1232,6 +1305,12 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = set_smem_attr<2>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<4>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<8>()) != cudaSuccess) return e;
+        const char* tr = getenv("KS_TRACE");
+        if (tr && tr[0] == '1') { // one trace buffer per device: the most recently prepared index owns the stamps
+            if ((e = cudaMalloc(&ix.trace, BP_TRACE_WORDS * sizeof(unsigned long long))) != cudaSuccess) return e;
+            if ((e = cudaMemset(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long))) != cudaSuccess) return e;
+            if ((e = cudaMemcpyToSymbol(c_trace, &ix.trace, sizeof(ix.trace))) != cudaSuccess) return e;
+        }
     }
     if (P > ix.cap_pods) {
         const size_t cap = (size_t)P + P / 8 + 64;
@@ -1252,6 +1331,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     if ((e = bitpar_prepare(ix, P)) != cudaSuccess) return e; // no-op when the caller prepared already
     const bool need_mask_pass = L.ov.mask || L.ov.cnt;
     const int sms = ix.sms;
+    if (ix.trace)
+        if ((e = cudaMemsetAsync(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long), L.stream)) != cudaSuccess) return e;
     const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256); // 6 CTAs x 32 KB of splitters per SM
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
                                                  ix.pod_ranks, (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, ix.W,
@@ -1269,22 +1350,24 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
     }
+    const uint32_t at = argmax_threads();
     auto enqueue_bind = [&](cudaStream_t bs) -> cudaError_t {
         uint32_t* tail_count = ix.tail_list + ix.cap_pods;
         if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), bs)) != cudaSuccess) return e;
         if (L.policy == KS_SCORE_LEAST_ALLOCATED) {
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)P + 7) / 8);
-            k_least_alloc<W><<<grid, 256, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live, ix.N);
+            const uint32_t wpc = at / 32; // one warp per pod
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * (2048 / at), ((uint64_t)P + wpc - 1) / wpc);
+            k_least_alloc<W><<<grid, at, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live, ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         } else {
             const bool has_tail = ix.layP.nt > FF_HEAD_TILES;
-            k_first_fit_head<W><<<(P + 255) / 256, 256, 0, bs>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
+            k_first_fit_head<W><<<(P + at - 1) / at, at, 0, bs>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
                                                                  ix.tail_list, tail_count, L.po, !has_tail, ix.live, ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (has_tail) {
-                k_first_fit_tail<W><<<sms * 2, 256, 0, bs>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
+                k_first_fit_tail<W><<<sms * (512 / at), at, 0, bs>>>(ix.blobP, ix.layP, ix.ord_idx, ix.ord_prio, L.pv, ix.pod_ranks, L.ov,
                                                              ix.tail_list, tail_count, L.po);
                 g_launches++;
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1352,6 +1435,15 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     }
     if (after_mask && !need_mask_pass)
         if ((e = cudaEventRecord(after_mask, L.stream)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t bitpar_read_trace(const BitparIndex& ix, unsigned long long out_ns[BP_TRACE_WORDS]) {
+    if (!ix.trace) return cudaErrorNotSupported;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpy(out_ns, ix.trace, BP_TRACE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+    if (out_ns[TR_MASK_FIRST_CTA_END_INV]) out_ns[TR_MASK_FIRST_CTA_END_INV] = ~out_ns[TR_MASK_FIRST_CTA_END_INV];
     return cudaSuccess;
 }
 

@@ -91,12 +91,16 @@ struct BitparIndex {
     int sms = 0;
     cudaStream_t aux = nullptr; // the argmax kernels run here, overlapped with k_mask_rows
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    unsigned long long* trace = nullptr; // KS_TRACE=1: per-kernel %globaltimer stamps of the last select (ks_last_trace)
 };
+constexpr int BP_TRACE_WORDS = 16;
 
 cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cudaStream_t st);
 bool bitpar_profitable(const BitparIndex& ix, uint32_t P);
 cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P);
 cudaError_t bitpar_select(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before_mask, cudaEvent_t after_mask);
 void bitpar_release(BitparIndex& ix);
+// slots of ks_last_trace (include/ksched.h); cudaErrorNotSupported unless the index was created under KS_TRACE=1
+cudaError_t bitpar_read_trace(const BitparIndex& ix, unsigned long long out_ns[BP_TRACE_WORDS]);
 
 } // namespace ks

@@ -71,6 +71,7 @@ cudaError_t launch_node_prio(const int64_t* free_cpu, const int64_t* free_mem, i
 // inside its argmax kernels (ks_bitpar.cu); the per-cell path pushes its finished arrays with this kernel.
 __global__ void __launch_bounds__(256)
     k_exchange_push(PeerOut po, const int32_t* __restrict__ node_idx, const int64_t* __restrict__ score, uint32_t P) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) exchange_stamp(po, 0);
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         const int32_t ix = node_idx[p];
         const int64_t sc = score[p];
@@ -86,22 +87,26 @@ __global__ void __launch_bounds__(256)
 // lockstep).  A peer that never arrives raises *error_flag after ~4 s instead of hanging the GPU.
 __global__ void __launch_bounds__(32) k_exchange_wait(PeerOut po, int* __restrict__ error_flag) {
     const uint32_t r = threadIdx.x;
-    if (r >= po.world || r == po.rank) return;
-    const uint32_t target = *reinterpret_cast<volatile uint32_t*>(po.state);
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        uint32_t v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(po.local_flags + r) : "memory");
-        if ((int32_t)(v - target) >= 0) break;
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) {
-            if (error_flag) atomicExch(error_flag, 2);
-            break;
+    if (r == 0) exchange_stamp(po, 2);
+    if (r < po.world && r != po.rank) {
+        const uint32_t target = *reinterpret_cast<volatile uint32_t*>(po.state);
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(po.local_flags + r) : "memory");
+            if ((int32_t)(v - target) >= 0) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) {
+                if (error_flag) atomicExch(error_flag, 2);
+                break;
+            }
+            __nanosleep(200);
         }
-        __nanosleep(200);
     }
+    __syncwarp();
+    if (r == 0) exchange_stamp(po, 3);
 }
 
 cudaError_t launch_exchange_push(const PeerOut& po, const int32_t* node_idx, const int64_t* score, uint32_t P, cudaStream_t st) {

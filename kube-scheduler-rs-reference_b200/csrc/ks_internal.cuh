@@ -51,8 +51,18 @@ struct PeerOut {
     int64_t* score[KS_MAX_PEERS];
     uint32_t* flag[KS_MAX_PEERS];
     uint32_t* local_flags = nullptr;
-    uint32_t* state = nullptr; // [0] = step sequence number, [1] = CTA completion counter
+    uint32_t* state = nullptr; // [0] = step sequence number, [1] = CTA completion counter, [2..11] = stamps (below)
 };
+
+// Diagnostic trace of the last exchange step: %globaltimer (ns) of 0 = first argmax CTA started, 1 = flags published,
+// 2 = wait kernel started, 3 = wait kernel saw every peer, 4 = first CTA of the tail kernel started.  Five 64-bit words
+// after the two state words.
+__device__ __forceinline__ void exchange_stamp(const PeerOut& po, int which) {
+    if (po.n == 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<volatile unsigned long long*>(po.state + 2)[which] = t;
+}
 
 // Last CTA of the kernel that completes this rank's bindings: publish a new sequence number to every peer.
 // Call at the very end of the kernel, by all threads of the CTA.
@@ -66,6 +76,7 @@ __device__ __forceinline__ void exchange_signal(const PeerOut& po) {
             po.state[1] = 0; // every CTA has arrived: ready for the next launch
             const uint32_t seq = po.state[0] + 1;
             po.state[0] = seq;
+            exchange_stamp(po, 1);
             __threadfence_system();
             for (uint32_t k = 0; k < po.n; k++)
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(po.flag[k]), "r"(seq) : "memory");

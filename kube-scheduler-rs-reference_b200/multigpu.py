@@ -123,6 +123,17 @@ class PeerExchange:
         idx = buf[self.off_idx:self.off_idx + self.world * self.cap * 4].view(np.int32).reshape(self.world, self.cap)
         return idx, score
 
+    def trace_ns(self):
+        """Device-clock stamps (ns, %globaltimer of this rank's GPU) of the last exchange step:
+        {"argmax1_start", "argmax2_start", "flags_published", "wait_started", "wait_done"}
+        (ks_exchange.local_state words 2..11; synchronises)."""
+        st = np.zeros(6, np.uint64)
+        rc = self._capi.lib.ks_device_read(self.device, self.base + self.off_state, st.ctypes.data, st.nbytes)
+        if rc != self._capi.KS_OK:
+            raise self._capi.KsError(rc, "ks_device_read")
+        names = ("argmax1_start", "flags_published", "wait_started", "wait_done", "argmax2_start")
+        return {k: int(st[1 + i]) for i, k in enumerate(names)}
+
     def close(self):
         lib = self._capi.lib
         for p in self.peer_base.values():

@@ -205,6 +205,23 @@ class Snapshot:
     def last_path(self):
         return lib.ks_last_path(self._h).decode()
 
+    def last_trace(self):
+        """Timeline of the last bit-parallel select (ks_last_trace; needs KS_TRACE=1 in the environment): microseconds
+        from the start of the pod-rank kernel, {name: (start, end)}; kernels that did not run are left out."""
+        ns = (C.c_uint64 * 16)()
+        rc = lib.ks_last_trace(self._h, ns)
+        if rc != capi.KS_OK:
+            raise KsError(rc, "ks_last_trace")
+        t0 = ns[0]
+        out = {}
+        for name, a, b in (("pod_ranks", 0, 1), ("argmax1", 2, 3), ("argmax2", 4, 5), ("mask", 6, 7)):
+            if ns[a] and ns[b]:
+                out[name] = ((ns[a] - t0) / 1e3, (ns[b] - t0) / 1e3)
+        if ns[8]:
+            out["mask_first_cta_end"] = (ns[8] - t0) / 1e3
+        out["t0_ns"] = int(t0)
+        return out
+
     def exchange_check(self):
         """Synchronise and raise if a fused all-gather (ks_exchange) timed out waiting for a peer."""
         rc = lib.ks_exchange_check(self._h)

@@ -113,6 +113,7 @@ int ks_last_timings(ks_snapshot*, float* ms) {
     return KS_OK;
 }
 const char* ks_last_path(const ks_snapshot*) { return "fake"; }
+int ks_last_trace(ks_snapshot*, uint64_t*) { return KS_ERR_INVALID; }
 
 int ks_select_sampling(ks_snapshot* s, const ks_pods* pods, uint32_t attempts, uint64_t seed, uint64_t first, int32_t* idx,
                        uint32_t* used, int32_t* dn, uint8_t* dc) {

@@ -500,9 +500,12 @@ __device__ __forceinline__ uint32_t selector_record(uint32_t W, LoadWord word) {
 __global__ void __launch_bounds__(256)
     k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM, uint32_t N,
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
-                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, uint32_t W, uint4* __restrict__ rec) {
+                uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, uint32_t W, uint4* __restrict__ rec,
+                uint32_t* __restrict__ cursor, uint32_t n_cursor) {
     __shared__ int64_t s_spl[2][RANK_SPLITTERS];
     if (threadIdx.x == 0) trace_start(TR_RANKS_START);
+    if (blockIdx.x == 0) // the mask kernel's chunk cursors
+        for (uint32_t k = threadIdx.x; k < n_cursor; k += blockDim.x) cursor[k] = 0;
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
         s_spl[1][k] = splM[k];
@@ -539,6 +542,8 @@ __global__ void __launch_bounds__(256)
 
 // Threads per CTA of the argmax kernels (128 or 256; KS_ARGMAX_THREADS overrides).  A 128-thread CTA of <= 64 registers
 // fits into the eighth of the register file that an 896-thread mask CTA leaves free, a 256-thread one does not.
+constexpr uint32_t MASK_MAX_CHUNKS = 64; // per CTA range of the mask kernel
+
 static uint32_t argmax_threads() {
     static const uint32_t v = [] {
         const char* e = getenv("KS_ARGMAX_THREADS");
@@ -594,6 +599,8 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
     uint32_t* mask;                  // may be nullptr
     uint32_t row_words;              // mask row pitch in 32-bit words
     uint32_t* cnt;                   // may be nullptr
+    uint32_t* cursor;                // [gridDim.x] next unclaimed chunk of every CTA's range; zeroed by k_pod_ranks
+    uint32_t n_sub;                  // chunks per range
 };
 
 // one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
@@ -672,6 +679,7 @@ template <int W, bool PSMEM, bool HINT, int THREADS>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_claim;
     constexpr uint32_t WARPS = THREADS / 32;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid & 7, ps = (tid >> 3) & 3;
     uint64_t pol_st = 0, pol_ld = 0;
@@ -689,87 +697,123 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
 
     const uint64_t n_slots = prm.n_groups; // pod groups per column block
     const uint64_t F = n_slots * prm.lay.ncb;
-    uint64_t f = F * blockIdx.x / gridDim.x;
-    const uint64_t f_end = F * (blockIdx.x + 1) / gridDim.x;
-
-    while (f < f_end) { // one iteration per column block touched by this CTA's range (1 or 2, rarely more)
-        const uint32_t cb = (uint32_t)(f / n_slots);
-        const uint32_t j0 = (uint32_t)(f - (uint64_t)cb * n_slots);
-        const uint32_t j1 = (uint32_t)min(n_slots, (uint64_t)j0 + (f_end - f));
-        f += j1 - j0;
-
-        __syncthreads(); // all reads of the previous blob are done
-        if (tid == 0) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bar, prm.lay.smem_bytes);
-            const uint8_t* src = prm.blob + (size_t)cb * prm.lay.cb_stride;
-            for (uint32_t off = 0; off < prm.lay.smem_bytes; off += 32768u)
-                tma_bulk_g2s(smem + off, src + off, min(32768u, prm.lay.smem_bytes - off), &bar);
-        }
-        // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
-        const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
-        const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
-
-        // loads are unconditional (group index clamped into the list)
-        const uint32_t last_grp = prm.n_groups - 1;
-        auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
-            const uint4* rp = rec_t + (size_t)min(j, last_grp) * 8u;
-            ra = __ldg(rp);
-            rb = __ldg(rp + 1);
-        };
-        auto fetch_ranks = [&](const uint4& ra, const uint4& rb, uint32_t& rCa, uint32_t& rMa, uint32_t& rCb, uint32_t& rMb) {
-            if (HINT) {
-                rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
-                rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
-                rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
-                rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
-            } else {
-                rCa = ldg_u16(rk_t + (size_t)ra.x * 16u);
-                rMa = ldg_u16(rk_t + (size_t)ra.y * 16u + 8);
-                rCb = ldg_u16(rk_t + (size_t)rb.x * 16u);
-                rMb = ldg_u16(rk_t + (size_t)rb.y * 16u + 8);
+    // Work = F items cut into gridDim.x equal contiguous ranges, one per CTA, each range cut into n_sub chunks that are
+    // handed out by an atomic cursor per range.  A CTA takes the chunks of its own range in order (same column block: no
+    // re-staging); when they are gone it takes chunks of the nearest range that still has some.  SMs do not all stream at
+    // the same rate (with equal static shares the first CTA finished 11 % before the last one on C3), so the fast ones
+    // end up doing a few chunks more.  n_sub == 1 (small problems): one chunk per CTA, no stealing, no extra barriers.
+    const uint32_t n_sub = prm.n_sub;
+    uint32_t victim = blockIdx.x, staged_cb = 0xFFFFFFFFu;
+    for (;;) {
+        __syncthreads(); // the previous chunk is finished by every warp; s_claim may be rewritten
+        if (tid == 0) s_claim = atomicAdd(prm.cursor + victim, 1u);
+        __syncthreads();
+        const uint32_t chunk = s_claim;
+        if (chunk >= n_sub) { // nothing left in that range
+            if (n_sub == 1) break;
+            __syncthreads();
+            if (tid == 0) s_claim = 0xFFFFFFFFu;
+            __syncthreads();
+            for (uint32_t k = tid; k < gridDim.x; k += THREADS) { // nearest range (cyclically) with unclaimed chunks
+                const uint32_t u = (blockIdx.x + 1u + k) % gridDim.x;
+                if (*reinterpret_cast<volatile uint32_t*>(prm.cursor + u) < n_sub) atomicMin(&s_claim, k);
             }
-        };
-        uint32_t j = j0 + warp;
-        // records of iteration k+1 are in flight while k computes (its ranks are loaded at the top of k; a deeper pipeline
-        // - records two ahead, ranks one ahead - measured 2 % slower: profiles/r02_experiments.txt)
-        uint4 nA, nB;
-        fetch_rec(j, nA, nB);
+            __syncthreads();
+            const uint32_t k = s_claim;
+            if (k == 0xFFFFFFFFu) break; // every chunk of every range has been claimed
+            victim = (blockIdx.x + 1u + k) % gridDim.x;
+            continue;
+        }
+        const uint64_t r0 = F * victim / gridDim.x, r1 = F * (victim + 1) / gridDim.x;
+        const uint64_t sub = (r1 - r0 + n_sub - 1) / n_sub;
+        uint64_t f = r0 + (uint64_t)chunk * sub;
+        const uint64_t f_end = min(r1, f + sub);
 
-        mbar_wait(&bar, phase);
-        phase ^= 1;
-        uint32_t tok; // every shared-memory load below depends on a value produced after the wait
-        asm volatile("mov.u32 %0, 0;" : "=r"(tok)::"memory");
-        const uint32_t a_tab = smem_u32(smem) + t * 16u + tok;
-        const uint32_t tile = cb * RW_TILES + t;
-        // a tile is written when it holds nodes, or when the caller's row pitch has room for it (a pitch that is a multiple
-        // of 256 bytes - ks_mask_row_bytes_aligned - lets the 8 lanes of a pod always store one whole, 256-byte-aligned
-        // block: partial blocks cost a third of the store bandwidth, profiles/r02_write_bw_v2.txt); padding tiles hold zeros
-        uint32_t* mask_col = (prm.mask != nullptr && (tile < prm.lay.n_tiles || (tile + 1u) * 8u <= prm.row_words))
-                                 ? opaque_ptr(prm.mask + (size_t)tile * 8u)
-                                 : nullptr;
+        while (f < f_end) { // one iteration per column block touched by this chunk (1, rarely 2)
+            const uint32_t cb = (uint32_t)(f / n_slots);
+            const uint32_t j0 = (uint32_t)(f - (uint64_t)cb * n_slots);
+            const uint32_t j1 = (uint32_t)min(n_slots, (uint64_t)j0 + (f_end - f));
+            f += j1 - j0;
 
-        for (; j < j1; j += WARPS) { // warp-uniform
-            const uint32_t pidA = nA.z, selA = nA.w, pidB = nB.z, selB = nB.w;
-            uint32_t rCa, rMa, rCb, rMb;
-            fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
-            fetch_rec(j + WARPS, nA, nB);
-            const uint32_t grp0 = j; // group of 8 consecutive pods
-            const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps, pol_st);
-            const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u, pol_st);
-            if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
-                uint32_t c = cA | (cB << 16);
-                c += __shfl_xor_sync(0xffffffffu, c, 1);
-                c += __shfl_xor_sync(0xffffffffu, c, 2);
-                c += __shfl_xor_sync(0xffffffffu, c, 4);
-                if (t == 0) {
-                    const uint32_t ca = c & 0xFFFFu, cb_ = c >> 16;
-                    if (prm.lay.ncb == 1) { // single writer, no zero-init needed
-                        if (pidA != RW_PID_NONE) prm.cnt[pidA] = ca;
-                        if (pidB != RW_PID_NONE) prm.cnt[pidB] = cb_;
-                    } else {
-                        if (pidA != RW_PID_NONE && ca) atomicAdd(&prm.cnt[pidA], ca);
-                        if (pidB != RW_PID_NONE && cb_) atomicAdd(&prm.cnt[pidB], cb_);
+            const bool stage = cb != staged_cb; // CTA-uniform
+            if (stage) {
+                staged_cb = cb;
+                __syncthreads(); // all reads of the previous blob are done
+                if (tid == 0) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&bar, prm.lay.smem_bytes);
+                    const uint8_t* src = prm.blob + (size_t)cb * prm.lay.cb_stride;
+                    for (uint32_t off = 0; off < prm.lay.smem_bytes; off += 32768u)
+                        tma_bulk_g2s(smem + off, src + off, min(32768u, prm.lay.smem_bytes - off), &bar);
+                }
+            }
+            // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
+            const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
+            const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
+
+            // loads are unconditional (group index clamped into the list)
+            const uint32_t last_grp = prm.n_groups - 1;
+            auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
+                const uint4* rp = rec_t + (size_t)min(j, last_grp) * 8u;
+                ra = __ldg(rp);
+                rb = __ldg(rp + 1);
+            };
+            auto fetch_ranks = [&](const uint4& ra, const uint4& rb, uint32_t& rCa, uint32_t& rMa, uint32_t& rCb, uint32_t& rMb) {
+                if (HINT) {
+                    rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
+                    rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
+                    rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
+                    rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
+                } else {
+                    rCa = ldg_u16(rk_t + (size_t)ra.x * 16u);
+                    rMa = ldg_u16(rk_t + (size_t)ra.y * 16u + 8);
+                    rCb = ldg_u16(rk_t + (size_t)rb.x * 16u);
+                    rMb = ldg_u16(rk_t + (size_t)rb.y * 16u + 8);
+                }
+            };
+            uint32_t j = j0 + warp;
+            // records of iteration k+1 are in flight while k computes (its ranks are loaded at the top of k; a deeper pipeline
+            // - records two ahead, ranks one ahead - measured 2 % slower: profiles/r02_experiments.txt)
+            uint4 nA, nB;
+            fetch_rec(j, nA, nB);
+
+            if (stage) {
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+            }
+            uint32_t tok; // every shared-memory load below depends on a value produced after the wait
+            asm volatile("mov.u32 %0, 0;" : "=r"(tok)::"memory");
+            const uint32_t a_tab = smem_u32(smem) + t * 16u + tok;
+            const uint32_t tile = cb * RW_TILES + t;
+            // a tile is written when it holds nodes, or when the caller's row pitch has room for it (a pitch that is a multiple
+            // of 256 bytes - ks_mask_row_bytes_aligned - lets the 8 lanes of a pod always store one whole, 256-byte-aligned
+            // block: partial blocks cost a third of the store bandwidth, profiles/r02_write_bw_v2.txt); padding tiles hold zeros
+            uint32_t* mask_col = (prm.mask != nullptr && (tile < prm.lay.n_tiles || (tile + 1u) * 8u <= prm.row_words))
+                                     ? opaque_ptr(prm.mask + (size_t)tile * 8u)
+                                     : nullptr;
+
+            for (; j < j1; j += WARPS) { // warp-uniform
+                const uint32_t pidA = nA.z, selA = nA.w, pidB = nB.z, selB = nB.w;
+                uint32_t rCa, rMa, rCb, rMb;
+                fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
+                fetch_rec(j + WARPS, nA, nB);
+                const uint32_t grp0 = j; // group of 8 consecutive pods
+                const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps, pol_st);
+                const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u, pol_st);
+                if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
+                    uint32_t c = cA | (cB << 16);
+                    c += __shfl_xor_sync(0xffffffffu, c, 1);
+                    c += __shfl_xor_sync(0xffffffffu, c, 2);
+                    c += __shfl_xor_sync(0xffffffffu, c, 4);
+                    if (t == 0) {
+                        const uint32_t ca = c & 0xFFFFu, cb_ = c >> 16;
+                        if (prm.lay.ncb == 1) { // single writer, no zero-init needed
+                            if (pidA != RW_PID_NONE) prm.cnt[pidA] = ca;
+                            if (pidB != RW_PID_NONE) prm.cnt[pidB] = cb_;
+                        } else {
+                            if (pidA != RW_PID_NONE && ca) atomicAdd(&prm.cnt[pidA], ca);
+                            if (pidB != RW_PID_NONE && cb_) atomicAdd(&prm.cnt[pidB], cb_);
+                        }
                     }
                 }
             }
@@ -1157,6 +1201,7 @@ void bitpar_release(BitparIndex& ix) {
                     ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (ix.cursor) cudaFree(ix.cursor);
     if (ix.trace) {
         unsigned long long* none = nullptr;
         cudaMemcpyToSymbol(c_trace, &none, sizeof(none));
@@ -1305,6 +1350,7 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = set_smem_attr<2>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<4>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<8>()) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ix.cursor, (size_t)std::max(ix.sms, 1) * sizeof(uint32_t))) != cudaSuccess) return e;
         const char* tr = getenv("KS_TRACE");
         if (tr && tr[0] == '1') { // one trace buffer per device: the most recently prepared index owns the stamps
             if ((e = cudaMalloc(&ix.trace, BP_TRACE_WORDS * sizeof(unsigned long long))) != cudaSuccess) return e;
@@ -1333,10 +1379,18 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const int sms = ix.sms;
     if (ix.trace)
         if ((e = cudaMemsetAsync(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long), L.stream)) != cudaSuccess) return e;
-    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256); // 6 CTAs x 32 KB of splitters per SM
+    // 6 CTAs x 32 KB of splitters per SM
+    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256);
+    // mask kernel: persistent, one CTA per SM; chunks of >= 8 warp iterations, at most 64 per CTA range (see the kernel)
+    const int threads = rows_threads();
+    const uint32_t n_groups = (P + 7) / 8;
+    const uint64_t F = (uint64_t)n_groups * ix.lay_r.ncb;
+    const uint32_t warps = (uint32_t)threads / 32;
+    const uint32_t mask_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + warps - 1) / warps);
+    const uint32_t n_sub = (uint32_t)std::min<uint64_t>(MASK_MAX_CHUNKS, std::max<uint64_t>(1, F / mask_grid / (8 * warps)));
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
                                                  ix.pod_ranks, (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, ix.W,
-                                                 need_mask_pass ? ix.rec_s : nullptr);
+                                                 need_mask_pass ? ix.rec_s : nullptr, ix.cursor, need_mask_pass ? mask_grid : 0u);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here: it is over in tens of microseconds and the
@@ -1345,7 +1399,6 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     // kernel instead, so that the event pair around the mask kernel times that kernel alone.
     const bool want_bind = L.ov.node_idx || L.ov.score;
     const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
-    const int threads = rows_threads();
     if (want_bind) {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
@@ -1397,10 +1450,6 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     if (need_mask_pass) {
         if (before_mask)
             if ((e = cudaEventRecord(before_mask, L.stream)) != cudaSuccess) return e;
-        const uint32_t n_groups = (P + 7) / 8;
-        const uint64_t F = (uint64_t)n_groups * ix.lay_r.ncb;
-        const uint32_t warps = (uint32_t)threads / 32;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + warps - 1) / warps);
         RowsParams prm;
         prm.blob = ix.blobR;
         prm.lay = ix.lay_r;
@@ -1411,6 +1460,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         prm.mask = L.ov.mask;
         prm.row_words = (uint32_t)L.ov.mask_row_words;
         prm.cnt = L.ov.cnt;
+        prm.cursor = ix.cursor;
+        prm.n_sub = n_sub;
         void (*kern)(RowsParams);
         if (!rows_hint_mode()) kern = k_mask_rows<W, W <= 4, false, 896>;
         else if (threads == 768) kern = k_mask_rows<W, W <= 4, true, 768>;
@@ -1419,7 +1470,7 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         else if (threads == 1024) kern = k_mask_rows<W, W <= 4, true, 1024>;
         else kern = k_mask_rows<W, W <= 4, true, 896>;
         const int launch_threads = rows_hint_mode() ? threads : 896;
-        kern<<<grid, launch_threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
+        kern<<<mask_grid, launch_threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)

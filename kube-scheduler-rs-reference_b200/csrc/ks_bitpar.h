@@ -91,6 +91,7 @@ struct BitparIndex {
     int sms = 0;
     cudaStream_t aux = nullptr; // the argmax kernels run here, overlapped with k_mask_rows
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint32_t* cursor = nullptr; // [sms] chunk cursors of the mask kernel (k_mask_rows), zeroed by k_pod_ranks
     unsigned long long* trace = nullptr; // KS_TRACE=1: per-kernel %globaltimer stamps of the last select (ks_last_trace)
 };
 constexpr int BP_TRACE_WORDS = 16;

@@ -257,6 +257,40 @@ def test_config_c2_full_size_bit_exact(ks, orc, path):
     _assert_same(r, _oracle(orc, cl, 0), f"C2 {path}")
 
 
+def test_mask_chunk_stealing_mid_size(ks, orc):
+    """400k pods x 6000 nodes (3 column blocks): large enough for the mask kernel to cut every CTA's range into several
+    chunks (k_mask_rows: atomic cursors, idle CTAs take chunks of other ranges), small enough for a full compare.  The mask
+    is pre-filled so that a chunk nobody processed - or a byte written twice with different data - shows."""
+    import torch
+    cl = ks.synth.make(400000, 6000, seed=0x5EA1, bound_per_node=2)
+    ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()
+    P, N = cl.P, cl.N
+    dev = torch.device("cuda:0")
+    row_min, row = ks.mask_row_bytes(N), ks.mask_row_bytes_aligned(N)
+    t = [torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).to(dev) for x in (rc, rm, sel)]
+    idx = torch.empty(P, dtype=torch.int32, device=dev)
+    score = torch.empty(P, dtype=torch.int64, device=dev)
+    cnt = torch.empty(P, dtype=torch.int32, device=dev)
+    mask = torch.empty((P, row), dtype=torch.uint8, device=dev)
+    st = torch.cuda.Stream()
+    snap, _ = _snapshot(ks, cl)
+    o_idx, o_score, o_cnt, o_mask, _ = _oracle(orc, cl, 0)
+    with snap:
+        for rep in range(3):  # replays of the cached graph re-arm the cursors every time
+            mask.fill_(0xA5)
+            cnt.fill_(-1)
+            torch.cuda.synchronize()
+            snap.select_raw(P, t[0], t[1], t[2], ks.KS_MEM_DEVICE, idx, score, cnt, ks.KS_MEM_DEVICE, mask=mask,
+                            mask_row_bytes=row, mask_space=ks.KS_MEM_DEVICE, flags=PATHS.get("bitpar", 0), stream=st.cuda_stream)
+            st.synchronize()
+            assert snap.last_path() == "bitpar"
+            m = mask.cpu().numpy()
+            assert np.array_equal(m[:, :row_min], o_mask), f"mask, pass {rep}"
+            assert (m[:, row_min:] == 0).all(), f"mask padding, pass {rep}"
+            assert np.array_equal(cnt.cpu().numpy().view(np.uint32), o_cnt), f"feasible_cnt, pass {rep}"
+            assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(score.cpu().numpy(), o_score)
+
+
 def test_config_c3_full_size_bit_exact(ks, orc):
     """BASELINE.json configs[2]: 1M x 50k (5e10 cells).  EVERY output of the bit-parallel path is compared with the
     packed oracle: the 6.27 GB feasible mask stays in HBM and is checked slab by slab (all host threads run the

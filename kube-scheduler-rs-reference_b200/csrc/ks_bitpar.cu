@@ -542,8 +542,6 @@ __global__ void __launch_bounds__(256)
 
 // Threads per CTA of the argmax kernels (128 or 256; KS_ARGMAX_THREADS overrides).  A 128-thread CTA of <= 64 registers
 // fits into the eighth of the register file that an 896-thread mask CTA leaves free, a 256-thread one does not.
-constexpr uint32_t MASK_MAX_CHUNKS = 64; // per CTA range of the mask kernel
-
 static uint32_t argmax_threads() {
     static const uint32_t v = [] {
         const char* e = getenv("KS_ARGMAX_THREADS");
@@ -556,14 +554,15 @@ static uint32_t argmax_threads() {
 // ------------------------------------------------------------------------------------------------ rows kernel
 // k_mask_rows: the round-2 mask / count kernel ("rows" format, ks_bitpar.h).
 //   * lane = (pod slot, tile): 8 lanes per pod = the 8 tiles of the column block = 256 contiguous bytes of the
-//     pod's mask row per 256-bit store; a warp iteration covers 8 consecutive sorted pods (two per thread, two
+//     pod's mask row per 256-bit store; a warp iteration covers 8 consecutive pods (two per thread, two
 //     independent dependency chains);
 //   * the tile-local rank of the pod's thresholds comes from the rank tables (one 16-bit load per resource from
 //     L1/L2; the 8 lanes of a pod read 16 contiguous bytes) - no base/membership lookup, no POPC for ranks;
 //   * table rows and label-pair columns are octet-interleaved: the 8 lanes of a shared-memory phase read granule t
 //     of their own 256-byte line -> conflict-free for any ranks, plain (unswapped) stores;
-//   * work = flattened (column block, pod group) space cut into gridDim.x equal contiguous ranges: every SM gets
-//     the same share whatever ncb is, a CTA re-stages the table blob only when its range crosses a column block;
+//   * work = (column block, pod group) items handed out dynamically: one atomic cursor per column block, warps claim
+//     RW_CLAIM groups at a time, a CTA whose block is exhausted re-stages the blob of the block with the most work left
+//     (all SMs busy whatever ncb is, and SMs that stream faster simply claim more);
 //   * pod records (pod order: no sort) are fetched one iteration ahead.
 __device__ __forceinline__ uint4 lds128(uint32_t a) { // pure: scheduled freely; ordered after the blob wait by the
     uint4 v;                                          // address dependence on the post-wait token
@@ -599,9 +598,10 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
     uint32_t* mask;                  // may be nullptr
     uint32_t row_words;              // mask row pitch in 32-bit words
     uint32_t* cnt;                   // may be nullptr
-    uint32_t* cursor;                // [gridDim.x] next unclaimed chunk of every CTA's range; zeroed by k_pod_ranks
-    uint32_t n_sub;                  // chunks per range
+    uint32_t* cursor;                // [ncb] next unclaimed pod group of every column block; zeroed by k_pod_ranks
 };
+constexpr uint32_t RW_CLAIM = 4;     // pod groups per claim (one atomicAdd per warp and ~4 x 2 KB x 8 of mask)
+constexpr uint32_t RW_HOP_MIN = 256; // a partly claimed column block is worth moving to while it has this many groups left
 
 // one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
 // a_tab = shared-window address of granule t of line 0 of tabC; tabM and the pair columns sit at constant offsets.
@@ -679,9 +679,8 @@ template <int W, bool PSMEM, bool HINT, int THREADS>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_claim;
-    constexpr uint32_t WARPS = THREADS / 32;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid & 7, ps = (tid >> 3) & 3;
+    __shared__ unsigned long long s_key;
+    const uint32_t tid = threadIdx.x, t = tid & 7, ps = (tid >> 3) & 3;
     uint64_t pol_st = 0, pol_ld = 0;
     if (HINT) {
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_st));
@@ -695,111 +694,87 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
     __syncthreads();
     uint32_t phase = 0;
 
-    const uint64_t n_slots = prm.n_groups; // pod groups per column block
-    const uint64_t F = n_slots * prm.lay.ncb;
-    // Work = F items cut into gridDim.x equal contiguous ranges, one per CTA, each range cut into n_sub chunks that are
-    // handed out by an atomic cursor per range.  A CTA takes the chunks of its own range in order (same column block: no
-    // re-staging); when they are gone it takes chunks of the nearest range that still has some.  SMs do not all stream at
-    // the same rate (with equal static shares the first CTA finished 11 % before the last one on C3), so the fast ones
-    // end up doing a few chunks more.  n_sub == 1 (small problems): one chunk per CTA, no stealing, no extra barriers.
-    const uint32_t n_sub = prm.n_sub;
-    uint32_t victim = blockIdx.x, staged_cb = 0xFFFFFFFFu;
-    for (;;) {
-        __syncthreads(); // the previous chunk is finished by every warp; s_claim may be rewritten
-        if (tid == 0) s_claim = atomicAdd(prm.cursor + victim, 1u);
-        __syncthreads();
-        const uint32_t chunk = s_claim;
-        if (chunk >= n_sub) { // nothing left in that range
-            if (n_sub == 1) break;
-            __syncthreads();
-            if (tid == 0) s_claim = 0xFFFFFFFFu;
-            __syncthreads();
-            for (uint32_t k = tid; k < gridDim.x; k += THREADS) { // nearest range (cyclically) with unclaimed chunks
-                const uint32_t u = (blockIdx.x + 1u + k) % gridDim.x;
-                if (*reinterpret_cast<volatile uint32_t*>(prm.cursor + u) < n_sub) atomicMin(&s_claim, k);
-            }
-            __syncthreads();
-            const uint32_t k = s_claim;
-            if (k == 0xFFFFFFFFu) break; // every chunk of every range has been claimed
-            victim = (blockIdx.x + 1u + k) % gridDim.x;
-            continue;
+    // Work = (column block, pod group) items.  Every column block has one cursor (zeroed by k_pod_ranks); a warp claims
+    // RW_CLAIM consecutive pod groups of the staged column block at a time with one atomicAdd, one claim ahead of the one
+    // it is working on.  The CTAs that share a column block therefore finish it together whatever their individual rates
+    // (with equal static shares the first CTA finished 11 % before the last one on C3: SMs do not all stream at the same
+    // rate), and a CTA whose block is exhausted moves - one barrier, one re-staging of the 148 KB blob - to the block
+    // with the most unclaimed groups.  CTAs start spread evenly over the column blocks.
+    const uint32_t n_slots = prm.n_groups; // pod groups per column block
+    const uint32_t ncb = prm.lay.ncb;
+    const uint32_t lane = tid & 31;
+    const uint32_t last_grp = n_slots - 1;
+    const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
+    // loads are unconditional (group index clamped into the list)
+    auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
+        const uint4* rp = rec_t + (size_t)min(j, last_grp) * 8u;
+        ra = __ldg(rp);
+        rb = __ldg(rp + 1);
+    };
+    uint32_t cb = (uint32_t)((uint64_t)blockIdx.x * ncb / gridDim.x);
+    for (;;) { // one iteration per column block this CTA works on
+        __syncthreads(); // all reads of the previous blob are done
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar, prm.lay.smem_bytes);
+            const uint8_t* src = prm.blob + (size_t)cb * prm.lay.cb_stride;
+            for (uint32_t off = 0; off < prm.lay.smem_bytes; off += 32768u)
+                tma_bulk_g2s(smem + off, src + off, min(32768u, prm.lay.smem_bytes - off), &bar);
         }
-        const uint64_t r0 = F * victim / gridDim.x, r1 = F * (victim + 1) / gridDim.x;
-        const uint64_t sub = (r1 - r0 + n_sub - 1) / n_sub;
-        uint64_t f = r0 + (uint64_t)chunk * sub;
-        const uint64_t f_end = min(r1, f + sub);
-
-        while (f < f_end) { // one iteration per column block touched by this chunk (1, rarely 2)
-            const uint32_t cb = (uint32_t)(f / n_slots);
-            const uint32_t j0 = (uint32_t)(f - (uint64_t)cb * n_slots);
-            const uint32_t j1 = (uint32_t)min(n_slots, (uint64_t)j0 + (f_end - f));
-            f += j1 - j0;
-
-            const bool stage = cb != staged_cb; // CTA-uniform
-            if (stage) {
-                staged_cb = cb;
-                __syncthreads(); // all reads of the previous blob are done
-                if (tid == 0) {
-                    fence_proxy_async();
-                    mbar_arrive_expect_tx(&bar, prm.lay.smem_bytes);
-                    const uint8_t* src = prm.blob + (size_t)cb * prm.lay.cb_stride;
-                    for (uint32_t off = 0; off < prm.lay.smem_bytes; off += 32768u)
-                        tma_bulk_g2s(smem + off, src + off, min(32768u, prm.lay.smem_bytes - off), &bar);
-                }
+        uint32_t* cursor = prm.cursor + cb;
+        auto claim = [&]() -> uint32_t { // lane 0 holds the result; broadcast where it is needed
+            return lane == 0 ? atomicAdd(cursor, RW_CLAIM) : 0u;
+        };
+        uint32_t base = __shfl_sync(0xffffffffu, claim(), 0);
+        uint32_t next_raw = claim();
+        // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
+        const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
+        auto fetch_ranks = [&](const uint4& ra, const uint4& rb, uint32_t& rCa, uint32_t& rMa, uint32_t& rCb, uint32_t& rMb) {
+            if (HINT) {
+                rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
+                rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
+                rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
+                rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
+            } else {
+                rCa = ldg_u16(rk_t + (size_t)ra.x * 16u);
+                rMa = ldg_u16(rk_t + (size_t)ra.y * 16u + 8);
+                rCb = ldg_u16(rk_t + (size_t)rb.x * 16u);
+                rMb = ldg_u16(rk_t + (size_t)rb.y * 16u + 8);
             }
-            // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
-            const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
-            const uint4* rec_t = opaque_ptr(prm.rec_s + 2 * ps); // this thread's pods: 2*ps and 2*ps+1 of the group (neighbours)
+        };
+        // records of iteration k+1 are in flight while k computes (its ranks are loaded at the top of k; a deeper pipeline
+        // - records two ahead, ranks one ahead - measured 2 % slower: profiles/r02_experiments.txt)
+        uint4 nA, nB;
+        fetch_rec(base, nA, nB);
 
-            // loads are unconditional (group index clamped into the list)
-            const uint32_t last_grp = prm.n_groups - 1;
-            auto fetch_rec = [&](uint32_t j, uint4& ra, uint4& rb) {
-                const uint4* rp = rec_t + (size_t)min(j, last_grp) * 8u;
-                ra = __ldg(rp);
-                rb = __ldg(rp + 1);
-            };
-            auto fetch_ranks = [&](const uint4& ra, const uint4& rb, uint32_t& rCa, uint32_t& rMa, uint32_t& rCb, uint32_t& rMb) {
-                if (HINT) {
-                    rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
-                    rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
-                    rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
-                    rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
-                } else {
-                    rCa = ldg_u16(rk_t + (size_t)ra.x * 16u);
-                    rMa = ldg_u16(rk_t + (size_t)ra.y * 16u + 8);
-                    rCb = ldg_u16(rk_t + (size_t)rb.x * 16u);
-                    rMb = ldg_u16(rk_t + (size_t)rb.y * 16u + 8);
-                }
-            };
-            uint32_t j = j0 + warp;
-            // records of iteration k+1 are in flight while k computes (its ranks are loaded at the top of k; a deeper pipeline
-            // - records two ahead, ranks one ahead - measured 2 % slower: profiles/r02_experiments.txt)
-            uint4 nA, nB;
-            fetch_rec(j, nA, nB);
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        uint32_t tok; // every shared-memory load below depends on a value produced after the wait
+        asm volatile("mov.u32 %0, 0;" : "=r"(tok)::"memory");
+        const uint32_t a_tab = smem_u32(smem) + t * 16u + tok;
+        const uint32_t tile = cb * RW_TILES + t;
+        // a tile is written when it holds nodes, or when the caller's row pitch has room for it (a pitch that is a multiple
+        // of 256 bytes - ks_mask_row_bytes_aligned - lets the 8 lanes of a pod always store one whole, 256-byte-aligned
+        // block: partial blocks cost a third of the store bandwidth, profiles/r02_write_bw_v2.txt); padding tiles hold zeros
+        uint32_t* mask_col = (prm.mask != nullptr && (tile < prm.lay.n_tiles || (tile + 1u) * 8u <= prm.row_words))
+                                 ? opaque_ptr(prm.mask + (size_t)tile * 8u)
+                                 : nullptr;
 
-            if (stage) {
-                mbar_wait(&bar, phase);
-                phase ^= 1;
-            }
-            uint32_t tok; // every shared-memory load below depends on a value produced after the wait
-            asm volatile("mov.u32 %0, 0;" : "=r"(tok)::"memory");
-            const uint32_t a_tab = smem_u32(smem) + t * 16u + tok;
-            const uint32_t tile = cb * RW_TILES + t;
-            // a tile is written when it holds nodes, or when the caller's row pitch has room for it (a pitch that is a multiple
-            // of 256 bytes - ks_mask_row_bytes_aligned - lets the 8 lanes of a pod always store one whole, 256-byte-aligned
-            // block: partial blocks cost a third of the store bandwidth, profiles/r02_write_bw_v2.txt); padding tiles hold zeros
-            uint32_t* mask_col = (prm.mask != nullptr && (tile < prm.lay.n_tiles || (tile + 1u) * 8u <= prm.row_words))
-                                     ? opaque_ptr(prm.mask + (size_t)tile * 8u)
-                                     : nullptr;
-
-            for (; j < j1; j += WARPS) { // warp-uniform
+        while (base < n_slots) { // warp-uniform: one claim of up to RW_CLAIM pod groups
+            const uint32_t end = min(base + RW_CLAIM, n_slots);
+            uint32_t next = 0;
+            for (uint32_t j = base; j < end; j++) {
                 const uint32_t pidA = nA.z, selA = nA.w, pidB = nB.z, selB = nB.w;
                 uint32_t rCa, rMa, rCb, rMb;
                 fetch_ranks(nA, nB, rCa, rMa, rCb, rMb);
-                fetch_rec(j + WARPS, nA, nB);
-                const uint32_t grp0 = j; // group of 8 consecutive pods
-                const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, grp0 * 8u + 2u * ps, pol_st);
-                const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, grp0 * 8u + 2u * ps + 1u, pol_st);
+                uint32_t jn = j + 1;
+                if (jn == end) { // last group of the claim: the next claim (requested a whole claim ago) says what follows
+                    next = __shfl_sync(0xffffffffu, next_raw, 0);
+                    jn = next;
+                }
+                fetch_rec(jn, nA, nB);
+                const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, j * 8u + 2u * ps, pol_st);
+                const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, j * 8u + 2u * ps + 1u, pol_st);
                 if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
                     uint32_t c = cA | (cB << 16);
                     c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -807,7 +782,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
                     c += __shfl_xor_sync(0xffffffffu, c, 4);
                     if (t == 0) {
                         const uint32_t ca = c & 0xFFFFu, cb_ = c >> 16;
-                        if (prm.lay.ncb == 1) { // single writer, no zero-init needed
+                        if (ncb == 1) { // single writer, no zero-init needed
                             if (pidA != RW_PID_NONE) prm.cnt[pidA] = ca;
                             if (pidB != RW_PID_NONE) prm.cnt[pidB] = cb_;
                         } else {
@@ -817,7 +792,28 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
                     }
                 }
             }
+            base = next;
+            if (base < n_slots) next_raw = claim();
         }
+
+        // this column block is exhausted (its last groups are being finished by the warps that claimed them, here or in
+        // other CTAs): move to the block with the most unclaimed groups, if any is worth a re-staging
+        if (ncb == 1) break;
+        __syncthreads();
+        if (tid == 0) s_key = 0;
+        __syncthreads();
+        for (uint32_t c = tid; c < ncb; c += THREADS) {
+            const uint32_t used = *reinterpret_cast<volatile uint32_t*>(prm.cursor + c);
+            const uint32_t left = used < n_slots ? n_slots - used : 0u;
+            if (left >= RW_HOP_MIN || (left > 0 && used == 0)) { // key: groups left, then nearness to the current block
+                const uint32_t dist = (c + ncb - cb) % ncb;
+                atomicMax(&s_key, ((unsigned long long)left << 32) | (0xFFFFFFFFu - dist));
+            }
+        }
+        __syncthreads();
+        const unsigned long long key = s_key;
+        if (key == 0) break;
+        cb = (cb + (0xFFFFFFFFu - (uint32_t)key)) % ncb;
     }
     if (c_trace) {
         __syncthreads();
@@ -1198,10 +1194,9 @@ void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
                     ix.ord_idx, ix.splC,  ix.splM,  ix.blobP,    ix.pod_ranks, ix.tail_list,
                     ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.rec_s,
-                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live};
+                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live, ix.cursor};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    if (ix.cursor) cudaFree(ix.cursor);
     if (ix.trace) {
         unsigned long long* none = nullptr;
         cudaMemcpyToSymbol(c_trace, &none, sizeof(none));
@@ -1284,6 +1279,10 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cu
             if ((e = regrow(ix.rank, cap)) != cudaSuccess) return e;
             ix.cap_rank = cap;
         }
+        if (lr.ncb > ix.cap_cursor) { // one work cursor per column block (k_mask_rows)
+            if ((e = regrow(ix.cursor, (size_t)lr.ncb + 64)) != cudaSuccess) return e;
+            ix.cap_cursor = (size_t)lr.ncb + 64;
+        }
         const size_t need_ts = 2ull * lr.ncb * RW_TILES * BP_TILE;
         if (need_ts > ix.cap_tsorted) {
             if ((e = regrow(ix.tile_sorted, need_ts + need_ts / 8)) != cudaSuccess) return e;
@@ -1350,7 +1349,6 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = set_smem_attr<2>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<4>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<8>()) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&ix.cursor, (size_t)std::max(ix.sms, 1) * sizeof(uint32_t))) != cudaSuccess) return e;
         const char* tr = getenv("KS_TRACE");
         if (tr && tr[0] == '1') { // one trace buffer per device: the most recently prepared index owns the stamps
             if ((e = cudaMalloc(&ix.trace, BP_TRACE_WORDS * sizeof(unsigned long long))) != cudaSuccess) return e;
@@ -1381,16 +1379,15 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if ((e = cudaMemsetAsync(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long), L.stream)) != cudaSuccess) return e;
     // 6 CTAs x 32 KB of splitters per SM
     const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256);
-    // mask kernel: persistent, one CTA per SM; chunks of >= 8 warp iterations, at most 64 per CTA range (see the kernel)
+    // mask kernel: persistent, one CTA per SM (fewer when there is less than one pod group per warp)
     const int threads = rows_threads();
     const uint32_t n_groups = (P + 7) / 8;
     const uint64_t F = (uint64_t)n_groups * ix.lay_r.ncb;
     const uint32_t warps = (uint32_t)threads / 32;
     const uint32_t mask_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + warps - 1) / warps);
-    const uint32_t n_sub = (uint32_t)std::min<uint64_t>(MASK_MAX_CHUNKS, std::max<uint64_t>(1, F / mask_grid / (8 * warps)));
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
                                                  ix.pod_ranks, (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, ix.W,
-                                                 need_mask_pass ? ix.rec_s : nullptr, ix.cursor, need_mask_pass ? mask_grid : 0u);
+                                                 need_mask_pass ? ix.rec_s : nullptr, ix.cursor, need_mask_pass ? ix.lay_r.ncb : 0u);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here: it is over in tens of microseconds and the
@@ -1461,7 +1458,6 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         prm.row_words = (uint32_t)L.ov.mask_row_words;
         prm.cnt = L.ov.cnt;
         prm.cursor = ix.cursor;
-        prm.n_sub = n_sub;
         void (*kern)(RowsParams);
         if (!rows_hint_mode()) kern = k_mask_rows<W, W <= 4, false, 896>;
         else if (threads == 768) kern = k_mask_rows<W, W <= 4, true, 768>;

@@ -75,7 +75,7 @@ struct BitparIndex {
     uint8_t* blobR = nullptr;      // rows kernel: lay_r.ncb column-block blobs
     uint16_t* rank = nullptr;      // rows kernel: [cb][threshold g][resource][tile] = nodes of the tile at sorted positions < g
     uint32_t* tile_sorted = nullptr; // build scratch: per tile, its nodes' global positions in ascending order
-    size_t cap_blobR = 0, cap_rank = 0, cap_tsorted = 0;
+    size_t cap_blobR = 0, cap_rank = 0, cap_tsorted = 0, cap_cursor = 0;
     RowsLayout lay_r{};
     uint64_t epoch = 0;            // bumped whenever a device buffer of the index is reallocated (CUDA-graph cache key)
     uint32_t* rk_hist = nullptr;   // node sample sort scratch: [3][256] bucket counts, splitters, per-node bucket / slot, lists
@@ -91,7 +91,7 @@ struct BitparIndex {
     int sms = 0;
     cudaStream_t aux = nullptr; // the argmax kernels run here, overlapped with k_mask_rows
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    uint32_t* cursor = nullptr; // [sms] chunk cursors of the mask kernel (k_mask_rows), zeroed by k_pod_ranks
+    uint32_t* cursor = nullptr; // [ncb] work cursors of the mask kernel (k_mask_rows), zeroed by k_pod_ranks
     unsigned long long* trace = nullptr; // KS_TRACE=1: per-kernel %globaltimer stamps of the last select (ks_last_trace)
 };
 constexpr int BP_TRACE_WORDS = 16;

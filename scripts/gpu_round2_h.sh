@@ -3,7 +3,7 @@
 # argmax block size (128-thread CTAs run beside the mask CTAs, 256-thread ones after them).
 mkdir -p gpurun_out
 timeout 500 python -m pytest tests/test_gpu_parity.py tests/test_trace_gpu.py -m gpu -q -x \
-    -k "chunk_stealing or c3_full or c2_full or step_trace or device_buffers or random_clusters_leftover" > gpurun_out/h_pytest.log 2>&1
+    -k "dynamic_work or c3_full or c2_full or step_trace or device_buffers or random_clusters_leftover" > gpurun_out/h_pytest.log 2>&1
 echo "pytest rc=$? $(tail -1 gpurun_out/h_pytest.log)"
 B="python bench.py --no-cpu-baseline --no-secondary --no-objects"
 show() { python - "$1" <<'PY'

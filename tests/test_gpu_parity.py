@@ -257,10 +257,10 @@ def test_config_c2_full_size_bit_exact(ks, orc, path):
     _assert_same(r, _oracle(orc, cl, 0), f"C2 {path}")
 
 
-def test_mask_chunk_stealing_mid_size(ks, orc):
-    """400k pods x 6000 nodes (3 column blocks): large enough for the mask kernel to cut every CTA's range into several
-    chunks (k_mask_rows: atomic cursors, idle CTAs take chunks of other ranges), small enough for a full compare.  The mask
-    is pre-filled so that a chunk nobody processed - or a byte written twice with different data - shows."""
+def test_mask_dynamic_work_distribution_mid_size(ks, orc):
+    """400k pods x 6000 nodes (3 column blocks, ~50 CTAs each): the mask kernel's dynamic work distribution (k_mask_rows:
+    one atomic cursor per column block, warps claim pod groups, CTAs move to the block with the most work left) on a
+    problem small enough for a full compare.  The mask is pre-filled so that a pod group nobody processed shows."""
     import torch
     cl = ks.synth.make(400000, 6000, seed=0x5EA1, bound_per_node=2)
     ac, am, lab, bn, bc, bm, rc, rm, sel = cl.packed()

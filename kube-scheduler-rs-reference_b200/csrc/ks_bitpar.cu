@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(256) k_node_bound(NodeTable nt, int64_t* __res
 }
 
 constexpr int RANK_SAMPLES = 1024, RANK_BUCKETS = 256;
+// Work cursors of k_mask_rows (one per column block), zeroed by k_pod_ranks.  One cursor per 128-byte line: with all cursors in one line the L2 serialised every claim of the whole chip on it
+// (~3 ns each: 781k claims = the whole 2.4 ms the kernel then took at C3, whatever the block size).
+constexpr uint32_t RW_CURSOR_STRIDE = 32;
 constexpr int RANK_SPLITTERS = 2048; // per resource, in k_pod_ranks' shared memory (32 KB)
 constexpr int N_ORDERS = 4; // free_cpu, free_mem, leftover priority, least-allocated bound
 
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(256)
     __shared__ int64_t s_spl[2][RANK_SPLITTERS];
     if (threadIdx.x == 0) trace_start(TR_RANKS_START);
     if (blockIdx.x == 0) // the mask kernel's chunk cursors
-        for (uint32_t k = threadIdx.x; k < n_cursor; k += blockDim.x) cursor[k] = 0;
+        for (uint32_t k = threadIdx.x; k < n_cursor; k += blockDim.x) cursor[(size_t)k * RW_CURSOR_STRIDE] = 0;
     for (uint32_t k = threadIdx.x; k < n_spl; k += blockDim.x) {
         s_spl[0][k] = splC[k];
         s_spl[1][k] = splM[k];
@@ -598,7 +601,7 @@ struct RowsParams { // kernel parameters stay in the constant bank: the loop rea
     uint32_t* mask;                  // may be nullptr
     uint32_t row_words;              // mask row pitch in 32-bit words
     uint32_t* cnt;                   // may be nullptr
-    uint32_t* cursor;                // [ncb] next unclaimed pod group of every column block; zeroed by k_pod_ranks
+    uint32_t* cursor;                // [ncb * RW_CURSOR_STRIDE] next unclaimed pod group of every column block
 };
 constexpr uint32_t RW_CLAIM = 4;     // pod groups per claim (one atomicAdd per warp and ~4 x 2 KB x 8 of mask)
 constexpr uint32_t RW_HOP_MIN = 256; // a partly claimed column block is worth moving to while it has this many groups left
@@ -721,7 +724,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
             for (uint32_t off = 0; off < prm.lay.smem_bytes; off += 32768u)
                 tma_bulk_g2s(smem + off, src + off, min(32768u, prm.lay.smem_bytes - off), &bar);
         }
-        uint32_t* cursor = prm.cursor + cb;
+        uint32_t* cursor = prm.cursor + (size_t)cb * RW_CURSOR_STRIDE;
         auto claim = [&]() -> uint32_t { // lane 0 holds the result; broadcast where it is needed
             return lane == 0 ? atomicAdd(cursor, RW_CLAIM) : 0u;
         };
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         if (tid == 0) s_key = 0;
         __syncthreads();
         for (uint32_t c = tid; c < ncb; c += THREADS) {
-            const uint32_t used = *reinterpret_cast<volatile uint32_t*>(prm.cursor + c);
+            const uint32_t used = *reinterpret_cast<volatile uint32_t*>(prm.cursor + (size_t)c * RW_CURSOR_STRIDE);
             const uint32_t left = used < n_slots ? n_slots - used : 0u;
             if (left >= RW_HOP_MIN || (left > 0 && used == 0)) { // key: groups left, then nearness to the current block
                 const uint32_t dist = (c + ncb - cb) % ncb;
@@ -1280,7 +1283,7 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cu
             ix.cap_rank = cap;
         }
         if (lr.ncb > ix.cap_cursor) { // one work cursor per column block (k_mask_rows)
-            if ((e = regrow(ix.cursor, (size_t)lr.ncb + 64)) != cudaSuccess) return e;
+            if ((e = regrow(ix.cursor, ((size_t)lr.ncb + 64) * RW_CURSOR_STRIDE)) != cudaSuccess) return e;
             ix.cap_cursor = (size_t)lr.ncb + 64;
         }
         const size_t need_ts = 2ull * lr.ncb * RW_TILES * BP_TILE;

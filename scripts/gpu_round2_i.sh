@@ -21,12 +21,23 @@ except Exception as e:
     print(sys.argv[1], 'unreadable:', e)
 PY
 }
-for at in 256 128; do
-  run c2w_p2p_trace_a$at KS_TRACE=1 KS_ARGMAX_THREADS=$at -- --workload c2
-  run c4_p2p_trace_a$at KS_TRACE=1 KS_ARGMAX_THREADS=$at --
-  run c2w_p2p_a$at KS_ARGMAX_THREADS=$at -- --workload c2
-  run c4_p2p_a$at KS_ARGMAX_THREADS=$at --
-done
+run c2w_p2p_trace_a256 KS_TRACE=1 -- --workload c2
+run c4_p2p_trace_a256 KS_TRACE=1 --
+run c2w_p2p_trace_a128 KS_TRACE=1 KS_ARGMAX_THREADS=128 -- --workload c2
+run c4_p2p_trace_a128 KS_TRACE=1 KS_ARGMAX_THREADS=128 --
 run c2w_none KS_X=0 -- --workload c2 --exchange none
 run c4_none KS_X=0 -- --exchange none
-run c2w_nccl KS_X=0 -- --workload c2 --exchange nccl
+run c4_p2p KS_X=0 --
+run c4_p2p_a128 KS_ARGMAX_THREADS=128 --
+# block-size check of the mask kernel after the dynamic work distribution (1 GPU)
+B="python bench.py --no-cpu-baseline --no-secondary --no-objects"
+for t in 896 960 1024; do
+  for wl in c3 c2; do
+    KS_ROWS_THREADS=$t timeout 240 $B --workload $wl > gpurun_out/i_${wl}_t$t.json 2> gpurun_out/i_${wl}_t$t.err
+    python - gpurun_out/i_${wl}_t$t.json <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r = d['roofline']
+print(sys.argv[1], 'K2', round(1e3*r['kernel_ms'],1), 'us frac', round(r['frac'],3), 'step', round(1e3*d['ms_per_step'],1), 'us')
+PY
+  done
+done

@@ -57,8 +57,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"])
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "bitpar"])
     ap.add_argument("--policy", default="leftover", choices=["leftover", "least_allocated"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "none"],
-                    help="N>1: how the bindings are all-gathered (none = diagnostic only: shards are not exchanged)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: how the bindings are all-gathered")
     ap.add_argument("--no-mask", action="store_true", help="do not emit the feasible mask (bindings only)")
     ap.add_argument("--mask-pitch", default="aligned", choices=["aligned", "minimal"],
                     help="row pitch of the mask buffer: ks_mask_row_bytes_aligned (256-byte blocks) or the smallest legal one")
@@ -314,11 +313,9 @@ def run_workload(ks, torch, dist, args, workload, world, rank, local, steps, war
                 xch.close()
                 xch, use_nccl = None, True
                 exchange_note = "NCCL all-gather (CUDA IPC unavailable on another rank)"
-        elif args.exchange == "nccl":
+        else:
             use_nccl = True
             exchange_note = "1 NCCL all-gather of bindings/step (side stream, under the mask kernel)"
-        else:
-            exchange_note = "NONE (diagnostic run: every rank keeps its shard's bindings; not a valid C4 number)"
     if xch is not None:
         p_idx, p_score = xch.node_idx_ptr, xch.score_ptr
         d_bind = None
@@ -606,7 +603,7 @@ def main():
                         f"mask {'emitted' if r['emit_mask'] else 'not emitted'}",
             "label_words": W, "bound_pods": r["B"], "seed": hex(r["seed"]), "path": r["path"],
             "mask_row_pitch_bytes": r["row"], "mask_row_min_bytes": ks.mask_row_bytes(N),
-            "kernel_switches": {k: os.environ[k] for k in ("KS_ROWS_HINT", "KS_ROWS_THREADS") if k in os.environ} or None,
+            "trace": os.environ.get("KS_TRACE") == "1",
             "parallelism": f"pods sharded x{world}, node table replicated" + (f"; bindings exchange: {r['exchange']}" if world > 1 else ""),
             "l2": "256 MiB flush write between timed iterations", "wall_s_timed_region": r["t_wall"],
             "clocks_window": "0.4 s untimed soak of the same step + both timed loops (timed region alone is a few ms)",

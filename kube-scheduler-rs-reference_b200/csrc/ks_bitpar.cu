@@ -231,21 +231,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-static int rows_hint_mode() { // 1 (default) = mask stores carry an L2 evict-first policy, rank loads evict-last
-    static const int v = [] {   // (measured: C3 1.681 -> 1.642 ms, C2 36.6 -> 34.7 us; profiles/r02_experiments.txt)
-        const char* e = getenv("KS_ROWS_HINT");
-        return e ? atoi(e) : 1;
-    }();
-    return v;
-}
-static int rows_threads() { // threads per CTA of the mask kernel.  Measured at C3 (K2 / step, us): 512: 1693 / 1783, 640: 1384 / 1494,
-    static const int v = [] {   // 768: 1297 / 1396, 896: 1275 / 1331, 1024: 1338 / 1396 (profiles/r02_experiments.txt) -> 896
-        const char* e = getenv("KS_ROWS_THREADS");
-        const int t = e ? atoi(e) : 896;
-        return (t == 768 || t == 832 || t == 896 || t == 960 || t == 1024) ? t : 896;
-    }();
-    return v;
-}
 static uint32_t pair_stride(uint32_t nt) { return nt * 32u; }
 
 // Prefix tables are interleaved by QUADS of tiles: row r of tiles 4k..4k+3 forms one 128-byte line
@@ -517,41 +502,57 @@ __global__ void __launch_bounds__(256)
     if (rec) // padding of the last group of 8
         for (uint32_t p = pv.P + blockIdx.x * blockDim.x + threadIdx.x; p < ((pv.P + 7u) & ~7u); p += gridDim.x * blockDim.x)
             rec[p] = make_uint4(0, 0, RW_PID_NONE, 0);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < pv.P; p += gridDim.x * blockDim.x) {
-        uint32_t out[2];
+    // Two pods per thread and pass, i.e. four searches (2 pods x 2 resources) side by side: the part over the sorted array
+    // in global memory is a chain of dependent L2 loads, and the four chains advance in lockstep (4 loads in flight).
+    const uint32_t T = gridDim.x * blockDim.x;
+    for (uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < pv.P; p0 += 2 * T) {
+        int64_t x[4];
+        uint32_t lo[4], len[4];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int64_t x = r ? __ldg(pv.req_mem + p) : __ldg(pv.req_cpu + p);
-            const int64_t* sorted = r ? sortedM : sortedC;
-            const uint32_t c = lower_bound_i64(s_spl[r], n_spl, x);
-            uint32_t ans = 0;
-            if (c > 0) {
-                const uint32_t lo = (c - 1) * stride + 1; // sorted[lo-1] < x <= sorted[c*stride] (if it exists)
-                const uint32_t len = min(stride - 1, N - lo);
-                ans = lo + lower_bound_i64(sorted + lo, len, x);
-            }
-            out[r] = ans;
+        for (int k = 0; k < 4; k++) { // k = 2 * pod + resource
+            const uint32_t p = min(p0 + (k >> 1) * T, pv.P - 1);
+            x[k] = (k & 1) ? __ldg(pv.req_mem + p) : __ldg(pv.req_cpu + p);
         }
-        rk[p] = make_uint2(out[0], out[1]);
-        if (cnt_zero) cnt_zero[p] = 0; // k_mask_rows accumulates feasible counts with REDs
-        if (rec) // the mask kernel's 16-byte pod record, in pod order
-            rec[p] = make_uint4(out[0], out[1], p, selector_record(W, [&](uint32_t w) { return __ldg(pv.sel + (size_t)p * W + w); }));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t c = lower_bound_i64(s_spl[k & 1], n_spl, x[k]);
+            lo[k] = c > 0 ? (c - 1) * stride + 1 : 0u; // sorted[lo-1] < x <= sorted[c*stride] (if it exists)
+            len[k] = c > 0 ? min(stride - 1, N - lo[k]) : 0u;
+        }
+        while (len[0] | len[1] | len[2] | len[3]) {
+            int64_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int64_t* sorted = (k & 1) ? sortedM : sortedC;
+                v[k] = len[k] ? __ldg(sorted + lo[k] + (len[k] >> 1)) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t half = len[k] >> 1;
+                if (len[k] == 0) continue;
+                if (v[k] < x[k]) {
+                    lo[k] += half + 1;
+                    len[k] -= half + 1;
+                } else {
+                    len[k] = half;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint32_t p = p0 + q * T;
+            if (p >= pv.P) break;
+            rk[p] = make_uint2(lo[2 * q], lo[2 * q + 1]);
+            if (cnt_zero) cnt_zero[p] = 0; // k_mask_rows accumulates feasible counts with REDs
+            if (rec) // the mask kernel's 16-byte pod record, in pod order
+                rec[p] = make_uint4(lo[2 * q], lo[2 * q + 1], p,
+                                    selector_record(W, [&](uint32_t w) { return __ldg(pv.sel + (size_t)p * W + w); }));
+        }
     }
     if (c_trace) {
         __syncthreads();
         if (threadIdx.x == 0) trace_end(TR_RANKS_END);
     }
-}
-
-// Threads per CTA of the argmax kernels (128 or 256; KS_ARGMAX_THREADS overrides).  A 128-thread CTA of <= 64 registers
-// fits into the eighth of the register file that an 896-thread mask CTA leaves free, a 256-thread one does not.
-static uint32_t argmax_threads() {
-    static const uint32_t v = [] {
-        const char* e = getenv("KS_ARGMAX_THREADS");
-        const int t = e ? atoi(e) : 256;
-        return (t == 128 || t == 256) ? (uint32_t)t : 256u;
-    }();
-    return v;
 }
 
 // ------------------------------------------------------------------------------------------------ rows kernel
@@ -570,11 +571,6 @@ static uint32_t argmax_threads() {
 __device__ __forceinline__ uint4 lds128(uint32_t a) { // pure: scheduled freely; ordered after the blob wait by the
     uint4 v;                                          // address dependence on the post-wait token
     asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldg_u16(const uint16_t* p) { // zero-extended into a 32-bit register
-    uint32_t v;
-    asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ uint32_t ldg_u16_keep(const uint16_t* p, uint64_t pol) { // L2 evict-last: the rank tables are re-read
@@ -608,7 +604,7 @@ constexpr uint32_t RW_HOP_MIN = 256; // a partly claimed column block is worth m
 
 // one (pod, tile) item: 256 cells -> mask words a (0..3), b (4..7); returns the number of feasible cells.
 // a_tab = shared-window address of granule t of line 0 of tabC; tabM and the pair columns sit at constant offsets.
-template <int W, bool PSMEM, bool HINT>
+template <int W, bool PSMEM>
 __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_tab, uint32_t cb, uint32_t t, uint32_t* mask_col,
                                               uint32_t rC, uint32_t rM, uint32_t pid, uint32_t sel, uint32_t q, uint64_t pol_st) {
     const uint32_t aC = a_tab + rC * RW_LINE, aM = a_tab + rM * RW_LINE;
@@ -664,31 +660,25 @@ __device__ __forceinline__ uint32_t rows_item(const RowsParams& prm, uint32_t a_
     }
     if (mask_col != nullptr && pid != RW_PID_NONE) {
         uint32_t* dst = mask_col + (size_t)pid * prm.row_words; // 32-byte aligned
-        if (HINT) // the mask is write-once streaming data: first in line for eviction from L2
-            asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(dst), "r"(a.x), "r"(a.y),
-                         "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol_st)
-                         : "memory");
-        else
-            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-                         "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                         : "memory");
+        // the mask is write-once streaming data: first in line for eviction from L2 (plain stores: +2.4 % kernel time)
+        asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(dst), "r"(a.x), "r"(a.y),
+                     "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol_st)
+                     : "memory");
     }
     return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
 }
 
 // (launch bounds of 1024 threads for both block sizes: 64 registers per thread, so that a 768-thread CTA leaves a quarter
 // of the register file to the argmax CTAs that run beside it)
-template <int W, bool PSMEM, bool HINT, int THREADS>
+template <int W, bool PSMEM, int THREADS>
 __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_constant__ RowsParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long s_key;
     const uint32_t tid = threadIdx.x, t = tid & 7, ps = (tid >> 3) & 3;
-    uint64_t pol_st = 0, pol_ld = 0;
-    if (HINT) {
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_st));
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_ld));
-    }
+    uint64_t pol_st, pol_ld; // L2 policies: mask stores evict-first, rank-table loads evict-last
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_st));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_ld));
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -733,17 +723,10 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
         // rank entry of (g, resource r, tile t): rk_t[g * 16 + r * 8]
         const uint16_t* rk_t = opaque_ptr(prm.rank + (size_t)cb * prm.lay.n_thr * (2 * RW_TILES) + t);
         auto fetch_ranks = [&](const uint4& ra, const uint4& rb, uint32_t& rCa, uint32_t& rMa, uint32_t& rCb, uint32_t& rMb) {
-            if (HINT) {
-                rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
-                rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
-                rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
-                rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
-            } else {
-                rCa = ldg_u16(rk_t + (size_t)ra.x * 16u);
-                rMa = ldg_u16(rk_t + (size_t)ra.y * 16u + 8);
-                rCb = ldg_u16(rk_t + (size_t)rb.x * 16u);
-                rMb = ldg_u16(rk_t + (size_t)rb.y * 16u + 8);
-            }
+            rCa = ldg_u16_keep(rk_t + (size_t)ra.x * 16u, pol_ld);
+            rMa = ldg_u16_keep(rk_t + (size_t)ra.y * 16u + 8, pol_ld);
+            rCb = ldg_u16_keep(rk_t + (size_t)rb.x * 16u, pol_ld);
+            rMb = ldg_u16_keep(rk_t + (size_t)rb.y * 16u + 8, pol_ld);
         };
         // records of iteration k+1 are in flight while k computes (its ranks are loaded at the top of k; a deeper pipeline
         // - records two ahead, ranks one ahead - measured 2 % slower: profiles/r02_experiments.txt)
@@ -776,8 +759,8 @@ __global__ void __launch_bounds__(BP_THREADS, 1) k_mask_rows(const __grid_consta
                     jn = next;
                 }
                 fetch_rec(jn, nA, nB);
-                const uint32_t cA = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, j * 8u + 2u * ps, pol_st);
-                const uint32_t cB = rows_item<W, PSMEM, HINT>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, j * 8u + 2u * ps + 1u, pol_st);
+                const uint32_t cA = rows_item<W, PSMEM>(prm, a_tab, cb, t, mask_col, rCa, rMa, pidA, selA, j * 8u + 2u * ps, pol_st);
+                const uint32_t cB = rows_item<W, PSMEM>(prm, a_tab, cb, t, mask_col, rCb, rMb, pidB, selB, j * 8u + 2u * ps + 1u, pol_st);
                 if (prm.cnt != nullptr) { // the 8 lanes of a pod are adjacent; both pods' counts ride in one register
                     uint32_t c = cA | (cB << 16);
                     c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -1322,19 +1305,15 @@ bool bitpar_profitable(const BitparIndex& ix, uint32_t P) {
     return ix.valid && (uint64_t)P * ix.N >= (1ull << 24) && (uint64_t)P * ix.lay.nt < (1ull << 31);
 }
 
-template <int W, bool HINT, int THREADS>
+template <int W, int THREADS>
 static cudaError_t set_smem_attr1() {
-    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, HINT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
+    return cudaFuncSetAttribute(k_mask_rows<W, W <= 4, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM_MAX - 1024);
 }
 template <int W>
 static cudaError_t set_smem_attr() {
     cudaError_t e;
-    if ((e = set_smem_attr1<W, false, 896>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 768>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 832>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 896>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr1<W, true, 960>()) != cudaSuccess) return e;
-    return set_smem_attr1<W, true, 1024>();
+    if ((e = set_smem_attr1<W, 896>()) != cudaSuccess) return e;
+    return set_smem_attr1<W, 960>();
 }
 
 // everything that allocates or configures: must run before a (possibly stream-captured) bitpar_select
@@ -1380,30 +1359,42 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const int sms = ix.sms;
     if (ix.trace)
         if ((e = cudaMemsetAsync(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long), L.stream)) != cudaSuccess) return e;
-    // 6 CTAs x 32 KB of splitters per SM
-    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256);
-    // mask kernel: persistent, one CTA per SM (fewer when there is less than one pod group per warp)
-    const int threads = rows_threads();
+    // 6 CTAs x 32 KB of splitters per SM; two pods per thread and pass
+    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 511) / 512);
+    const bool want_bind = L.ov.node_idx || L.ov.score;
+    const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
+    // How the mask kernel (persistent, one CTA per SM, SM-bound: every SM it does not get costs it 1/#SMs) and the argmax
+    // kernels (latency-bound, ~15 us + 45 ns per 1000 pods on their own) share the chip.  Inside a CUDA graph the mask
+    // kernel gets the SMs first, and a 256-thread argmax CTA does not fit beside a mask CTA (registers), so by default the
+    // argmax kernels run after it (profiles/r02_experiments.txt, sessions G-I).
+    //   * short mask pass (< 256 MB of mask, ~60 us): the mask kernel leaves one SM in six to the argmax kernels, which then
+    //     run beside it from the start; what they (and the exchange behind them) would add at the end costs more than the SMs.
+    //   * long mask pass with an exchange attached: 896-thread mask CTAs + 128-thread argmax CTAs, which do fit beside them:
+    //     the bindings go out to the peers early and the ~18 us of fences / flag latency hide under the mask kernel (the mask
+    //     kernel pays for the company roughly what the argmax kernels cost alone, so without an exchange this buys nothing).
+    //   * long mask pass, no exchange: 960-thread mask CTAs (fastest), argmax kernels behind them.
+    const uint64_t mask_bytes = (uint64_t)P * (L.ov.mask ? L.ov.mask_row_words * 4ull : (uint64_t)ix.lay_r.n_tiles * 32ull);
+    // (timing mode keeps the same shapes; it only moves the argmax kernels behind the mask kernel)
+    const bool short_pass = need_mask_pass && want_bind && mask_bytes < (256ull << 20) && sms >= 48;
+    const bool beside = !short_pass && need_mask_pass && want_bind && L.po.n > 0;
+    const int threads = beside ? 896 : 960;
+    const uint32_t at = beside ? 128u : 256u; // threads per argmax CTA
+    const uint32_t mask_sms = short_pass ? (uint32_t)(sms - sms / 6) : (uint32_t)sms;
     const uint32_t n_groups = (P + 7) / 8;
     const uint64_t F = (uint64_t)n_groups * ix.lay_r.ncb;
     const uint32_t warps = (uint32_t)threads / 32;
-    const uint32_t mask_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, (F + warps - 1) / warps);
+    const uint32_t mask_grid = (uint32_t)std::min<uint64_t>((uint64_t)mask_sms, (F + warps - 1) / warps);
     k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
                                                  ix.pod_ranks, (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, ix.W,
                                                  need_mask_pass ? ix.rec_s : nullptr, ix.cursor, need_mask_pass ? ix.lay_r.ncb : 0u);
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here: it is over in tens of microseconds and the
-    // mask CTAs start as its CTAs drain (launching the mask kernel first and letting the argmax CTAs fill the room a
-    // 768-thread mask CTA leaves made no difference: profiles/r02_experiments.txt).  In timing mode it runs after the mask
-    // kernel instead, so that the event pair around the mask kernel times that kernel alone.
-    const bool want_bind = L.ov.node_idx || L.ov.score;
-    const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
+    // argmax scan (needs only the pod ranks) on an auxiliary stream, forked here.  In timing mode it is enqueued on the main
+    // stream behind the mask kernel instead, so that the event pair around the mask kernel times that kernel alone.
     if (want_bind) {
         if ((e = cudaEventRecord(ix.ev_fork, L.stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ix.aux, ix.ev_fork, 0)) != cudaSuccess) return e;
     }
-    const uint32_t at = argmax_threads();
     auto enqueue_bind = [&](cudaStream_t bs) -> cudaError_t {
         uint32_t* tail_count = ix.tail_list + ix.cap_pods;
         if ((e = cudaMemsetAsync(tail_count, 0, sizeof(uint32_t), bs)) != cudaSuccess) return e;
@@ -1461,15 +1452,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         prm.row_words = (uint32_t)L.ov.mask_row_words;
         prm.cnt = L.ov.cnt;
         prm.cursor = ix.cursor;
-        void (*kern)(RowsParams);
-        if (!rows_hint_mode()) kern = k_mask_rows<W, W <= 4, false, 896>;
-        else if (threads == 768) kern = k_mask_rows<W, W <= 4, true, 768>;
-        else if (threads == 832) kern = k_mask_rows<W, W <= 4, true, 832>;
-        else if (threads == 960) kern = k_mask_rows<W, W <= 4, true, 960>;
-        else if (threads == 1024) kern = k_mask_rows<W, W <= 4, true, 1024>;
-        else kern = k_mask_rows<W, W <= 4, true, 896>;
-        const int launch_threads = rows_hint_mode() ? threads : 896;
-        kern<<<mask_grid, launch_threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
+        void (*kern)(RowsParams) = threads == 896 ? k_mask_rows<W, W <= 4, 896> : k_mask_rows<W, W <= 4, 960>;
+        kern<<<mask_grid, threads, ix.lay_r.smem_bytes, L.stream>>>(prm);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (after_mask)

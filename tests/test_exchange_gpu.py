@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, P, N, flags, q):
+def _worker(rank, world, port, P, N, flags, steps, q):
     try:
         sys.path.insert(0, ROOT)
         import torch
@@ -45,7 +45,7 @@ def _worker(rank, world, port, P, N, flags, q):
         st = torch.cuda.Stream()
         fc, fm = orc.free_reduce(ac, am, bn, bc, bm)
         ok = True
-        for step in range(3):
+        for step in range(steps):
             rc_it = rc + 50 * step  # new requests every step: stale data in a gather buffer would be detected
             t[0].copy_(torch.from_numpy(np.ascontiguousarray(rc_it[lo:hi])))
             torch.cuda.synchronize()
@@ -56,7 +56,7 @@ def _worker(rank, world, port, P, N, flags, q):
             st.synchronize()
             snap.exchange_check()
             g_idx, g_score = xch.read()
-            fi, fs, fcn, fmask, _ = orc.run_packed(fc, fm, ac, am, lab, rc_it, rm, sel, want_mask=True, nthreads=2)
+            fi, fs, fcn, fmask, _ = orc.run_packed(fc, fm, ac, am, lab, rc_it, rm, sel, want_mask=True, nthreads=2 if P * N < 10**9 else 16)
             for r in range(world):
                 l, h = ks.multigpu.shard_bounds(P, world, r)
                 ok &= np.array_equal(g_idx[r, :h - l], fi[l:h]) and np.array_equal(g_score[r, :h - l], fs[l:h])
@@ -72,18 +72,19 @@ def _worker(rank, world, port, P, N, flags, q):
         q.put((rank, False, -1, traceback.format_exc()[-1500:] + str(e)))
 
 
-@pytest.mark.parametrize("P,N,flags", [(40000, 3000, 2), (3001, 2500, 1), (1, 5000, 2)])
-def test_fused_exchange_two_ranks(P, N, flags):
+@pytest.mark.parametrize("P,N,flags,steps", [(40000, 3000, 2, 3), (3001, 2500, 1, 3), (1, 5000, 2, 3), (90000, 50000, 2, 1)])
+def test_fused_exchange_two_ranks(P, N, flags, steps):
     """flags 2 = bit-parallel path (stores fused into the argmax kernels), 1 = per-cell path (push kernel);
-    P = 1 leaves rank 1 with an empty shard."""
+    P = 1 leaves rank 1 with an empty shard; 90000 x 50000 is a long mask pass (282 MB per rank): 896-thread mask CTAs with
+    128-thread argmax CTAs beside them, where the small cases run the argmax kernels on SMs the mask kernel leaves free."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 32000 + (os.getpid() % 2000) + flags
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, P, N, flags, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, P, N, flags, steps, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert sorted(r[0] for r in res) == [0, 1], res

@@ -509,9 +509,9 @@ __global__ void __launch_bounds__(256)
         int64_t x[4];
         uint32_t lo[4], len[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { // k = 2 * pod + resource
-            const uint32_t p = min(p0 + (k >> 1) * T, pv.P - 1);
-            x[k] = (k & 1) ? __ldg(pv.req_mem + p) : __ldg(pv.req_cpu + p);
+        for (int k = 0; k < 4; k++) { // k = 2 * pod + resource; a missing second pod searches for "below everything": no probes
+            const uint32_t p = p0 + (k >> 1) * T;
+            x[k] = p >= pv.P ? INT64_MIN : (k & 1) ? __ldg(pv.req_mem + p) : __ldg(pv.req_cpu + p);
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1359,8 +1359,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const int sms = ix.sms;
     if (ix.trace)
         if ((e = cudaMemsetAsync(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long), L.stream)) != cudaSuccess) return e;
-    // 6 CTAs x 32 KB of splitters per SM; two pods per thread and pass
-    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 511) / 512);
+    // 6 CTAs x 32 KB of splitters per SM; two pods per thread and pass once every thread slot of the chip is taken
+    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256);
     const bool want_bind = L.ov.node_idx || L.ov.score;
     const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
     // How the mask kernel (persistent, one CTA per SM, SM-bound: every SM it does not get costs it 1/#SMs) and the argmax

@@ -31,7 +31,8 @@ for (P, N, keys) in [(300, 700, 8), (70000, 300, 8), (129, 2049, 32)]:
         idx, score, rounds = snap.stream_bind(rc[:200], rm[:200], sel[:200])  # device-side loop (k_stream_batch)
         assert rounds >= 1 and snap.last_path() == "stream_batch"
         with ks.Stream(snap) as q:  # async surface
-            q.submit(rc[200:260], rm[200:260], sel[200:260], np.arange(60, dtype=np.uint64))
+            k0 = min(200, P - 60)
+            q.submit(rc[k0:k0 + 60], rm[k0:k0 + 60], sel[k0:k0 + 60], np.arange(60, dtype=np.uint64))
             q.flush()
             assert len(q.poll()[0]) == 60
 # object level: pack -> upload -> micro-batch loop -> commits

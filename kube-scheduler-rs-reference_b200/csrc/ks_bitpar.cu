@@ -94,7 +94,11 @@ constexpr int RANK_SAMPLES = 1024, RANK_BUCKETS = 256;
 // Work cursors of k_mask_rows (one per column block), zeroed by k_pod_ranks.  One cursor per 128-byte line: with all cursors in one line the L2 serialised every claim of the whole chip on it
 // (~3 ns each: 781k claims = the whole 2.4 ms the kernel then took at C3, whatever the block size).
 constexpr uint32_t RW_CURSOR_STRIDE = 32;
-constexpr int RANK_SPLITTERS = 2048; // per resource, in k_pod_ranks' shared memory (32 KB)
+// Splitters per resource in k_pod_ranks' shared memory (dynamic, 16 bytes per splitter pair: <= 128 KB).  With 8192 the part
+// of a search that is left for the sorted array in L2 covers <= 7 elements of one 64-byte block (C3: stride 8): ~1.6 random
+// 32-byte sector requests per search instead of ~4 with 2048 splitters - and that request rate is what bounds the kernel.
+constexpr int RANK_SPLITTERS = 8192;
+constexpr int RANK_THREADS = 1024; // one CTA per SM
 constexpr int N_ORDERS = 4; // free_cpu, free_mem, leftover priority, least-allocated bound
 
 __global__ void __launch_bounds__(RANK_SAMPLES)
@@ -485,12 +489,13 @@ __device__ __forceinline__ uint32_t selector_record(uint32_t W, LoadWord word) {
     return n_req > 3 ? RW_SEL_GENERIC : (cols | (n_req << 30));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RANK_THREADS, 1)
     k_pod_ranks(PodView pv, const int64_t* __restrict__ sortedC, const int64_t* __restrict__ sortedM, uint32_t N,
                 const int64_t* __restrict__ splC, const int64_t* __restrict__ splM, uint32_t n_spl, uint32_t stride,
                 uint2* __restrict__ rk, uint32_t* __restrict__ cnt_zero, uint32_t W, uint4* __restrict__ rec,
                 uint32_t* __restrict__ cursor, uint32_t n_cursor) {
-    __shared__ int64_t s_spl[2][RANK_SPLITTERS];
+    extern __shared__ __align__(16) unsigned char ranks_smem[];
+    int64_t* const s_spl[2] = {reinterpret_cast<int64_t*>(ranks_smem), reinterpret_cast<int64_t*>(ranks_smem) + n_spl};
     if (threadIdx.x == 0) trace_start(TR_RANKS_START);
     if (blockIdx.x == 0) // the mask kernel's chunk cursors
         for (uint32_t k = threadIdx.x; k < n_cursor; k += blockDim.x) cursor[(size_t)k * RW_CURSOR_STRIDE] = 0;
@@ -983,8 +988,13 @@ struct NodeEval { // one row per slot of the bound order
     int32_t pad;
 };
 
+// Single-precision view of the same row for the pre-filter of k_least_alloc: the real-valued score of (pod, node) is
+//   R = (Sc - rc * Ac + Sm - rm * Am) / 2,  Sc = fc * 100 / ac, Ac = 100 / ac (both 0 when ac <= 0), likewise for memory,
+// and the exact score (two floors, then a halving floor; feasible cells have fc >= rc, fm >= rm) lies in (R - 1.5, R].
+// x = Sc + Sm, y = Ac, z = Am, w = |Sc| + |Sm| (magnitude for the rounding-error bound).
 __global__ void __launch_bounds__(256)
-    k_build_eval(NodeTable nt, const int32_t* __restrict__ ordL_idx, uint32_t Nord, NodeEval* __restrict__ ev) {
+    k_build_eval(NodeTable nt, const int32_t* __restrict__ ordL_idx, uint32_t Nord, NodeEval* __restrict__ ev,
+                 float4* __restrict__ hint) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= Nord) return;
     const int32_t n = ordL_idx[s];
@@ -1003,6 +1013,8 @@ __global__ void __launch_bounds__(256)
     e.inv_ac = e.ac > 0 ? 1.0 / (double)e.ac : 0.0;
     e.inv_am = e.am > 0 ? 1.0 / (double)e.am : 0.0;
     ev[s] = e;
+    const double Sc = e.ac > 0 ? (double)e.fc * 100.0 * e.inv_ac : 0.0, Sm = e.am > 0 ? (double)e.fm * 100.0 * e.inv_am : 0.0;
+    hint[s] = make_float4((float)(Sc + Sm), (float)(100.0 * e.inv_ac), (float)(100.0 * e.inv_am), (float)(fabs(Sc) + fabs(Sm)));
 }
 
 // floor(x / d) for x >= 0, d > 0 (both < 2^63): double estimate, then exact correction in integers
@@ -1038,7 +1050,7 @@ __device__ __forceinline__ int64_t least_alloc_score(const NodeEval& e, int64_t 
 template <int W>
 __global__ void __launch_bounds__(256)
     k_least_alloc(const uint8_t* __restrict__ blobL, BitparLayout lay, const NodeEval* __restrict__ ev,
-                  const int64_t* __restrict__ ordL_s0, PodView pv, const uint2* __restrict__ rk, OutView ov, PeerOut po,
+                  const float4* __restrict__ hint, const int64_t* __restrict__ ordL_s0, PodView pv, const uint2* __restrict__ rk, OutView ov, PeerOut po,
                   const unsigned long long* __restrict__ live, uint32_t N) {
     const longlong2 amax = *reinterpret_cast<const longlong2*>(live + KS_MAX_LABEL_WORDS); // max allocatable cpu / memory
     const uint32_t lane = threadIdx.x & 31, wq = lane & 7, quarter = lane >> 3;
@@ -1056,6 +1068,7 @@ __global__ void __launch_bounds__(256)
             dead |= (sel[w] & ~__ldg(live + w)) != 0; // a required pair that no node carries
         }
         const int64_t rc = __ldg(pv.req_cpu + p), rm = __ldg(pv.req_mem + p);
+        const float rcf = (float)rc, rmf = (float)rm;
         const bool bounded = rc >= 0 && rm >= 0; // else the bound does not hold: no early exit
         // per-pod slack: floor((f-r)*100/a) <= floor(f*100/a) - floor(r*100/a) and a <= a_max, so every feasible cell
         // scores <= bound(n) - D with D = (rc*100/ac_max + rm*100/am_max) / 2
@@ -1071,9 +1084,33 @@ __global__ void __launch_bounds__(256)
             for (int j = 0; j < 8; j++)
                 if ((uint32_t)j == wq) bits = m[j];
             bits &= 0x11111111u << quarter;
-            while (bits) {
-                const uint32_t b = __ffs(bits) - 1;
-                bits &= bits - 1;
+            // Pre-filter in single precision (k_build_eval): an upper estimate `hi` and a lower estimate `lo` of the real-valued
+            // score R of each of this lane's feasible slots; exact <= R and exact > R - 1.5, so the tile's winner scores more
+            // than max(lo) - 1.5, and only slots with hi >= max(best so far, max(lo) - 1.5) can win or tie.  They alone load
+            // the 64-byte evaluation row and pay for the two exact divisions; values at the API limits make the error
+            // term large and simply keep every slot.
+            float hi[8];
+            float lmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t b = quarter + 4u * i;
+                const bool f = (bits >> b) & 1u;
+                const float4 h = f ? __ldg(hint + (size_t)k * BP_TILE + wq * 32 + b) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float tc = rcf * h.y, tm = rmf * h.z;
+                const float est = 0.5f * (h.x - tc - tm);
+                const float err = 2e-6f * (h.w + fabsf(tc) + fabsf(tm)) + 2e-3f;
+                hi[i] = f ? est + err : -INFINITY;
+                lmax = fmaxf(lmax, f ? est - err : -INFINITY);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+            const float floor_t = lmax - 1.5f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t b = quarter + 4u * i;
+                if (!((bits >> b) & 1u)) continue;              // not feasible
+                if (hi[i] < floor_t) continue;                  // cannot reach the tile's winner
+                if (bidx >= 0 && hi[i] < (float)best) continue; // cannot reach the best so far (merged or this lane's)
                 const NodeEval e = ev[(size_t)k * BP_TILE + wq * 32 + b];
                 const int64_t sc = least_alloc_score(e, rc, rm);
                 if (sc > best || (sc == best && e.idx < bidx)) {
@@ -1180,7 +1217,7 @@ void bitpar_release(BitparIndex& ix) {
     void* ptrs[] = {ix.sortedC, ix.sortedM, ix.gposC, ix.gposM, ix.ord_prio,
                     ix.ord_idx, ix.splC,  ix.splM,  ix.blobP,    ix.pod_ranks, ix.tail_list,
                     ix.rk_hist, ix.rk_spl_v, ix.rk_spl_i, ix.rk_bkt, ix.rk_loc, ix.rk_perm, ix.rec_s,
-                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.blobL, ix.live, ix.cursor};
+                    ix.blobR,   ix.rank,   ix.tile_sorted, ix.ordL_s0, ix.ordL_idx, ix.evalL, ix.hintL, ix.blobL, ix.live, ix.cursor};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ix.trace) {
@@ -1218,6 +1255,7 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cu
         if ((e = regrow(ix.ordL_s0, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.ordL_idx, cap)) != cudaSuccess) return e;
         if ((e = regrow(ix.evalL, cap)) != cudaSuccess) return e;
+        if ((e = regrow(ix.hintL, cap)) != cudaSuccess) return e;
         ix.cap_nodes = cap;
     }
     uint32_t stride = 1;
@@ -1289,7 +1327,7 @@ cudaError_t bitpar_build(BitparIndex& ix, const NodeTable& nt, int64_t* prio, cu
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // KS_SCORE_LEAST_ALLOCATED: the same flat index in descending order of the score bound + per-slot evaluation rows
     k_build_tile<<<layP.nt, 288, 0, st>>>(nt, ix.gposC, ix.gposM, ix.ordL_idx, ix.blobL, layP);
-    k_build_eval<<<(Nord + 255) / 256, 256, 0, st>>>(nt, ix.ordL_idx, Nord, ix.evalL);
+    k_build_eval<<<(Nord + 255) / 256, 256, 0, st>>>(nt, ix.ordL_idx, Nord, ix.evalL, ix.hintL);
     g_launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ix.lay = lay;
@@ -1331,6 +1369,9 @@ cudaError_t bitpar_prepare(BitparIndex& ix, uint32_t P) {
         if ((e = set_smem_attr<2>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<4>()) != cudaSuccess) return e;
         if ((e = set_smem_attr<8>()) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_pod_ranks, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      RANK_SPLITTERS * 2 * (int)sizeof(int64_t))) != cudaSuccess)
+            return e;
         const char* tr = getenv("KS_TRACE");
         if (tr && tr[0] == '1') { // one trace buffer per device: the most recently prepared index owns the stamps
             if ((e = cudaMalloc(&ix.trace, BP_TRACE_WORDS * sizeof(unsigned long long))) != cudaSuccess) return e;
@@ -1359,8 +1400,9 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const int sms = ix.sms;
     if (ix.trace)
         if ((e = cudaMemsetAsync(ix.trace, 0, BP_TRACE_WORDS * sizeof(unsigned long long), L.stream)) != cudaSuccess) return e;
-    // 6 CTAs x 32 KB of splitters per SM; two pods per thread and pass once every thread slot of the chip is taken
-    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 6, ((uint64_t)P + 255) / 256);
+    // one 1024-thread CTA per SM (splitters in dynamic shared memory); two pods per thread and pass once P > #SMs * 1024
+    const uint32_t rank_grid = (uint32_t)std::min<uint64_t>((uint64_t)sms, ((uint64_t)P + RANK_THREADS - 1) / RANK_THREADS);
+    const size_t rank_smem = (size_t)ix.n_spl * 2 * sizeof(int64_t);
     const bool want_bind = L.ov.node_idx || L.ov.score;
     const bool overlap_bind = before_mask == nullptr && after_mask == nullptr;
     // How the mask kernel (persistent, one CTA per SM, SM-bound: every SM it does not get costs it 1/#SMs) and the argmax
@@ -1384,7 +1426,7 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
     const uint64_t F = (uint64_t)n_groups * ix.lay_r.ncb;
     const uint32_t warps = (uint32_t)threads / 32;
     const uint32_t mask_grid = (uint32_t)std::min<uint64_t>((uint64_t)mask_sms, (F + warps - 1) / warps);
-    k_pod_ranks<<<rank_grid, 256, 0, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
+    k_pod_ranks<<<rank_grid, RANK_THREADS, rank_smem, L.stream>>>(L.pv, ix.sortedC, ix.sortedM, ix.N, ix.splC, ix.splM, ix.n_spl, ix.spl_stride,
                                                  ix.pod_ranks, (need_mask_pass && ix.lay.ncb > 1) ? L.ov.cnt : nullptr, ix.W,
                                                  need_mask_pass ? ix.rec_s : nullptr, ix.cursor, need_mask_pass ? ix.lay_r.ncb : 0u);
     g_launches++;
@@ -1401,7 +1443,7 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if (L.policy == KS_SCORE_LEAST_ALLOCATED) {
             const uint32_t wpc = at / 32; // one warp per pod
             const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * (2048 / at), ((uint64_t)P + wpc - 1) / wpc);
-            k_least_alloc<W><<<grid, at, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live, ix.N);
+            k_least_alloc<W><<<grid, at, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.hintL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live, ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         } else {

@@ -60,7 +60,7 @@ struct BitparIndex {
     uint32_t* gposM = nullptr;
     int64_t* ord_prio = nullptr; // nodes in descending priority order (ties by node index), padded to a tile
     int32_t* ord_idx = nullptr;
-    int64_t* splC = nullptr;     // every `spl_stride`-th element of sortedC / sortedM (<= 1024 splitters)
+    int64_t* splC = nullptr;     // every `spl_stride`-th element of sortedC / sortedM (<= RANK_SPLITTERS = 8192 splitters)
     int64_t* splM = nullptr;
     uint8_t* blobP = nullptr;    // one blob of layP.blob_bytes: priority order (tile k = priority ranks 256k..),
                                  // read through L1/L2 by k_first_fit_bp
@@ -69,6 +69,7 @@ struct BitparIndex {
     int64_t* ordL_s0 = nullptr;    // KS_SCORE_LEAST_ALLOCATED: score bound of every node in descending order (ties by index)
     int32_t* ordL_idx = nullptr;
     struct NodeEval* evalL = nullptr; // per slot of that order: what the exact score needs
+    float4* hintL = nullptr;          // per slot of that order: single-precision score model (pre-filter of k_least_alloc)
     uint8_t* blobL = nullptr;      // flat index (layP) in that order
     unsigned long long* live = nullptr; // [KS_MAX_LABEL_WORDS] label bits carried by at least one node
     uint4* rec_s = nullptr;        // rows kernel: {threshold_cpu, threshold_mem, pod index, selector columns} per sorted pod

@@ -117,6 +117,38 @@ def test_random_clusters_least_allocated(ks, orc, path, P, N, keys):
         assert auto.path == ("bitpar" if P * N >= 1 << 24 else "direct") and np.array_equal(auto.node_idx, r.node_idx)
 
 
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("seed,P,N", [(11, 3000, 6000), (12, 700, 40_000)])
+def test_least_allocated_near_ties(ks, orc, path, seed, P, N):
+    """Homogeneous clusters: thousands of nodes whose LeastAllocated scores lie within a point or two of each other
+    (and many exact ties), so the single-precision pre-filter of k_least_alloc keeps whole tiles of candidates and the
+    winner is decided by the exact integer score and then the lowest node index - vs the oracle, every pod."""
+    rng = np.random.default_rng(seed)
+    ac = rng.choice(np.array([64000, 64000, 64001, 63999, 32000], np.int64), N)
+    am = rng.choice(np.array([1 << 38, (1 << 38) + 4096, 1 << 37], np.int64), N)
+    lab = np.zeros((N, 1), np.uint64)
+    lab[:, 0] = rng.choice(np.array([1, 3, 7], np.uint64), N)
+    B = 2 * N  # bound pods leave every node about half full, within a percent of each other
+    bn = np.repeat(np.arange(N, dtype=np.int32), 2)
+    bc = (ac[bn] // 4 + rng.integers(0, 400, B)).astype(np.int64)
+    bm = (am[bn] // 4 + rng.integers(0, 1 << 30, B)).astype(np.int64)
+    rc = rng.integers(0, 16000, P).astype(np.int64)
+    rm = rng.integers(0, 1 << 35, P).astype(np.int64)
+    sel = np.zeros((P, 1), np.uint64)
+    sel[:, 0] = rng.choice(np.array([0, 1, 2, 4], np.uint64), P)
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes(ac, am, lab)
+        snap.set_bound(bn, bc, bm)
+        ofc, ofm = orc.free_reduce(ac, am, bn, bc, bm)
+        r = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, flags=PATHS[path], want_mask=False)
+        o = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=1, want_mask=False)
+        assert r.path == path
+        assert np.array_equal(r.score, o[1]), f"near ties {path}: score"
+        assert np.array_equal(r.node_idx, o[0]), f"near ties {path}: node_idx (tie-break by node index)"
+        assert np.array_equal(r.feasible_cnt, o[2])
+        assert len(np.unique(r.score[r.node_idx >= 0])) <= 60  # the scores really are bunched
+
+
 def test_reason_codes_match_oracle(ks, orc):
     cl = ks.synth.make(200, 777, seed=31, bound_per_node=4)
     snap, (rc, rm, sel) = _snapshot(ks, cl)

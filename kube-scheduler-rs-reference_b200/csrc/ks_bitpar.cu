@@ -988,10 +988,15 @@ struct NodeEval { // one row per slot of the bound order
     int32_t pad;
 };
 
-// Single-precision view of the same row for the pre-filter of k_least_alloc: the real-valued score of (pod, node) is
-//   R = (Sc - rc * Ac + Sm - rm * Am) / 2,  Sc = fc * 100 / ac, Ac = 100 / ac (both 0 when ac <= 0), likewise for memory,
-// and the exact score (two floors, then a halving floor; feasible cells have fc >= rc, fm >= rm) lies in (R - 1.5, R].
-// x = Sc + Sm, y = Ac, z = Am, w = |Sc| + |Sm| (magnitude for the rounding-error bound).
+// Single-precision view of the same row: in the common case it gives k_least_alloc the EXACT integer score of a cell
+// without the 64-byte row and the two 64-bit divisions.  x = (float)free_cpu and y = (float)alloc_cpu when they are
+// exactly representable (|free_cpu| < 2^24, 0 < alloc_cpu < 2^24; y = +inf for alloc_cpu <= 0, where the cpu term is 0
+// by definition; NaN otherwise): for a request that is exact too, t = (x - r) * 100 is exact while t < 2^24, and the
+// floor of the correctly rounded quotient t / y of two such integers IS floor((free_cpu - r) * 100 / alloc_cpu) (a
+// quotient that is not an integer is at least 1 / y away from one, more than the rounding error t / y * 2^-24 for
+// t < 2^24).  Memory is in bytes and does not fit: z = free_mem * 100 / alloc_mem and w = 100 / alloc_mem (both 0 for
+// alloc_mem <= 0) give the real-valued quotient z - r * w with a relative error of a few 2^-24; its floor is known
+// whenever no integer lies within the error bound (the kernel uses 2e-6 * (|z| + |r * w|) + 1e-3, > 8 x the worst case).
 __global__ void __launch_bounds__(256)
     k_build_eval(NodeTable nt, const int32_t* __restrict__ ordL_idx, uint32_t Nord, NodeEval* __restrict__ ev,
                  float4* __restrict__ hint) {
@@ -1013,8 +1018,11 @@ __global__ void __launch_bounds__(256)
     e.inv_ac = e.ac > 0 ? 1.0 / (double)e.ac : 0.0;
     e.inv_am = e.am > 0 ? 1.0 / (double)e.am : 0.0;
     ev[s] = e;
-    const double Sc = e.ac > 0 ? (double)e.fc * 100.0 * e.inv_ac : 0.0, Sm = e.am > 0 ? (double)e.fm * 100.0 * e.inv_am : 0.0;
-    hint[s] = make_float4((float)(Sc + Sm), (float)(100.0 * e.inv_ac), (float)(100.0 * e.inv_am), (float)(fabs(Sc) + fabs(Sm)));
+    const float qnan = __int_as_float(0x7fc00000);
+    const bool fc_exact = e.fc > -(1ll << 24) && e.fc < (1ll << 24);
+    const double Sm = e.am > 0 ? (double)e.fm * 100.0 * e.inv_am : 0.0;
+    hint[s] = make_float4(fc_exact ? (float)e.fc : qnan, e.ac <= 0 ? INFINITY : (e.ac < (1ll << 24) ? (float)e.ac : qnan), (float)Sm,
+                          (float)(100.0 * e.inv_am));
 }
 
 // floor(x / d) for x >= 0, d > 0 (both < 2^63): double estimate, then exact correction in integers
@@ -1053,8 +1061,8 @@ constexpr uint32_t LA_FIRST_WINDOW = 8;  // tiles of the first window (then 32 p
 template <int W>
 __global__ void __launch_bounds__(256)
     k_least_alloc(const uint8_t* __restrict__ blobL, BitparLayout lay, const NodeEval* __restrict__ ev,
-                  const float4* __restrict__ hint, const int64_t* __restrict__ ordL_s0, PodView pv, const uint2* __restrict__ rk, OutView ov, PeerOut po,
-                  const unsigned long long* __restrict__ live, uint32_t N) {
+                  const float4* __restrict__ hint, const int64_t* __restrict__ ordL_s0, const int32_t* __restrict__ ordL_idx, PodView pv,
+                  const uint2* __restrict__ rk, OutView ov, PeerOut po, const unsigned long long* __restrict__ live, uint32_t N) {
     const longlong2 amax = *reinterpret_cast<const longlong2*>(live + KS_MAX_LABEL_WORDS); // max allocatable cpu / memory
     __shared__ uint4 s_mask[LA_MAX_WARPS][32][2]; // per warp: the feasibility masks of the current window of tiles
     __shared__ int64_t s_top[LA_MAX_WARPS][32];   //           and the score bound of the first slot of each of them
@@ -1075,6 +1083,7 @@ __global__ void __launch_bounds__(256)
         }
         const int64_t rc = __ldg(pv.req_cpu + p), rm = __ldg(pv.req_mem + p);
         const float rcf = (float)rc, rmf = (float)rm;
+        const bool rc_exact = rc > -(1ll << 24) && rc < (1ll << 24); // (float)rc is rc
         const bool bounded = rc >= 0 && rm >= 0; // else the bound does not hold: no early exit
         // per-pod slack: floor((f-r)*100/a) <= floor(f*100/a) - floor(r*100/a) and a <= a_max, so every feasible cell
         // scores <= bound(n) - D with D = (rc*100/ac_max + rm*100/am_max) / 2
@@ -1116,39 +1125,56 @@ __global__ void __launch_bounds__(256)
                 }
                 // this lane's share of the tile's feasible slots: word wq, bit positions congruent to `quarter` mod 4
                 const uint32_t bits = reinterpret_cast<const uint32_t*>(&s_mask[wid][j][0])[wq] & (0x11111111u << quarter);
-                // Pre-filter in single precision (k_build_eval): an upper estimate `hi` and a lower estimate `lo` of the real-valued
-                // score R of each of this lane's feasible slots; exact <= R and exact > R - 1.5, so the tile's winner scores more
-                // than max(lo) - 1.5, and only slots with hi >= max(best so far, max(lo) - 1.5) can win or tie.  They alone load
-                // the 64-byte evaluation row and pay for the two exact divisions; values at the API limits make the error
-                // term large and simply keep every slot.
+                // Scores in single precision (k_build_eval): per feasible slot of this lane an interval [lo, hi] of integers that
+                // contains the exact score - lo == hi (the score is KNOWN) unless the memory quotient lies within its error bound of
+                // an integer, and [-inf, +inf] when the numbers leave the range in which the float arithmetic below is exact.  The
+                // tile's winner scores >= max(lo), so only slots with hi >= max(max(lo), best so far) can win or tie: they load the
+                // 4-byte node index (score known) or the 64-byte evaluation row for the exact 64-bit arithmetic (score not known).
                 float hi[8];
+                uint32_t known = 0; // bit i: lo == hi for this lane's i-th slot
                 float lmax = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const uint32_t b = quarter + 4u * i;
                     const bool f = (bits >> b) & 1u;
-                    const float4 h = f ? __ldg(hint + (size_t)k * BP_TILE + wq * 32 + b) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float tc = rcf * h.y, tm = rmf * h.z;
-                    const float est = 0.5f * (h.x - tc - tm);
-                    const float err = 2e-6f * (h.w + fabsf(tc) + fabsf(tm)) + 2e-3f;
-                    hi[i] = f ? est + err : -INFINITY;
-                    lmax = fmaxf(lmax, f ? est - err : -INFINITY);
+                    const float4 h = f ? __ldg(hint + (size_t)k * BP_TILE + wq * 32 + b) : make_float4(0.f, 1.f, 0.f, 0.f);
+                    const float x = (h.x - rcf) * 100.0f;           // exact while it is an integer below 2^24
+                    const float pc = floorf(__fdiv_rn(x, h.y));     // = floor((free_cpu - rc) * 100 / alloc_cpu); 0 for y = +inf
+                    const float tm = rmf * h.w, qm = h.z - tm;      // memory quotient, real-valued estimate
+                    const float em = 2e-6f * (fabsf(h.z) + fabsf(tm)) + 1e-3f;
+                    const float pm_lo = h.w == 0.f ? 0.f : floorf(qm - em), pm_hi = h.w == 0.f ? 0.f : floorf(qm + em);
+                    // every float sum below must be exact: integers under 2^23
+                    const bool ok = rc_exact && x >= 0.f && x < 16777216.f && pc < 4.0e6f && fabsf(qm) + em < 4.0e6f; // false for NaN
+                    const float lo = floorf((pc + pm_lo) * 0.5f);
+                    hi[i] = f ? (ok ? floorf((pc + pm_hi) * 0.5f) : INFINITY) : -INFINITY;
+                    if (f && ok) {
+                        lmax = fmaxf(lmax, lo);
+                        known |= (lo == hi[i] ? 1u : 0u) << i;
+                    }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
-                const float floor_t = lmax - 1.5f;
                 bool changed = false;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const uint32_t b = quarter + 4u * i;
                     if (!((bits >> b) & 1u)) continue;              // not feasible
-                    if (hi[i] < floor_t) continue;                  // cannot reach the tile's winner
+                    if (hi[i] < lmax) continue;                     // cannot reach the tile's winner
                     if (bidx >= 0 && hi[i] < (float)best) continue; // cannot reach the best so far (merged or this lane's)
-                    const NodeEval e = ev[(size_t)k * BP_TILE + wq * 32 + b];
-                    const int64_t sc = least_alloc_score(e, rc, rm);
-                    if (sc > best || (sc == best && e.idx < bidx)) {
+                    const size_t slot = (size_t)k * BP_TILE + wq * 32 + b;
+                    int64_t sc;
+                    int32_t ni;
+                    if ((known >> i) & 1u) {
+                        sc = (int64_t)hi[i];
+                        ni = __ldg(ordL_idx + slot);
+                    } else {
+                        const NodeEval e = ev[slot];
+                        sc = least_alloc_score(e, rc, rm);
+                        ni = e.idx;
+                    }
+                    if (sc > best || (sc == best && ni < bidx)) {
                         best = sc;
-                        bidx = e.idx;
+                        bidx = ni;
                         changed = true;
                     }
                 }
@@ -1484,7 +1510,8 @@ static cudaError_t select_w(BitparIndex& ix, SelectLaunch& L, cudaEvent_t before
         if (L.policy == KS_SCORE_LEAST_ALLOCATED) {
             const uint32_t wpc = at / 32; // one warp per pod
             const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * (2048 / at), ((uint64_t)P + wpc - 1) / wpc);
-            k_least_alloc<W><<<grid, at, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.hintL, ix.ordL_s0, L.pv, ix.pod_ranks, L.ov, L.po, ix.live, ix.N);
+            k_least_alloc<W><<<grid, at, 0, bs>>>(ix.blobL, ix.layP, ix.evalL, ix.hintL, ix.ordL_s0, ix.ordL_idx, L.pv, ix.pod_ranks, L.ov, L.po, ix.live,
+                                                  ix.N);
             g_launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         } else {

@@ -16,3 +16,4 @@ PY
 timeout 300 python -m pytest tests -m gpu -q -x > gpurun_out/m_pytest_all.log 2>&1
 echo "pytest all rc=$? $(tail -1 gpurun_out/m_pytest_all.log)"
 grep -E "FAILED|ERROR" gpurun_out/m_pytest_all.log | head -10
+timeout 60 python __graft_entry__.py smoke 2>&1 | tail -2

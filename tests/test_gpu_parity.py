@@ -149,6 +149,34 @@ def test_least_allocated_near_ties(ks, orc, path, seed, P, N):
         assert len(np.unique(r.score[r.node_idx >= 0])) <= 60  # the scores really are bunched
 
 
+@pytest.mark.parametrize("path", list(PATHS))
+def test_least_allocated_round_fills(ks, orc, path):
+    """Nodes filled to exact quarters of round capacities and round requests: the memory quotient (free - request) * 100 /
+    allocatable is often EXACTLY an integer, where k_least_alloc's single-precision estimate cannot know the floor and must
+    fall back to the 64-bit arithmetic of the evaluation row; every node is feasible for most pods and most scores tie."""
+    rng = np.random.default_rng(5)
+    N, P = 9000, 2500
+    ac = rng.choice(np.array([4000, 8000, 16000], np.int64), N)
+    am = rng.choice(np.array([16, 32, 64], np.int64) << 30, N)
+    lab = np.zeros((N, 1), np.uint64)
+    bn = np.arange(N, dtype=np.int32)
+    bc = (ac // 4 * rng.integers(0, 4, N)).astype(np.int64)
+    bm = (am // 4 * rng.integers(0, 4, N)).astype(np.int64)
+    rc = rng.choice(np.array([0, 250, 1000], np.int64), P)
+    rm = rng.choice(np.array([0, 1 << 30, 1 << 32], np.int64), P)
+    sel = np.zeros((P, 1), np.uint64)
+    with ks.Snapshot(0) as snap:
+        snap.set_nodes(ac, am, lab)
+        snap.set_bound(bn, bc, bm)
+        ofc, ofm = orc.free_reduce(ac, am, bn, bc, bm)
+        r = snap.select(rc, rm, sel, policy=ks.KS_SCORE_LEAST_ALLOCATED, flags=PATHS[path], want_mask=False)
+        o = orc.run_packed(ofc, ofm, ac, am, lab, rc, rm, sel, policy=1, want_mask=False)
+        assert r.path == path
+        assert np.array_equal(r.score, o[1]), f"round fills {path}: score"
+        assert np.array_equal(r.node_idx, o[0]), f"round fills {path}: node_idx"
+        assert np.array_equal(r.feasible_cnt, o[2])
+
+
 def test_reason_codes_match_oracle(ks, orc):
     cl = ks.synth.make(200, 777, seed=31, bound_per_node=4)
     snap, (rc, rm, sel) = _snapshot(ks, cl)

@@ -262,6 +262,8 @@ struct ksh_context {
     std::vector<int64_t> tmp_cpu, tmp_mem;
     std::vector<uint64_t> tmp_hash;
     std::vector<uint32_t> tmp_len;
+    std::vector<int64_t> pk_cpu, pk_mem; // packed form of the last ksh_select_nodes batch
+    std::vector<uint64_t> pk_sel;
     bool dirty = true; // device snapshot must be re-uploaded
     // one lock per context: every ksh_* entry that takes a context holds it for the whole call (entries call each other)
     mutable std::recursive_mutex mu;
@@ -682,20 +684,45 @@ static inline int32_t node_index_of(const ksh_context* c, const char* name) {
 
 // Every selector pair of the batch that some node carries gets a dictionary bit (first occurrence first).
 // The scan runs on all host threads; bits are assigned in pod order afterwards.
-static int grow_dictionary(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
-    std::vector<std::vector<uint32_t>> need(host_threads());
-    parallel_ranges(n, 4096, [&](unsigned t, uint64_t b, uint64_t e) {
-        std::vector<uint32_t>& out = need[t];
+// ---- packing a batch of pending pods (src/util.rs:54-75 + the selector side of src/predicates.rs:45-61) ----
+// One pass over the objects does all the string work: request totals (quantity parse) and ONE interner lookup per selector
+// entry, whose pair ids are parked per thread in array order.  Then the dictionary grows (serial, tiny), and a second pass over
+// the same ranges turns the parked pair ids into selector bits without touching a string again.
+constexpr uint64_t PACK_MIN_PER_THREAD = 2048; // both passes must cut [0,n) into the same ranges
+
+struct PackScratch {
+    std::vector<std::vector<int32_t>> pids;  // per thread: pair id (-1 = unknown pair) of every selector entry of its range, in order
+    std::vector<std::vector<uint32_t>> need; // per thread: known pairs some node carries that have no dictionary bit yet
+};
+
+static int pack_scan(const ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* req_cpu, int64_t* req_mem, PackScratch& ps) {
+    ps.pids.assign(host_threads(), {});
+    ps.need.assign(host_threads(), {});
+    std::vector<RangeError> errs(host_threads());
+    parallel_ranges(n, PACK_MIN_PER_THREAD, [&](unsigned t, uint64_t b, uint64_t e) {
+        std::vector<int32_t>& pids = ps.pids[t];
+        std::vector<uint32_t>& need = ps.need[t];
         for (uint64_t p = b; p < e; p++) {
             const ks_pod_obj& pod = pods[p];
+            const int rc = total_pod_resources(&pod, &req_cpu[p], &req_mem[p], &errs[t].msg);
+            if (rc) {
+                errs[t].rc = rc;
+                return;
+            }
             if (!(pod.has_spec && pod.has_node_selector)) continue;
             for (uint32_t i = 0; i < pod.n_selector; i++) {
                 const int64_t pid = c->pairs.find(nz(pod.selector[i].key), '\0', nz(pod.selector[i].val));
+                pids.push_back((int32_t)pid);
                 if (pid < 0 || c->pair_bit[(size_t)pid] >= 0 || c->pair_refcnt[(size_t)pid] == 0) continue; // unknown pair, known bit, or absent everywhere
-                if (out.empty() || out.back() != (uint32_t)pid) out.push_back((uint32_t)pid);
+                if (need.empty() || need.back() != (uint32_t)pid) need.push_back((uint32_t)pid);
             }
         }
     });
+    return first_error(errs);
+}
+
+static int grow_dictionary(ksh_context* c, const PackScratch& ps, const ks_pod_obj* pods, uint64_t n) {
+    const std::vector<std::vector<uint32_t>>& need = ps.need;
     // Room check first.  The dictionary only has to cover the pairs THIS batch names (node columns are re-uploaded
     // whenever it changes), so when the pairs accumulated over the context's lifetime leave no room - e.g. hostname
     // selectors across more than 511 nodes over time - it is rebuilt from the current batch instead of failing.
@@ -742,30 +769,24 @@ static int grow_dictionary(ksh_context* c, const ks_pod_obj* pods, uint64_t n) {
     return KS_OK;
 }
 
-// request totals and selector words of a batch under the current dictionary (grow_dictionary has run)
-static int pack_rows(const ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* req_cpu, int64_t* req_mem,
-                     uint64_t* sel, uint32_t stride) {
+// selector words of the batch under the current dictionary, from the pair ids parked by pack_scan (same ranges, same order)
+static void pack_selectors(const ksh_context* c, const ks_pod_obj* pods, uint64_t n, const PackScratch& ps, uint64_t* sel,
+                           uint32_t stride) {
     const uint32_t absent = c->W * 64 - 1;
-    std::vector<RangeError> errs(host_threads());
-    parallel_ranges(n, 2048, [&](unsigned t, uint64_t b, uint64_t e) {
+    parallel_ranges(n, PACK_MIN_PER_THREAD, [&](unsigned t, uint64_t b, uint64_t e) {
+        const int32_t* pid = ps.pids[t].data();
         for (uint64_t p = b; p < e; p++) {
-            const int rc = total_pod_resources(&pods[p], &req_cpu[p], &req_mem[p], &errs[t].msg);
-            if (rc) {
-                errs[t].rc = rc;
-                return;
-            }
             uint64_t* row = sel + p * stride;
             for (uint32_t w = 0; w < stride; w++) row[w] = 0;
-            if (pods[p].has_spec && pods[p].has_node_selector)
-                for (uint32_t i = 0; i < pods[p].n_selector; i++) {
-                    const int64_t pid = c->pairs.find(nz(pods[p].selector[i].key), '\0', nz(pods[p].selector[i].val));
-                    const int32_t b_ = pid < 0 ? -1 : c->pair_bit[(size_t)pid];
-                    const uint32_t bit = b_ < 0 ? absent : (uint32_t)b_; // a pair no node carries: never-set bit
-                    row[bit >> 6] |= 1ull << (bit & 63);
-                }
+            if (!(pods[p].has_spec && pods[p].has_node_selector)) continue;
+            for (uint32_t i = 0; i < pods[p].n_selector; i++) {
+                const int32_t id = *pid++;
+                const int32_t b_ = id < 0 ? -1 : c->pair_bit[(size_t)id];
+                const uint32_t bit = b_ < 0 ? absent : (uint32_t)b_; // a pair no node carries: never-set bit
+                row[bit >> 6] |= 1ull << (bit & 63);
+            }
         }
     });
-    return first_error(errs);
 }
 
 extern "C" {
@@ -1085,24 +1106,28 @@ int ksh_pack_pods(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int64_t* r
                   uint64_t* sel, uint32_t stride) try {
     if (!c || (n && (!pods || !req_cpu || !req_mem || !sel))) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
-    int rc = grow_dictionary(c, pods, n);
+    PackScratch ps;
+    int rc = pack_scan(c, pods, n, req_cpu, req_mem, ps);
+    if (rc) return rc;
+    rc = grow_dictionary(c, ps, pods, n);
     if (rc) return rc;
     if (stride < c->W) return fail(KS_ERR_INVALID, "sel_stride_words smaller than the dictionary's word count");
-    rc = pack_rows(c, pods, n, req_cpu, req_mem, sel, stride);
-    if (rc) return rc;
+    pack_selectors(c, pods, n, ps, sel, stride);
     return (int)c->W;
 }
 KSH_CATCH
 
 static int pack_and_upload(ksh_context* c, const ks_pod_obj* pods, uint64_t n, std::vector<int64_t>& rc_, std::vector<int64_t>& rm_,
                            std::vector<uint64_t>& sel) {
-    int rc = grow_dictionary(c, pods, n);
-    if (rc) return rc;
     rc_.resize(n);
     rm_.resize(n);
-    sel.resize((size_t)n * c->W);
-    rc = pack_rows(c, pods, n, rc_.data(), rm_.data(), sel.data(), c->W);
+    PackScratch ps;
+    int rc = pack_scan(c, pods, n, rc_.data(), rm_.data(), ps);
     if (rc) return rc;
+    rc = grow_dictionary(c, ps, pods, n);
+    if (rc) return rc;
+    sel.resize((size_t)n * c->W);
+    pack_selectors(c, pods, n, ps, sel.data(), c->W);
     return upload(c);
 }
 
@@ -1123,8 +1148,9 @@ int ksh_select_nodes(ksh_context* c, const ks_pod_obj* pods, uint64_t n, int pol
     if (!c || (n && !pods)) return fail(KS_ERR_INVALID, "NULL argument");
     std::lock_guard<std::recursive_mutex> lk(c->mu);
     if (n == 0) return KS_OK;
-    std::vector<int64_t> rc_, rm_;
-    std::vector<uint64_t> sel;
+    // packed form of the batch: kept in the context between calls (24 bytes per pod; fresh pages cost more than the packing)
+    std::vector<int64_t>&rc_ = c->pk_cpu, &rm_ = c->pk_mem;
+    std::vector<uint64_t>& sel = c->pk_sel;
     int rc = pack_and_upload(c, pods, n, rc_, rm_, sel);
     if (rc) return rc;
     ks_pods kp{n, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};

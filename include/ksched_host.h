@@ -90,6 +90,10 @@ int ksh_pack_pods(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int
                   uint64_t* sel, uint32_t sel_stride_words);
 
 int ksh_check_node_validity(ksh_context* ctx, const ks_pod_obj* pod, uint32_t node_idx);
+/* select_node_for_pod for a whole batch (src/main.rs:51-71 with the argmax over ALL feasible nodes instead of <= 5 draws):
+ * out_node_idx[p] < 0 = None.  A pod whose quantities do not parse fails the call before anything is evaluated (status +
+ * ks_last_error(), the reference panics there: src/util.rs:65,68).  The context keeps the packed form of the last batch
+ * (24 + 8W bytes per pod) until it is destroyed, so that repeated calls do not fault in fresh pages. */
 int ksh_select_nodes(ksh_context* ctx, const ks_pod_obj* pods, uint64_t n_pods, int policy, int32_t* out_node_idx,
                      int64_t* out_score, uint32_t* out_feasible_cnt);
 

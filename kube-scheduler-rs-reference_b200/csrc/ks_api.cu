@@ -218,8 +218,14 @@ int ks_snapshot_set_nodes(ks_snapshot* s, uint32_t n_nodes, uint32_t label_words
     s->derived_dirty = true;
     s->version++;
     if (Npad == 0) return KS_OK;
-    std::vector<int64_t> h(Npad);
-    std::vector<uint64_t> hl((size_t)Npad * label_words, 0);
+    std::vector<int64_t> h;
+    std::vector<uint64_t> hl;
+    try { // no exception crosses the ABI
+        h.resize(Npad);
+        hl.assign((size_t)Npad * label_words, 0);
+    } catch (...) {
+        return fail(KS_ERR_NOMEM, "out of host memory staging %u nodes", n_nodes);
+    }
     const size_t nb = (size_t)Npad * 8;
     CU_TRY(s->alloc_cpu.ensure(nb));
     CU_TRY(s->alloc_mem.ensure(nb));
@@ -940,52 +946,56 @@ int ks_stream_bind(ks_snapshot* s, const ks_pods* pods, int policy, int32_t* out
         s->last_path = "stream_batch";
         return KS_OK;
     }
-    std::vector<uint64_t> pending(n);
-    for (uint64_t i = 0; i < n; i++) {
-        pending[i] = i;
-        out_node_idx[i] = -1;
-        if (out_score) out_score[i] = 0;
-    }
-    std::vector<int64_t> rc_, rm_, score;
-    std::vector<uint64_t> sel;
-    std::vector<int32_t> idx;
-    std::vector<uint8_t> acc;
-    uint32_t rounds = 0;
-    while (!pending.empty() && rounds <= n + 1) {
-        const uint64_t m = pending.size();
-        rc_.resize(m);
-        rm_.resize(m);
-        sel.resize(m * W);
-        idx.resize(m);
-        score.resize(m);
-        acc.resize(m);
-        for (uint64_t k = 0; k < m; k++) {
-            const uint64_t p = pending[k];
-            rc_[k] = pods->req_cpu[p];
-            rm_[k] = pods->req_mem[p];
-            for (uint32_t w = 0; w < W; w++) sel[k * W + w] = pods->sel[p * W + w];
+    try { // host-driven loop (large batches, A/B): its vectors must not throw across the ABI
+        std::vector<uint64_t> pending(n);
+        for (uint64_t i = 0; i < n; i++) {
+            pending[i] = i;
+            out_node_idx[i] = -1;
+            if (out_score) out_score[i] = 0;
         }
-        ks_pods kp{m, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
-        ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr, nullptr};
-        rc = ks_select(s, &kp, policy, KS_SELECT_FORCE_DIRECT, &kb, nullptr); // claims against the current free[]
-        if (rc) return rc;
-        rc = ks_snapshot_commit_claims(s, m, idx.data(), rc_.data(), rm_.data(), acc.data());
-        if (rc) return rc;
-        std::vector<uint64_t> next;
-        for (uint64_t k = 0; k < m; k++) {
-            if (idx[k] < 0) continue; // no feasible node: NoNodeFound (src/main.rs:116-118)
-            if (acc[k]) {
-                out_node_idx[pending[k]] = idx[k];
-                if (out_score) out_score[pending[k]] = score[k];
-            } else {
-                next.push_back(pending[k]); // lost the node to an earlier pod of the batch: retry
+        std::vector<int64_t> rc_, rm_, score;
+        std::vector<uint64_t> sel;
+        std::vector<int32_t> idx;
+        std::vector<uint8_t> acc;
+        uint32_t rounds = 0;
+        while (!pending.empty() && rounds <= n + 1) {
+            const uint64_t m = pending.size();
+            rc_.resize(m);
+            rm_.resize(m);
+            sel.resize(m * W);
+            idx.resize(m);
+            score.resize(m);
+            acc.resize(m);
+            for (uint64_t k = 0; k < m; k++) {
+                const uint64_t p = pending[k];
+                rc_[k] = pods->req_cpu[p];
+                rm_[k] = pods->req_mem[p];
+                for (uint32_t w = 0; w < W; w++) sel[k * W + w] = pods->sel[p * W + w];
             }
+            ks_pods kp{m, rc_.data(), rm_.data(), sel.data(), KS_MEM_HOST};
+            ks_bindings kb{idx.data(), score.data(), nullptr, KS_MEM_HOST, nullptr, 0, KS_MEM_HOST, nullptr, nullptr};
+            rc = ks_select(s, &kp, policy, KS_SELECT_FORCE_DIRECT, &kb, nullptr); // claims against the current free[]
+            if (rc) return rc;
+            rc = ks_snapshot_commit_claims(s, m, idx.data(), rc_.data(), rm_.data(), acc.data());
+            if (rc) return rc;
+            std::vector<uint64_t> next;
+            for (uint64_t k = 0; k < m; k++) {
+                if (idx[k] < 0) continue; // no feasible node: NoNodeFound (src/main.rs:116-118)
+                if (acc[k]) {
+                    out_node_idx[pending[k]] = idx[k];
+                    if (out_score) out_score[pending[k]] = score[k];
+                } else {
+                    next.push_back(pending[k]); // lost the node to an earlier pod of the batch: retry
+                }
+            }
+            pending.swap(next);
+            rounds++;
         }
-        pending.swap(next);
-        rounds++;
+        if (out_rounds) *out_rounds = rounds;
+        return KS_OK;
+    } catch (...) {
+        return fail(KS_ERR_NOMEM, "out of host memory in ks_stream_bind");
     }
-    if (out_rounds) *out_rounds = rounds;
-    return KS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- async streaming
@@ -1009,6 +1019,7 @@ struct ks_stream {
     std::deque<StreamDone> out;
     uint64_t submitted = 0, finished = 0, batches = 0, rounds = 0, max_seen = 0;
     bool stop = false;
+    bool dead = false; // the dispatcher thread could not start working (out of memory)
     int error = KS_OK;
     std::thread worker;
 };
@@ -1017,6 +1028,20 @@ static void stream_worker(ks_stream* q) {
     std::vector<int64_t> rc, rm, score;
     std::vector<uint64_t> sel, tickets;
     std::vector<int32_t> idx;
+    try { // every per-batch resize below stays within these capacities: the loop itself never allocates
+        rc.reserve(q->max_batch);
+        rm.reserve(q->max_batch);
+        score.reserve(q->max_batch);
+        idx.reserve(q->max_batch);
+        tickets.reserve(q->max_batch);
+        sel.reserve((size_t)q->max_batch * q->W);
+    } catch (...) { // no dispatcher: submissions are answered with the error code by ks_stream_poll / ks_stream_flush
+        std::lock_guard<std::mutex> lk(q->mu);
+        q->error = KS_ERR_NOMEM;
+        q->dead = true;
+        q->cv_idle.notify_all();
+        return;
+    }
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(q->mu);
@@ -1045,7 +1070,11 @@ static void stream_worker(ks_stream* q) {
         {
             std::lock_guard<std::mutex> lk(q->mu);
             if (e) q->error = e;
-            for (size_t k = 0; k < m; k++) q->out.push_back(StreamDone{tickets[k], e ? -1 : idx[k], e ? 0 : score[k]});
+            try {
+                for (size_t k = 0; k < m; k++) q->out.push_back(StreamDone{tickets[k], e ? -1 : idx[k], e ? 0 : score[k]});
+            } catch (...) { // results that could not be queued are lost; the poller gets the error code
+                q->error = KS_ERR_NOMEM;
+            }
             q->finished += m;
             q->batches++;
             q->rounds += rounds;
@@ -1120,7 +1149,8 @@ int ks_stream_poll(ks_stream* q, uint64_t max, uint64_t* out_ticket, int32_t* ou
 int ks_stream_flush(ks_stream* q) {
     if (!q) return fail(KS_ERR_INVALID, "NULL argument");
     std::unique_lock<std::mutex> lk(q->mu);
-    q->cv_idle.wait(lk, [&] { return q->finished == q->submitted; });
+    q->cv_idle.wait(lk, [&] { return q->dead || q->finished == q->submitted; });
+    if (q->dead) return fail(KS_ERR_NOMEM, "the stream's dispatcher thread is not running (out of host memory)");
     return KS_OK;
 }
 

@@ -682,12 +682,11 @@ static inline int32_t node_index_of(const ksh_context* c, const char* name) {
     return id < 0 ? -1 : c->nameid2idx[(size_t)id];
 }
 
-// Every selector pair of the batch that some node carries gets a dictionary bit (first occurrence first).
-// The scan runs on all host threads; bits are assigned in pod order afterwards.
 // ---- packing a batch of pending pods (src/util.rs:54-75 + the selector side of src/predicates.rs:45-61) ----
 // One pass over the objects does all the string work: request totals (quantity parse) and ONE interner lookup per selector
 // entry, whose pair ids are parked per thread in array order.  Then the dictionary grows (serial, tiny), and a second pass over
-// the same ranges turns the parked pair ids into selector bits without touching a string again.
+// the same ranges turns the parked pair ids into selector bits without touching a string again.  Every selector pair of the
+// batch that some node carries gets a dictionary bit, first occurrence (in pod order) first, whatever the thread count.
 constexpr uint64_t PACK_MIN_PER_THREAD = 2048; // both passes must cut [0,n) into the same ranges
 
 struct PackScratch {
